@@ -1,0 +1,200 @@
+/*
+ * sxcross.h -- C ABI of libsxcross, the B200 (sm_100a) network-crossover hot path.
+ *
+ * This is the drop-in boundary.  The reference (wcwj0147/smart-crossover) is pure
+ * Python; the arithmetic of its hot path runs inside NumPy / SciPy calls made from
+ * `smart_crossover/network_methods/{net_manager,tree_BI,algorithms}.py`.  Each entry
+ * point below replaces one of those call sites (cited as file:line relative to
+ * /root/reference/src/smart_crossover/) and is what a ctypes binding inside the
+ * reference's managers would bind.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++ or torch types.
+ *  - Every function returns 0 (SX_OK) or a negative SX_ERR_* code; nothing throws.
+ *  - Pointers are DEVICE pointers owned by the caller unless the parameter name ends
+ *    in `_h` (host pointer).  No hidden allocation: `sx_*_workspace_bytes` reports the
+ *    scratch a call needs and the caller passes `ws` / `ws_bytes`.
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous with respect
+ *    to the host and ordered by that stream, except the `_h` entry points, which
+ *    synchronise the stream before returning.
+ *  - Reals are IEEE fp64, computed without fast-math or FMA contraction.  Arc ids are
+ *    uint32 inside the sort (n < 2^32) and int64 at the boundary.
+ *  - OT arc id k = i * D + j; OT nodes: sources 0..S-1, sinks S..S+D-1
+ *    (formats.py:156-160, net_manager.py:366).  Arc lists use tail/head int32 arrays.
+ */
+#ifndef SXCROSS_H_
+#define SXCROSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SX_API __attribute__((visibility("default")))
+#else
+#define SX_API
+#endif
+
+#define SX_OK                   0
+#define SX_ERR_INVALID         -1   /* bad argument (null pointer, negative size, ...) */
+#define SX_ERR_CUDA            -2   /* a CUDA runtime call failed; see sx_last_cuda_error() */
+#define SX_ERR_WORKSPACE       -3   /* ws_bytes smaller than sx_*_workspace_bytes() */
+#define SX_ERR_TOO_LARGE       -4   /* n >= 2^32 arcs in a sort, or N >= 2^31 nodes */
+#define SX_ERR_NOT_SPANNING    -5   /* sx_tree_potentials: arcs are not a spanning tree */
+#define SX_ERR_UNALIGNED       -6   /* TMA path needs 16-byte aligned base and even ld */
+#define SX_ERR_NO_DEVICE       -7   /* no sm_100 device / driver entry point missing */
+
+#define SX_ABI_VERSION 1
+
+/* Endpoint convention of sx_tree_potentials (which end of an arc carries +1 in A). */
+#define SX_PLUS_IS_HEAD 0   /* OT:  A[S+j,k] = +1, A[i,k] = -1      (formats.py:156-158)     */
+#define SX_PLUS_IS_TAIL 1   /* MCF: A[tail,k] = +1, A[head,k] = -1  (scripts/min2mcf.py:36-37) */
+
+/* Result header of a pricing pass (device memory, 32 bytes, written by sx_price_*). */
+typedef struct sx_price_header {
+    unsigned long long n_violating;   /* #arcs with rc < -tol (exact, even past the candidate cap) */
+    long long          min_rc_key;    /* order-preserving int64 image of min rc; see sx_key_to_f64 */
+    unsigned long long n_priced;      /* arcs priced by this launch (sanity / throughput) */
+    unsigned long long reserved;
+} sx_price_header;
+
+SX_API int         sx_abi_version(void);
+SX_API const char *sx_error_string(int code);
+SX_API int         sx_last_cuda_error(void);            /* cudaError_t of the last SX_ERR_CUDA */
+SX_API double      sx_key_to_f64(long long key);        /* decode sx_price_header.min_rc_key */
+
+/* ---- K1: flow indicators ------------------------------------------------------------
+ * sx_score_ot replaces `np.maximum(X / s[:,None], X / d[None,:])`, net_manager.py:377-378.
+ *   x (S*D), s (S), d (D) -> score_out (S*D).  Correctly rounded IEEE divisions; NumPy
+ *   `maximum` semantics (NaN propagates).
+ * sx_score_mcf replaces net_manager.py:165-182: reversal of arcs with x > u/2, per-node
+ *   out/in sums in ascending arc id (SciPy csr_matvec order), f_inv = 1/max(f1,f2),
+ *   indicator = max over the two end nodes of |f_inv * x_hat|.  node_ptr (N+1) /
+ *   node_arc / node_sign are the CSR arrays of the incidence matrix A (formats.py:118).
+ */
+SX_API int    sx_score_ot(const double *x, const double *s, const double *d, int64_t S, int64_t D,
+                   double *score_out, void *stream);
+SX_API size_t sx_score_mcf_workspace_bytes(int64_t N, int64_t E);
+SX_API int    sx_score_mcf(const double *x, const double *u, const int32_t *tail, const int32_t *head,
+                    const int64_t *node_ptr, const int32_t *node_arc, const int8_t *node_sign,
+                    int64_t N, int64_t E, double *score_out, void *ws, size_t ws_bytes,
+                    void *stream);
+
+/* ---- K1c: stable radix argsort --------------------------------------------------------
+ * Replaces `np.argsort(flow_indicators)` at net_manager.py:184,379 (run stable, north_star)
+ * and the stable argsort inside scipy.sparse.csgraph.minimum_spanning_tree (tree_BI.py:53).
+ *   order_asc_out[p] = arc id of the p-th smallest key; ties by ascending arc id;
+ *   -0.0 == +0.0; NaN sorts last (NumPy order).  sorted_key_out (optional, may be NULL)
+ *   receives the keys in sorted order.
+ * sx_queue_from_order:   queue = order_asc[::-1] widened to int64 (net_manager.py:184,379).
+ * sx_kruskal_order:      descending key, ties by ASCENDING id = stable argsort of -key, the
+ *   order SciPy's Kruskal visits arcs in (tree_BI.py:47,53).
+ */
+SX_API size_t sx_argsort_workspace_bytes(int64_t n);
+SX_API int    sx_argsort_f64(const double *key, int64_t n, uint32_t *order_asc_out,
+                      double *sorted_key_out, void *ws, size_t ws_bytes, void *stream);
+SX_API int    sx_argsort_u64(const unsigned long long *key, int64_t n, int key_bits,
+                      uint32_t *order_asc_out, unsigned long long *sorted_key_out,
+                      void *ws, size_t ws_bytes, void *stream);
+SX_API int    sx_queue_from_order(const uint32_t *order_asc, int64_t n, int64_t *queue_out, void *stream);
+SX_API size_t sx_kruskal_order_workspace_bytes(int64_t n);
+SX_API int    sx_kruskal_order(const double *sorted_key, const uint32_t *order_asc, int64_t n,
+                        uint32_t *korder_out, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- K2: spanning-tree basis identification -------------------------------------------
+ * Replaces `sp.csgraph.minimum_spanning_tree(-w)` + flatnonzero, tree_BI.py:32-59.
+ * Visits arcs in `korder`; keeps an arc when its end nodes are in different components
+ * (lock-free union-find, path halving; chunked filter + min-rank hooking, exact because
+ * the order is a strict total order); stops at N-1 arcs.  Endpoints: tail == NULL selects
+ * the implicit OT graph (arc k = (k / D, S + k % D)), else tail[k], head[k].
+ *   tree_out (capacity N-1): kept arc ids, ascending.  n_tree_out: their number.
+ */
+SX_API size_t sx_kruskal_workspace_bytes(int64_t N, int64_t n);
+SX_API int    sx_kruskal(const uint32_t *korder, int64_t n, const int32_t *tail, const int32_t *head,
+                  int64_t S, int64_t D, int64_t N, int64_t *tree_out, int64_t *n_tree_out,
+                  void *ws, size_t ws_bytes, void *stream);
+
+/* ---- K3: node potentials from the tree ------------------------------------------------
+ * The reference takes duals from the LP solver (solver_caller/gurobi.py:157-159, used at
+ * network_methods/algorithms.py:132); this computes them from the tree: y[root] = 0 and
+ * y[plus] - y[minus] = cost for every tree arc (B^T y = c_B with B = A[:-1, tree],
+ * tree_BI.py:74).  Euler tour + list ranking by pointer jumping.
+ *   cost: indexed by arc id with leading dimension: cost[(k / D) * ld + k % D] when
+ *   tail == NULL (dense OT cost matrix M), cost[k] otherwise.
+ *   status_out (device int32): 0 or SX_ERR_NOT_SPANNING.
+ */
+SX_API size_t sx_tree_potentials_workspace_bytes(int64_t N);
+SX_API int    sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int32_t *tail,
+                          const int32_t *head, int64_t S, int64_t D, int64_t N,
+                          const double *cost, int64_t ld, int plus_convention, int64_t root,
+                          double *y_out, int32_t *status_out, void *ws, size_t ws_bytes,
+                          void *stream);
+
+/* ---- K4: pricing ----------------------------------------------------------------------
+ * sx_price_dense_ot replaces `c - A.T @ y` + `np.all(rc >= -tol)` over the dense OT cost
+ * matrix, net_manager.py:474-497:  rc_ij = fl(M_ij - fl(y_dst[j] - y_src[i])).
+ *   M: rows [row0, row0 + S_loc) of the S x D cost matrix, leading dimension ld (elements);
+ *   y_src: the S_loc source potentials of those rows; y_dst: the D sink potentials.
+ *   Arc ids reported are global: (row0 + i) * D + j.
+ *   header: counts / min (see sx_price_header).  Candidates (rc < -tol) are appended to
+ *   cand_rc / cand_id (capacity cand_cap, unordered; may be NULL with cand_cap = 0).
+ *   rc_out: optional full reduced-cost output (S_loc x D, ld_out), else NULL.
+ *   variant: 0 = TMA-staged pipeline (needs 16 B aligned M and even ld; returns
+ *   SX_ERR_UNALIGNED otherwise), 1 = vectorised direct loads, 2 = scalar loads (any
+ *   alignment), -1 = choose automatically.
+ * sx_price_arcs replaces net_manager.py:293-319 for an arc list:
+ *   rc_k = c_k - (y[tail_k] - y[head_k]), negated where vbasis_k == -2.
+ * sx_price_header_reset must be enqueued before the first sx_price_* call of a pass;
+ *   several calls (row slabs, arc-list tail) may then accumulate into one header.
+ */
+SX_API int    sx_price_header_reset(sx_price_header *header, void *stream);
+SX_API int    sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int64_t S_loc, int64_t D,
+                         const double *y_src, const double *y_dst, double tol,
+                         sx_price_header *header, double *cand_rc, int64_t *cand_id,
+                         int64_t cand_cap, double *rc_out, int64_t ld_out, int variant,
+                         void *stream);
+SX_API int    sx_price_arcs(const double *c, const int32_t *tail, const int32_t *head,
+                     const int8_t *vbasis, const double *y, int64_t E, int64_t id0, double tol,
+                     sx_price_header *header, double *cand_rc, int64_t *cand_id,
+                     int64_t cand_cap, double *rc_out, void *stream);
+
+/* Tuning knobs of sx_price_dense_ot (bench sweeps): rows per TMA box / pipeline stages of
+ * variant 0 -- supported pairs (8,8) (8,12) (16,4) (16,6) (32,3) -- and CTAs per SM of the
+ * direct-load variants.  Values <= 0 leave a knob unchanged. */
+SX_API int    sx_price_set_tuning(int tma_rows, int tma_stages, int direct_ctas_per_sm);
+
+/* ---- top-k most violating arcs (north_star extension) -------
+ * Among the candidates (rc, id) select the K smallest by (rc ascending, id ascending).
+ *   n_cand_dev: device pointer to the candidate count (header->n_violating; clamped to
+ *   cand_cap inside).  out_rc / out_id have capacity K; out_n (device int64) = min(K, n).
+ *   Entries past out_n are filled with (+inf, -1) so fixed-size blocks can be all-gathered.
+ *   K <= SX_TOPK_MAX_K uses the warp-shuffle bitonic path and needs no host round trip.
+ * sx_topk_merge merges G such blocks (as gathered from G ranks) into one.
+ */
+#define SX_TOPK_MAX_K 1024
+SX_API size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K);
+SX_API int    sx_topk_select(const double *cand_rc, const int64_t *cand_id,
+                      const unsigned long long *n_cand_dev, int64_t cand_cap, int64_t K,
+                      double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
+                      void *stream);
+SX_API int    sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t G, int64_t K,
+                     double *out_rc, int64_t *out_id, int64_t *out_n, void *stream);
+
+/* ---- host-buffer entry point (what a reference-side binding calls with NumPy arrays) ----
+ * One pricing pass with HOST buffers: uploads y (and M if M_dev == NULL), prices, selects
+ * the top K, and returns count / min / top-k on the host.  Synchronises before returning.
+ *   M_h: host S x D cost matrix (row-major, contiguous) or NULL when M_dev is given.
+ *   M_dev: device-resident copy from a previous call (managers upload M once), or NULL.
+ */
+SX_API int    sx_price_dense_ot_h(const double *M_h, const double *M_dev, int64_t S, int64_t D,
+                           const double *y_h, double tol, int64_t K,
+                           unsigned long long *n_violating_h, double *min_rc_h,
+                           double *topk_rc_h, int64_t *topk_id_h, int64_t *topk_n_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SXCROSS_H_ */

@@ -1,0 +1,232 @@
+// sx_kruskal.cu -- K2: spanning-tree basis identification (sm_100a).
+//
+// Replaces `sp.csgraph.minimum_spanning_tree(-w)` + `np.flatnonzero` of the reference
+// (tree_BI.py:32-59): Kruskal over the arcs in `korder` (descending weight, ties by ascending
+// arc id), keep an arc when its end nodes are in different components, stop at N-1 arcs.
+//
+// Parallel but bit-exact: the position in `korder` is a strict total order, so the maximum
+// spanning forest is unique and any correct algorithm returns the reference's arc set
+// (SURVEY.md H2).  One persistent cooperative kernel walks `korder` in growing chunks; per chunk
+//   phase A  filter: drop arcs whose ends already share a root (lock-free union-find, path
+//            halving), compact the survivors, and let every root take the atomicMin of the
+//            survivor positions incident to it (epoch-tagged so the table never needs a reset);
+//   phase B  hook: an arc that is the minimum of one of its roots is a tree arc (cut property
+//            on the contracted graph); hook that root under the other (smaller id wins when
+//            both picked the same arc) and record the arc;
+// and repeats until the chunk has no survivor.  Work is atomics / L2 bound, not HBM bound.
+#include <cooperative_groups.h>
+
+#include "sx_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sx {
+
+constexpr int kKrThreads = 256;
+constexpr unsigned long long kEpochMax = (1ull << 24) - 1;
+
+struct KrParams {
+    const uint32_t *korder;
+    long long       n;
+    const int32_t  *tail, *head;
+    long long       S, D, N;
+    int            *parent;               // N
+    unsigned long long *best;             // N, epoch-tagged minimum survivor position per root
+    uint32_t       *list[2];              // survivor positions (capacity list_cap)
+    int2           *roots[2];             // (root_u, root_v) of each survivor
+    long long       list_cap;
+    long long      *tree_out;             // capacity N-1, pre-filled with a sentinel by the host
+    unsigned long long *ctr;              // [0] tree count, [1],[2] survivor counts of list 0/1
+};
+
+__device__ __forceinline__ int kr_find(int *parent, int x) {
+    for (;;) {
+        const int p = __ldcg(parent + x);
+        if (p == x) return x;
+        const int gp = __ldcg(parent + p);
+        if (gp == p) return p;
+        parent[x] = gp;   // path halving; racing writers only ever store an ancestor
+        x = gp;
+    }
+}
+
+__device__ __forceinline__ void kr_endpoints(const KrParams &p, uint32_t e, int &u, int &v) {
+    if (p.tail) { u = p.tail[e]; v = p.head[e]; }
+    else { const long long i = (long long)e / p.D; u = (int)i; v = (int)(p.S + ((long long)e - i * p.D)); }
+}
+
+__global__ void __launch_bounds__(kKrThreads) kruskal_kernel(KrParams p) {
+    cg::grid_group grid = cg::this_grid();
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gsz  = (long long)gridDim.x * blockDim.x;
+    for (long long v = gtid; v < p.N; v += gsz) { p.parent[v] = (int)v; p.best[v] = ~0ull; }
+    grid.sync();
+
+    long long pos = 0;
+    long long csize = 4 * p.N;
+    if (csize > p.list_cap) csize = p.list_cap;
+    unsigned long long epoch = 0;
+    const unsigned long long want = (unsigned long long)(p.N - 1);
+    bool done = false;
+
+    while (pos < p.n && !done) {
+        long long cend = pos + csize;
+        if (cend > p.n) cend = p.n;
+        bool first = true;
+        int cur = 0;                       // list[cur] holds the survivors of the previous round
+        for (;;) {
+            ++epoch;
+            const unsigned long long tag = (kEpochMax - epoch) << 40;
+            const int nxt = cur ^ 1;
+            const long long cnt_in = first ? (cend - pos) : (long long)__ldcg(&p.ctr[1 + cur]);
+            // ---- phase A: filter + propose ----
+            for (long long base = (long long)blockIdx.x * blockDim.x; base < cnt_in; base += gsz) {
+                const long long idx = base + threadIdx.x;
+                bool alive = false;
+                uint32_t q = 0;
+                int ru = 0, rv = 0;
+                if (idx < cnt_in) {
+                    q = first ? (uint32_t)(pos + idx) : p.list[cur][idx];
+                    int u, v;
+                    kr_endpoints(p, p.korder[q], u, v);
+                    ru = kr_find(p.parent, u);
+                    rv = kr_find(p.parent, v);
+                    alive = ru != rv;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, alive);
+                if (m) {
+                    unsigned long long slot0 = 0;
+                    if (lane_id() == (unsigned)(__ffs(m) - 1))
+                        slot0 = atomicAdd(&p.ctr[1 + nxt], (unsigned long long)__popc(m));
+                    slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(m) - 1);
+                    if (alive) {
+                        const long long slot = (long long)slot0 + __popc(m & ((1u << lane_id()) - 1u));
+                        p.list[nxt][slot]  = q;
+                        p.roots[nxt][slot] = make_int2(ru, rv);
+                        atomicMin(&p.best[ru], tag | q);
+                        atomicMin(&p.best[rv], tag | q);
+                    }
+                }
+            }
+            grid.sync();
+            const long long alive_n = (long long)__ldcg(&p.ctr[1 + nxt]);
+            if (alive_n == 0) break;
+            // ---- phase B: hook the winners ----
+            if (gtid == 0) p.ctr[1 + cur] = 0;   // becomes the append counter of the next round
+            for (long long idx = gtid; idx < alive_n; idx += gsz) {
+                const uint32_t q = p.list[nxt][idx];
+                const int2 r = p.roots[nxt][idx];
+                const unsigned long long key = tag | q;
+                const bool su = __ldcg(&p.best[r.x]) == key;
+                const bool sv = __ldcg(&p.best[r.y]) == key;
+                if (su || sv) {
+                    const unsigned long long t = atomicAdd(&p.ctr[0], 1ull);
+                    if (t < want) p.tree_out[t] = (long long)p.korder[q];
+                    if (su && sv) {
+                        const int hi = r.x > r.y ? r.x : r.y, lo = r.x > r.y ? r.y : r.x;
+                        p.parent[hi] = lo;
+                    } else if (su) {
+                        p.parent[r.x] = r.y;
+                    } else {
+                        p.parent[r.y] = r.x;
+                    }
+                }
+            }
+            grid.sync();
+            if (__ldcg(&p.ctr[0]) >= want) { done = true; break; }
+            first = false;
+            cur = nxt;
+        }
+        // the break on alive_n == 0 leaves ctr[1+nxt] == 0 and ctr[1+cur] possibly stale: clear both
+        grid.sync();
+        if (gtid == 0) { p.ctr[1] = 0; p.ctr[2] = 0; }
+        grid.sync();
+        pos = cend;
+        csize *= 2;
+        if (csize > p.list_cap) csize = p.list_cap;
+    }
+}
+
+__global__ void kr_fill_kernel(long long *tree_out, long long cap, unsigned long long *ctr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) tree_out[i] = 0x7fffffffffffffffll;
+    if (i < 4) ctr[i] = 0;
+}
+__global__ void kr_count_kernel(const unsigned long long *ctr, long long cap, long long *n_tree_out) {
+    const unsigned long long c = ctr[0];
+    *n_tree_out = (long long)(c < (unsigned long long)cap ? c : (unsigned long long)cap);
+}
+
+static long long kr_list_cap(long long N, long long n) {
+    long long cap = 8 * N;
+    if (cap < (1ll << 22)) cap = 1ll << 22;
+    if (cap > n) cap = n;
+    if (cap < 1) cap = 1;
+    return cap;
+}
+
+}  // namespace sx
+
+using namespace sx;
+
+extern "C" size_t sx_kruskal_workspace_bytes(int64_t N, int64_t n) {
+    if (N < 0 || n < 0) return 0;
+    const size_t cap = (size_t)kr_list_cap(N, n);
+    const size_t T = (size_t)(N > 0 ? N : 1);
+    return carve_bytes(N, 4) + carve_bytes(N, 8) + 2 * carve_bytes(cap, 4) + 2 * carve_bytes(cap, 8) +
+           carve_bytes(8, 8) + carve_bytes(T, 8) + carve_bytes(T, 4) + sx_argsort_workspace_bytes((int64_t)T) + 256;
+}
+
+extern "C" int sx_kruskal(const uint32_t *korder, int64_t n, const int32_t *tail, const int32_t *head,
+                          int64_t S, int64_t D, int64_t N, int64_t *tree_out, int64_t *n_tree_out,
+                          void *ws, size_t ws_bytes, void *stream) {
+    if (n < 0 || N < 0 || !tree_out || !n_tree_out) return SX_ERR_INVALID;
+    if ((tail == nullptr) != (head == nullptr)) return SX_ERR_INVALID;
+    if (!tail && (S <= 0 || D <= 0 || S + D != N || S * D != n)) return SX_ERR_INVALID;
+    if (N >= (1ll << 31) || n >= (1ll << 32)) return SX_ERR_TOO_LARGE;
+    if (n > 0 && !korder) return SX_ERR_INVALID;
+    if (!ws || ws_bytes < sx_kruskal_workspace_bytes(N, n)) return SX_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long tcap = N > 1 ? N - 1 : 0;
+
+    KrParams p;
+    Carver cv(ws);
+    p.korder = korder; p.n = n; p.tail = tail; p.head = head; p.S = S; p.D = D; p.N = N;
+    p.parent = cv.take<int>(N);
+    p.best = cv.take<unsigned long long>(N);
+    p.list_cap = kr_list_cap(N, n);
+    p.list[0] = cv.take<uint32_t>(p.list_cap); p.list[1] = cv.take<uint32_t>(p.list_cap);
+    p.roots[0] = cv.take<int2>(p.list_cap);    p.roots[1] = cv.take<int2>(p.list_cap);
+    p.ctr = cv.take<unsigned long long>(8);
+    const size_t T = (size_t)(N > 0 ? N : 1);
+    long long *raw_tree = cv.take<long long>(T);
+    uint32_t *perm = cv.take<uint32_t>(T);
+    void *sort_ws = cv.base + cv.off;
+    const size_t sort_ws_bytes = ws_bytes - cv.off;
+    p.tree_out = raw_tree;
+
+    kr_fill_kernel<<<(int)((tcap + 4 + 255) / 256), 256, 0, st>>>(raw_tree, tcap, p.ctr);
+    SX_LAUNCH_CHECK();
+    if (n > 0 && tcap > 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        SX_CUDA(cudaGetDevice(&dev));
+        SX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kruskal_kernel, kKrThreads, 0));
+        if (per_sm < 1) return SX_ERR_NO_DEVICE;
+        if (per_sm > 4) per_sm = 4;
+        void *args[] = {&p};
+        SX_CUDA(cudaLaunchCooperativeKernel((void *)kruskal_kernel, dim3(sms * per_sm), dim3(kKrThreads), args, 0, st));
+    }
+    kr_count_kernel<<<1, 1, 0, st>>>(p.ctr, tcap, (long long *)n_tree_out);
+    SX_LAUNCH_CHECK();
+    if (tcap > 0) {
+        // ascending arc ids (np.flatnonzero order, tree_BI.py:56-57); sentinels sort last
+        int bits = 1;
+        while (bits < 63 && (1ll << bits) <= n) ++bits;
+        // the low `bits` bits of the sentinel are all ones (>= n > any arc id), so it still sorts last
+        int rc = sx_argsort_u64((const unsigned long long *)raw_tree, tcap, bits, perm,
+                                (unsigned long long *)tree_out, sort_ws, sort_ws_bytes, st);
+        if (rc != SX_OK) return rc;
+    }
+    return SX_OK;
+}

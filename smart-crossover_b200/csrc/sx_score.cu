@@ -1,0 +1,147 @@
+// sx_score.cu -- K1a / K1b: per-arc flow-ratio scores (sm_100a).
+//
+// K1a replaces `np.maximum(X / s[:,None], X / d[None,:])` (reference net_manager.py:377-378).
+// K1b replaces the SciPy sparse pipeline of `MCFManagerStd.get_sorted_flows`
+// (net_manager.py:165-182).  Both must be bit-exact with NumPy/SciPy: correctly rounded
+// IEEE fp64 division, NumPy `maximum` semantics, no FMA contraction (built with -fmad=false)
+// and, for K1b, per-node sums taken sequentially in ascending arc id (csr_matvec order).
+#include "sx_common.cuh"
+
+namespace sx {
+
+// NumPy: maximum(a, b) = isnan(a) ? a : (a > b ? a : b)
+__device__ __forceinline__ double np_maximum(double a, double b) {
+    return (a != a) ? a : (a > b ? a : b);
+}
+
+constexpr int kScThreads = 256;
+constexpr int kScCols    = 4;   // columns per thread, strided by the block width (coalesced)
+
+__global__ void __launch_bounds__(kScThreads)
+score_ot_kernel(const double *__restrict__ x, const double *__restrict__ s, const double *__restrict__ d,
+                long long S, long long D, long long col_blocks, double *__restrict__ out) {
+    const long long tiles = S * col_blocks;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long i = t / col_blocks;
+        const long long j0 = (t - i * col_blocks) * (kScThreads * kScCols) + threadIdx.x;
+        const double si = __ldg(s + i);
+        double xv[kScCols], dv[kScCols];
+#pragma unroll
+        for (int q = 0; q < kScCols; ++q) {
+            const long long j = j0 + (long long)q * kScThreads;
+            if (j < D) { xv[q] = x[i * D + j]; dv[q] = __ldg(d + j); }
+        }
+#pragma unroll
+        for (int q = 0; q < kScCols; ++q) {
+            const long long j = j0 + (long long)q * kScThreads;
+            if (j < D) out[i * D + j] = np_maximum(xv[q] / si, xv[q] / dv[q]);
+        }
+    }
+}
+
+// ---- K1b ----------------------------------------------------------------------------------
+// x_hat and the reversal flag, net_manager.py:166-168 evaluated literally:
+//   x_hat = x * (~mask) + u * mask - x * mask ;  x_hat[(x < 0) | (x > u)] = 0
+__global__ void mcf_xhat_kernel(const double *__restrict__ x, const double *__restrict__ u, long long E,
+                                double *__restrict__ xhat, int8_t *__restrict__ flip) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < E;
+         k += (long long)gridDim.x * blockDim.x) {
+        const double xv = x[k], uv = u[k];
+        const bool   m  = xv > uv / 2;
+        const double nm = m ? 0.0 : 1.0, mm = m ? 1.0 : 0.0;
+        double xh = (xv * nm + uv * mm) - xv * mm;
+        if ((xv < 0) || (xv > uv)) xh = 0.0;
+        xhat[k] = xh;
+        flip[k] = m ? 1 : 0;
+    }
+}
+
+// per node: f1 = sum over incident arcs with A_bar = +1, f2 = with A_bar = -1, both sequential
+// from 0.0 in ascending arc id (net_manager.py:171-175); f_inv = 1 / max(f1, f2) or 0 (:176-177).
+__global__ void mcf_node_kernel(const long long *__restrict__ node_ptr, const int32_t *__restrict__ node_arc,
+                                const int8_t *__restrict__ node_sign, const int8_t *__restrict__ flip,
+                                const double *__restrict__ xhat, long long N, double *__restrict__ finv) {
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < N;
+         v += (long long)gridDim.x * blockDim.x) {
+        double f1 = 0.0, f2 = 0.0;
+        const long long q1 = node_ptr[v + 1];
+        for (long long q = node_ptr[v]; q < q1; ++q) {
+            const int32_t k = node_arc[q];
+            int sg = node_sign[q];
+            if (flip[k]) sg = -sg;
+            const double xh = xhat[k];
+            if (sg > 0) f1 += (double)sg * xh;
+            else if (sg < 0) f2 += (double)(-sg) * xh;
+        }
+        const double f = np_maximum(f1, f2);
+        finv[v] = (f != 0) ? 1.0 / f : 0.0;
+    }
+}
+
+// per arc: max over its end nodes of |f_inv[node] * x_hat| (net_manager.py:178-182)
+__global__ void mcf_arc_kernel(const int32_t *__restrict__ tail, const int32_t *__restrict__ head,
+                               const double *__restrict__ finv, const double *__restrict__ xhat, long long E,
+                               double *__restrict__ out) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < E;
+         k += (long long)gridDim.x * blockDim.x) {
+        const double xh = xhat[k];
+        const int32_t t = tail[k], h = head[k];
+        double r = 0.0;
+        if (t >= 0) r = np_maximum(r, fabs(__ldg(finv + t) * xh));
+        if (h >= 0) r = np_maximum(r, fabs(__ldg(finv + h) * xh));
+        out[k] = r;
+    }
+}
+
+static int grid_for(long long n, int threads) {
+    long long g = (n + threads - 1) / threads;
+    const long long cap = (long long)kNumSMs * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace sx
+
+using namespace sx;
+
+extern "C" int sx_score_ot(const double *x, const double *s, const double *d, int64_t S, int64_t D,
+                           double *score_out, void *stream) {
+    if (S < 0 || D < 0) return SX_ERR_INVALID;
+    if (S == 0 || D == 0) return SX_OK;
+    if (!x || !s || !d || !score_out) return SX_ERR_INVALID;
+    const long long col_blocks = (D + kScThreads * kScCols - 1) / (kScThreads * kScCols);
+    long long tiles = S * col_blocks;
+    long long grid = tiles < (long long)kNumSMs * 16 ? tiles : (long long)kNumSMs * 16;
+    score_ot_kernel<<<(int)grid, kScThreads, 0, (cudaStream_t)stream>>>(x, s, d, S, D, col_blocks, score_out);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}
+
+extern "C" size_t sx_score_mcf_workspace_bytes(int64_t N, int64_t E) {
+    if (N < 0 || E < 0) return 0;
+    return carve_bytes((size_t)E, 8) + carve_bytes((size_t)E, 1) + carve_bytes((size_t)N, 8) + 256;
+}
+
+extern "C" int sx_score_mcf(const double *x, const double *u, const int32_t *tail, const int32_t *head,
+                            const int64_t *node_ptr, const int32_t *node_arc, const int8_t *node_sign,
+                            int64_t N, int64_t E, double *score_out, void *ws, size_t ws_bytes,
+                            void *stream) {
+    if (N < 0 || E < 0) return SX_ERR_INVALID;
+    if (E == 0) return SX_OK;
+    if (!x || !u || !tail || !head || !node_ptr || !node_arc || !node_sign || !score_out) return SX_ERR_INVALID;
+    if (N >= (1ll << 31) || E >= (1ll << 31)) return SX_ERR_TOO_LARGE;
+    if (!ws || ws_bytes < sx_score_mcf_workspace_bytes(N, E)) return SX_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(ws);
+    double *xhat = cv.take<double>(E);
+    int8_t *flip = cv.take<int8_t>(E);
+    double *finv = cv.take<double>(N);
+    mcf_xhat_kernel<<<grid_for(E, 256), 256, 0, st>>>(x, u, E, xhat, flip);
+    SX_LAUNCH_CHECK();
+    mcf_node_kernel<<<grid_for(N, 128), 128, 0, st>>>((const long long *)node_ptr, node_arc, node_sign, flip, xhat, N, finv);
+    SX_LAUNCH_CHECK();
+    mcf_arc_kernel<<<grid_for(E, 256), 256, 0, st>>>(tail, head, finv, xhat, E, score_out);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}

@@ -1,0 +1,288 @@
+// sx_topk.cu -- selection of the K most violating arcs (sm_100a).
+//
+// north_star extension (the reference never ranks violators, it
+// only tests `np.all(rc >= -tol)`, net_manager.py:318,496): among the candidates (rc, arc id)
+// compacted by the pricing kernels, return the K smallest by (rc ascending, id ascending).
+// (rc, id) is a strict total order, so the result does not depend on the (unordered)
+// compaction, on the slicing below, or on how many GPUs priced the matrix.
+//
+// K <= 1024 (device-driven, no host round trip):
+//   1. every CTA bitonic-sorts one slice of 4096 candidates -- the 5 innermost stages of each
+//      merge step run on registers with warp shuffles, the wider ones through shared memory --
+//      and keeps the slice's K best as a padded, sorted list;
+//   2. rank merge: an element's global rank is the sum over lists of lower_bound(list, element);
+//      elements above the smallest "K-th of a full list" cannot be in the answer and are skipped.
+// The same rank merge combines the per-GPU lists after the all-gather (sx_topk_merge).
+// K > 1024: two stable radix argsorts (by id, then by rc) over the candidates.
+#include <math.h>
+
+#include "sx_common.cuh"
+
+namespace sx {
+
+constexpr int kTkSlice   = 4096;
+constexpr int kTkThreads = 1024;
+constexpr int kTkItems   = kTkSlice / kTkThreads;   // 4
+
+struct Cand {
+    double    rc;
+    long long id;
+};
+__device__ __forceinline__ bool cand_less(const Cand &a, const Cand &b) {
+    return a.rc < b.rc || (a.rc == b.rc && a.id < b.id);
+}
+__device__ __forceinline__ Cand cand_pad() { return Cand{INFINITY, -1}; }
+// padding must sort after every real candidate: compare as (+inf, max id)
+__device__ __forceinline__ bool cand_less_p(const Cand &a, const Cand &b) {
+    const long long ia = a.id < 0 ? 0x7fffffffffffffffll : a.id;
+    const long long ib = b.id < 0 ? 0x7fffffffffffffffll : b.id;
+    return a.rc < b.rc || (a.rc == b.rc && ia < ib);
+}
+
+__device__ __forceinline__ Cand shfl_xor_cand(const Cand &c, int mask) {
+    Cand r;
+    r.rc = __shfl_xor_sync(0xffffffffu, c.rc, mask);
+    r.id = __shfl_xor_sync(0xffffffffu, c.id, mask);
+    return r;
+}
+
+// One CTA sorts candidates [b*4096, (b+1)*4096) and writes its K best (padded) to lists[b].
+__global__ void __launch_bounds__(kTkThreads)
+topk_slice_sort_kernel(const double *__restrict__ cand_rc, const long long *__restrict__ cand_id,
+                       const unsigned long long *__restrict__ n_cand_dev, long long cand_cap, int K,
+                       double *__restrict__ lists_rc, long long *__restrict__ lists_id) {
+    extern __shared__ __align__(16) unsigned char tk_raw[];
+    Cand *sm = reinterpret_cast<Cand *>(tk_raw);
+    unsigned long long n64 = *n_cand_dev;
+    const long long n = n64 > (unsigned long long)cand_cap ? cand_cap : (long long)n64;
+    const long long base = (long long)blockIdx.x * kTkSlice;
+    double    *out_rc = lists_rc + (long long)blockIdx.x * K;
+    long long *out_id = lists_id + (long long)blockIdx.x * K;
+    if (base >= n) {   // empty slice: all padding
+        for (int i = threadIdx.x; i < K; i += kTkThreads) { out_rc[i] = INFINITY; out_id[i] = -1; }
+        return;
+    }
+    // element index i = q * 1024 + tid: bits 0-4 = lane, 5-9 = warp, 10-11 = register slot
+    Cand e[kTkItems];
+#pragma unroll
+    for (int q = 0; q < kTkItems; ++q) {
+        const long long g = base + q * kTkThreads + threadIdx.x;
+        e[q] = (g < n) ? Cand{cand_rc[g], cand_id[g]} : cand_pad();
+    }
+    for (int k = 2; k <= kTkSlice; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= kTkThreads) {
+                // partner lives in another register slot of the same thread
+                const int dq = j / kTkThreads;
+#pragma unroll
+                for (int q = 0; q < kTkItems; ++q) {
+                    if ((q & dq) == 0) {
+                        const int i = q * kTkThreads + threadIdx.x;
+                        const bool asc = (i & k) == 0;
+                        Cand &lo = e[q], &hi = e[q | dq];
+                        if (cand_less_p(hi, lo) == asc) { Cand t = lo; lo = hi; hi = t; }
+                    }
+                }
+            } else if (j >= 32) {
+                // partner lives in another warp: exchange through shared memory
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < kTkItems; ++q) sm[q * kTkThreads + threadIdx.x] = e[q];
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < kTkItems; ++q) {
+                    const int i = q * kTkThreads + threadIdx.x;
+                    const Cand other = sm[i ^ j];
+                    const bool asc = (i & k) == 0, lower = (i & j) == 0;
+                    const bool take_min = lower == asc;
+                    const bool other_smaller = cand_less_p(other, e[q]);
+                    if (take_min == other_smaller) e[q] = other;
+                }
+            } else {
+                // partner lives in another lane of the same warp: warp shuffle
+#pragma unroll
+                for (int q = 0; q < kTkItems; ++q) {
+                    const int i = q * kTkThreads + threadIdx.x;
+                    const Cand other = shfl_xor_cand(e[q], j);
+                    const bool asc = (i & k) == 0, lower = (i & j) == 0;
+                    const bool take_min = lower == asc;
+                    const bool other_smaller = cand_less_p(other, e[q]);
+                    if (take_min == other_smaller) e[q] = other;
+                }
+            }
+        }
+    }
+    // sorted ascending over i; the K best are i < K
+#pragma unroll
+    for (int q = 0; q < kTkItems; ++q) {
+        const int i = q * kTkThreads + threadIdx.x;
+        if (i < K) { out_rc[i] = e[q].rc; out_id[i] = e[q].id; }
+    }
+}
+
+__device__ __forceinline__ int lower_bound_list(const double *rc, const long long *id, int K, const Cand &x) {
+    int lo = 0, hi = K;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const Cand m{rc[mid], id[mid]};
+        if (cand_less_p(m, x)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void topk_fill_kernel(double *out_rc, long long *out_id, long long *out_n, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) { out_rc[i] = INFINITY; out_id[i] = -1; }
+    if (i == 0) *out_n = 0;
+}
+
+// lists: L sorted, padded lists of length K.  Writes the K globally smallest to out.
+__global__ void __launch_bounds__(256)
+topk_rank_merge_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, int L, int K,
+                       const unsigned long long *n_cand_dev, long long cand_cap,
+                       double *__restrict__ out_rc, long long *__restrict__ out_id, long long *out_n) {
+    __shared__ Cand s_thr[256];
+    // lists that can hold data (select path: only the first ceil(n / 4096) slices are non-empty)
+    int Lu = L;
+    if (n_cand_dev) {
+        unsigned long long n64 = *n_cand_dev;
+        const long long n = n64 > (unsigned long long)cand_cap ? cand_cap : (long long)n64;
+        Lu = (int)((n + kTkSlice - 1) / kTkSlice);
+        if (Lu > L) Lu = L;
+    }
+    // threshold: the smallest last element over lists (padding = +inf => no constraint)
+    Cand thr = cand_pad();
+    for (int l = threadIdx.x; l < Lu; l += blockDim.x) {
+        const Cand c{lists_rc[(long long)l * K + K - 1], lists_id[(long long)l * K + K - 1]};
+        if (cand_less_p(c, thr)) thr = c;
+    }
+    s_thr[threadIdx.x] = thr;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o && cand_less_p(s_thr[threadIdx.x + o], s_thr[threadIdx.x]))
+            s_thr[threadIdx.x] = s_thr[threadIdx.x + o];
+        __syncthreads();
+    }
+    thr = s_thr[0];
+    const long long total = (long long)Lu * K;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
+         w += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(w / K), i = (int)(w - (long long)l * K);
+        const Cand c{lists_rc[w], lists_id[w]};
+        if (c.id < 0) continue;                 // padding
+        if (cand_less_p(thr, c)) continue;      // cannot be among the K best
+        int rank = i;
+        for (int m = 0; m < Lu && rank < K; ++m)
+            if (m != l) rank += lower_bound_list(lists_rc + (long long)m * K, lists_id + (long long)m * K, K, c);
+        if (rank < K) {
+            out_rc[rank] = c.rc;
+            out_id[rank] = c.id;
+            atomicAdd((unsigned long long *)out_n, 1ull);
+        }
+    }
+}
+
+// ---- large-K path helpers ---------------------------------------------------------------
+__global__ void tk_gather_kernel(const double *__restrict__ rc, const long long *__restrict__ id,
+                                 const uint32_t *__restrict__ perm, long long n, double *rc_out, long long *id_out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t s = perm[i];
+        rc_out[i] = rc[s];
+        id_out[i] = id[s];
+    }
+}
+__global__ void tk_emit_kernel(const double *__restrict__ rc, const long long *__restrict__ id,
+                               const uint32_t *__restrict__ perm, long long n, long long K, double *out_rc,
+                               long long *out_id, long long *out_n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < K;
+         i += (long long)gridDim.x * blockDim.x) {
+        if (i < n) { const uint32_t s = perm[i]; out_rc[i] = rc[s]; out_id[i] = id[s]; }
+        else { out_rc[i] = INFINITY; out_id[i] = -1; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_n = n < K ? n : K;
+}
+
+static int tk_grid(long long n, int threads) {
+    long long g = (n + threads - 1) / threads;
+    if (g > kNumSMs * 8) g = kNumSMs * 8;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace sx
+
+using namespace sx;
+
+extern "C" size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K) {
+    if (cand_cap < 0 || K < 0) return 0;
+    if (K <= SX_TOPK_MAX_K) {
+        const size_t L = ((size_t)cand_cap + kTkSlice - 1) / kTkSlice + 1;
+        return carve_bytes(L * (size_t)(K > 0 ? K : 1), 8) * 2 + 256;
+    }
+    return 2 * carve_bytes((size_t)cand_cap, 8) + 2 * carve_bytes((size_t)cand_cap, 4) +
+           sx_argsort_workspace_bytes(cand_cap) + 256;
+}
+
+extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id,
+                              const unsigned long long *n_cand_dev, int64_t cand_cap, int64_t K,
+                              double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
+                              void *stream) {
+    if (K <= 0 || cand_cap < 0 || !n_cand_dev || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
+    if (cand_cap > 0 && (!cand_rc || !cand_id)) return SX_ERR_INVALID;
+    if (!ws || ws_bytes < sx_topk_workspace_bytes(cand_cap, K)) return SX_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(ws);
+    if (K <= SX_TOPK_MAX_K) {
+        const int L = (int)((cand_cap + kTkSlice - 1) / kTkSlice);
+        topk_fill_kernel<<<(int)((K + 255) / 256), 256, 0, st>>>(out_rc, (long long *)out_id, (long long *)out_n, (int)K);
+        SX_LAUNCH_CHECK();
+        if (L == 0) return SX_OK;
+        double *lists_rc = cv.take<double>((size_t)(L + 1) * K);
+        long long *lists_id = cv.take<long long>((size_t)(L + 1) * K);
+        const size_t smem = sizeof(Cand) * kTkSlice;
+        SX_CUDA(cudaFuncSetAttribute(topk_slice_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        topk_slice_sort_kernel<<<L, kTkThreads, smem, st>>>(cand_rc, (const long long *)cand_id, n_cand_dev, cand_cap,
+                                                            (int)K, lists_rc, lists_id);
+        SX_LAUNCH_CHECK();
+        topk_rank_merge_kernel<<<tk_grid((long long)L * K, 256), 256, 0, st>>>(
+            lists_rc, lists_id, L, (int)K, n_cand_dev, cand_cap, out_rc, (long long *)out_id, (long long *)out_n);
+        SX_LAUNCH_CHECK();
+        return SX_OK;
+    }
+    // large K: the candidate count is needed on the host to size the sorts (one stream sync)
+    unsigned long long n64 = 0;
+    SX_CUDA(cudaMemcpyAsync(&n64, n_cand_dev, sizeof(n64), cudaMemcpyDeviceToHost, st));
+    SX_CUDA(cudaStreamSynchronize(st));
+    const long long n = n64 > (unsigned long long)cand_cap ? cand_cap : (long long)n64;
+    double *rc1 = cv.take<double>(cand_cap);
+    long long *id1 = cv.take<long long>(cand_cap);
+    uint32_t *perm1 = cv.take<uint32_t>(cand_cap);
+    uint32_t *perm2 = cv.take<uint32_t>(cand_cap);
+    void *sort_ws = cv.base + cv.off;
+    const size_t sort_ws_bytes = ws_bytes - cv.off;
+    if (n > 0) {
+        int rc = sx_argsort_u64((const unsigned long long *)cand_id, n, 63, perm1, nullptr, sort_ws, sort_ws_bytes, st);
+        if (rc != SX_OK) return rc;
+        tk_gather_kernel<<<tk_grid(n, 256), 256, 0, st>>>(cand_rc, (const long long *)cand_id, perm1, n, rc1, id1);
+        SX_LAUNCH_CHECK();
+        rc = sx_argsort_f64(rc1, n, perm2, nullptr, sort_ws, sort_ws_bytes, st);
+        if (rc != SX_OK) return rc;
+    }
+    tk_emit_kernel<<<tk_grid(K, 256), 256, 0, st>>>(rc1, id1, perm2, n, K, out_rc, (long long *)out_id, (long long *)out_n);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}
+
+extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t G, int64_t K,
+                             double *out_rc, int64_t *out_id, int64_t *out_n, void *stream) {
+    if (G <= 0 || K <= 0 || !blocks_rc || !blocks_id || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
+    if (G > (1 << 20) || K > (1ll << 30)) return SX_ERR_TOO_LARGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    topk_fill_kernel<<<(int)((K + 255) / 256), 256, 0, st>>>(out_rc, (long long *)out_id, (long long *)out_n, (int)K);
+    SX_LAUNCH_CHECK();
+    topk_rank_merge_kernel<<<tk_grid(G * K, 256), 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, (int)G, (int)K,
+                                                               nullptr, 0, out_rc, (long long *)out_id, (long long *)out_n);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}

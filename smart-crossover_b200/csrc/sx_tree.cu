@@ -1,0 +1,198 @@
+// sx_tree.cu -- K3: node potentials of a spanning tree by Euler tour + list ranking (sm_100a).
+//
+// The reference takes the duals from the LP solver (`return_y`, solver_caller/gurobi.py:157-159,
+// consumed at network_methods/algorithms.py:132).  For a tree basis they are the solution of
+// B^T y[:-1] = c[tree], y[root] = 0 with B = A[:-1, tree] (tree_BI.py:74): every tree arc fixes
+// y[plus] - y[minus] = cost.  Here:
+//   1. every tree arc becomes two half-edges (minus->plus carrying +c, plus->minus carrying -c);
+//   2. half-edges are sorted by origin node (radix argsort) to get each node's adjacency;
+//   3. succ(u->v) = the half-edge after (v->u) in v's circular adjacency list = Euler tour;
+//      the tour is cut at the root's first half-edge;
+//   4. Wyllie pointer jumping over `pred` accumulates, for every half-edge, the inclusive prefix
+//      of the weights (fp64) and of ones (its position in the tour) in ceil(log2 2T) rounds;
+//   5. of each pair of half-edges the one met first goes down the tree, and the prefix sum at
+//      it is the potential of the node it enters.
+// Latency / L2-gather bound (2T <= 2.4e5 elements at C5).
+#include "sx_common.cuh"
+
+namespace sx {
+
+constexpr int kTrThreads = 256;
+
+struct TreeArrays {
+    unsigned long long *origin;   // H sort keys: origin node of each half-edge
+    unsigned long long *sorted_origin;   // H
+    uint32_t *ho;                 // H half-edge ids sorted by origin (stable)
+    int      *dest;               // H
+    int      *pos;                // H position of a half-edge in `ho`
+    int      *first;              // N first position of a node's run in `ho`, -1 if none
+    double   *sum[2];             // H
+    int      *rank[2];            // H
+    int      *pred[2];            // H
+};
+
+__global__ void tree_halfedges_kernel(const long long *__restrict__ tree, long long T,
+                                      const int32_t *__restrict__ tail, const int32_t *__restrict__ head,
+                                      long long S, long long D, const double *__restrict__ cost, long long ld,
+                                      int plus_is_tail, TreeArrays a) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long e = tree[t];
+        int plus, minus;
+        double c;
+        if (tail == nullptr) {
+            const long long i = e / D, j = e - i * D;
+            plus = (int)(S + j); minus = (int)i;
+            c = cost[i * ld + j];
+        } else {
+            plus = plus_is_tail ? tail[e] : head[e];
+            minus = plus_is_tail ? head[e] : tail[e];
+            c = cost[e];
+        }
+        a.origin[2 * t] = (unsigned long long)minus; a.dest[2 * t] = plus;      a.sum[0][2 * t] = c;
+        a.origin[2 * t + 1] = (unsigned long long)plus; a.dest[2 * t + 1] = minus; a.sum[0][2 * t + 1] = -c;
+    }
+}
+
+__global__ void tree_first_kernel(long long H, TreeArrays a) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < H;
+         p += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long v = a.sorted_origin[p];
+        if (p == 0 || a.sorted_origin[p - 1] != v) a.first[v] = (int)p;
+        a.pos[a.ho[p]] = (int)p;
+    }
+}
+
+__global__ void tree_succ_kernel(long long H, TreeArrays a) {
+    for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < H;
+         h += (long long)gridDim.x * blockDim.x) {
+        const long long twin = h ^ 1;
+        const unsigned long long v = (unsigned long long)a.dest[h];
+        long long p2 = (long long)a.pos[twin] + 1;
+        if (p2 >= H || a.sorted_origin[p2] != v) p2 = a.first[v];
+        const uint32_t succ = a.ho[p2];
+        a.pred[0][succ] = (int)h;
+        a.rank[0][h] = 1;
+    }
+}
+
+__global__ void tree_cut_kernel(long long root, TreeArrays a, int32_t *status) {
+    const int f = a.first[root];
+    if (f < 0) { *status = SX_ERR_NOT_SPANNING; return; }
+    a.pred[0][a.ho[f]] = -1;
+}
+
+__global__ void tree_jump_kernel(long long H, const double *__restrict__ sum_in, const int *__restrict__ rank_in,
+                                 const int *__restrict__ pred_in, double *__restrict__ sum_out,
+                                 int *__restrict__ rank_out, int *__restrict__ pred_out) {
+    for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < H;
+         h += (long long)gridDim.x * blockDim.x) {
+        const int p = pred_in[h];
+        double s = sum_in[h];
+        int r = rank_in[h], np = p;
+        if (p >= 0) {
+            s = sum_in[p] + s;
+            r += rank_in[p];
+            np = pred_in[p];
+        }
+        sum_out[h] = s; rank_out[h] = r; pred_out[h] = np;
+    }
+}
+
+__global__ void tree_finalize_kernel(long long T, long long root, const double *__restrict__ sum,
+                                     const int *__restrict__ rank, const int *__restrict__ pred,
+                                     const int *__restrict__ dest, double *__restrict__ y, int32_t *status) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long ha = 2 * t, hb = 2 * t + 1;
+        if (pred[ha] != -1 || pred[hb] != -1) { *status = SX_ERR_NOT_SPANNING; continue; }
+        const long long down = rank[ha] < rank[hb] ? ha : hb;
+        y[dest[down]] = sum[down];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) y[root] = 0.0;
+}
+
+__global__ void tree_status_kernel(int32_t *status, int32_t v) { *status = v; }
+
+static int tr_grid(long long n) {
+    long long g = (n + kTrThreads - 1) / kTrThreads;
+    if (g > kNumSMs * 8) g = kNumSMs * 8;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace sx
+
+using namespace sx;
+
+extern "C" size_t sx_tree_potentials_workspace_bytes(int64_t N) {
+    if (N < 0) return 0;
+    const size_t H = 2 * (size_t)(N > 0 ? N : 1);
+    return 2 * carve_bytes(H, 8) + carve_bytes(H, 4) * 3 + carve_bytes((size_t)N + 1, 4) +
+           2 * carve_bytes(H, 8) + 4 * carve_bytes(H, 4) + sx_argsort_workspace_bytes((int64_t)H) + 512;
+}
+
+extern "C" int sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int32_t *tail, const int32_t *head,
+                                  int64_t S, int64_t D, int64_t N, const double *cost, int64_t ld,
+                                  int plus_convention, int64_t root, double *y_out, int32_t *status_out,
+                                  void *ws, size_t ws_bytes, void *stream) {
+    if (!y_out || !status_out || N <= 0 || root < 0 || root >= N || n_tree < 0) return SX_ERR_INVALID;
+    if ((tail == nullptr) != (head == nullptr)) return SX_ERR_INVALID;
+    if (!tail && (S <= 0 || D <= 0 || S + D != N || ld < D)) return SX_ERR_INVALID;
+    if (N >= (1ll << 30)) return SX_ERR_TOO_LARGE;
+    if (!ws || ws_bytes < sx_tree_potentials_workspace_bytes(N)) return SX_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tree != N - 1) {   // cannot be a spanning tree
+        tree_status_kernel<<<1, 1, 0, st>>>(status_out, SX_ERR_NOT_SPANNING);
+        SX_LAUNCH_CHECK();
+        return SX_OK;
+    }
+    tree_status_kernel<<<1, 1, 0, st>>>(status_out, 0);
+    SX_LAUNCH_CHECK();
+    if (N == 1) {
+        SX_CUDA(cudaMemsetAsync(y_out, 0, sizeof(double), st));
+        return SX_OK;
+    }
+    if (!tree || !cost) return SX_ERR_INVALID;
+    const long long T = n_tree, H = 2 * T;
+    Carver cv(ws);
+    TreeArrays a;
+    a.origin = cv.take<unsigned long long>(H);
+    a.sorted_origin = cv.take<unsigned long long>(H);
+    a.ho = cv.take<uint32_t>(H);
+    a.dest = cv.take<int>(H);
+    a.pos = cv.take<int>(H);
+    a.first = cv.take<int>(N + 1);
+    a.sum[0] = cv.take<double>(H); a.sum[1] = cv.take<double>(H);
+    a.rank[0] = cv.take<int>(H);   a.rank[1] = cv.take<int>(H);
+    a.pred[0] = cv.take<int>(H);   a.pred[1] = cv.take<int>(H);
+    void *sort_ws = cv.base + cv.off;
+    const size_t sort_ws_bytes = ws_bytes - cv.off;
+
+    tree_halfedges_kernel<<<tr_grid(T), kTrThreads, 0, st>>>((const long long *)tree, T, tail, head, S, D, cost, ld,
+                                                             plus_convention == SX_PLUS_IS_TAIL, a);
+    SX_LAUNCH_CHECK();
+    int bits = 1;
+    while (bits < 32 && (1ll << bits) < N) ++bits;
+    int rc = sx_argsort_u64(a.origin, H, bits, a.ho, a.sorted_origin, sort_ws, sort_ws_bytes, st);
+    if (rc != SX_OK) return rc;
+    SX_CUDA(cudaMemsetAsync(a.first, 0xff, sizeof(int) * (size_t)(N + 1), st));
+    tree_first_kernel<<<tr_grid(H), kTrThreads, 0, st>>>(H, a);
+    SX_LAUNCH_CHECK();
+    tree_succ_kernel<<<tr_grid(H), kTrThreads, 0, st>>>(H, a);
+    SX_LAUNCH_CHECK();
+    tree_cut_kernel<<<1, 1, 0, st>>>(root, a, status_out);
+    SX_LAUNCH_CHECK();
+    int rounds = 1;
+    while ((1ll << rounds) < H) ++rounds;
+    int cur = 0;
+    for (int r = 0; r < rounds; ++r, cur ^= 1) {
+        tree_jump_kernel<<<tr_grid(H), kTrThreads, 0, st>>>(H, a.sum[cur], a.rank[cur], a.pred[cur],
+                                                            a.sum[cur ^ 1], a.rank[cur ^ 1], a.pred[cur ^ 1]);
+        SX_LAUNCH_CHECK();
+    }
+    tree_finalize_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, root, a.sum[cur], a.rank[cur], a.pred[cur], a.dest,
+                                                            y_out, status_out);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}

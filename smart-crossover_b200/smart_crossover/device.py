@@ -1,0 +1,249 @@
+"""Device-side operators of the hot path: thin wrappers that hand torch CUDA tensors
+(device memory + the current stream; plumbing only) to the C ABI of libsxcross.
+
+Every function fails loudly without a CUDA device or without the native library;
+nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import check, lib
+
+TOL_RC = 1e-6   # TOLERANCE_FOR_REDUCED_COSTS, reference parameters.py:8
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("smart_crossover device path needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _f64(t, device=None):
+    """Contiguous float64 CUDA tensor from a tensor / ndarray."""
+    _require_cuda()
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64))
+    t = t.to(device=device or "cuda", dtype=torch.float64)
+    return t.contiguous()
+
+
+# ---- K1 ------------------------------------------------------------------------------------
+def score_ot(x: torch.Tensor, s: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+    """Flow indicators max(x_ij/s_i, x_ij/d_j); reference net_manager.py:377-378."""
+    S, D = s.numel(), d.numel()
+    out = torch.empty(S * D, dtype=torch.float64, device=x.device)
+    check(lib.sx_score_ot(_ptr(x), _ptr(s), _ptr(d), S, D, _ptr(out), _stream()), "sx_score_ot")
+    return out
+
+
+def score_mcf(x, u, tail, head, node_ptr, node_arc, node_sign) -> torch.Tensor:
+    """MCF flow indicators; reference net_manager.py:165-182."""
+    N, E = node_ptr.numel() - 1, x.numel()
+    out = torch.empty(E, dtype=torch.float64, device=x.device)
+    ws = _ws(lib.sx_score_mcf_workspace_bytes(N, E), x.device)
+    check(lib.sx_score_mcf(_ptr(x), _ptr(u), _ptr(tail), _ptr(head), _ptr(node_ptr), _ptr(node_arc),
+                           _ptr(node_sign), N, E, _ptr(out), _ptr(ws), ws.numel(), _stream()), "sx_score_mcf")
+    return out
+
+
+def argsort_f64(key: torch.Tensor, want_sorted=True):
+    """Stable ascending argsort (ties by ascending id). Returns (order uint32-as-int32 tensor, sorted keys)."""
+    n = key.numel()
+    order = torch.empty(n, dtype=torch.int32, device=key.device)   # holds uint32 bit patterns
+    sorted_key = torch.empty(n, dtype=torch.float64, device=key.device) if want_sorted else None
+    ws = _ws(lib.sx_argsort_workspace_bytes(n), key.device)
+    check(lib.sx_argsort_f64(_ptr(key), n, _ptr(order), _ptr(sorted_key), _ptr(ws), ws.numel(), _stream()),
+          "sx_argsort_f64")
+    return order, sorted_key
+
+
+def queue_from_order(order: torch.Tensor) -> torch.Tensor:
+    """queue = argsort(score)[::-1] as int64; reference net_manager.py:184,379."""
+    n = order.numel()
+    q = torch.empty(n, dtype=torch.int64, device=order.device)
+    check(lib.sx_queue_from_order(_ptr(order), n, _ptr(q), _stream()), "sx_queue_from_order")
+    return q
+
+
+def kruskal_order(sorted_key: torch.Tensor, order: torch.Tensor) -> torch.Tensor:
+    """Descending key, ties by ascending id (SciPy Kruskal visiting order, tree_BI.py:47,53)."""
+    n = order.numel()
+    out = torch.empty(n, dtype=torch.int32, device=order.device)
+    ws = _ws(lib.sx_kruskal_order_workspace_bytes(n), order.device)
+    check(lib.sx_kruskal_order(_ptr(sorted_key), _ptr(order), n, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "sx_kruskal_order")
+    return out
+
+
+# ---- K2 ------------------------------------------------------------------------------------
+def kruskal(korder: torch.Tensor, N: int, S: int = 0, D: int = 0, tail=None, head=None):
+    """Spanning forest over `korder`; returns (tree arc ids ascending [device, capacity N-1], n_tree [device])."""
+    n = korder.numel()
+    tree = torch.empty(max(N - 1, 1), dtype=torch.int64, device=korder.device)
+    n_tree = torch.zeros(1, dtype=torch.int64, device=korder.device)
+    ws = _ws(lib.sx_kruskal_workspace_bytes(N, n), korder.device)
+    check(lib.sx_kruskal(_ptr(korder), n, _ptr(tail), _ptr(head), S, D, N, _ptr(tree), _ptr(n_tree),
+                         _ptr(ws), ws.numel(), _stream()), "sx_kruskal")
+    return tree, n_tree
+
+
+# ---- K3 ------------------------------------------------------------------------------------
+def tree_potentials(tree: torch.Tensor, n_tree: int, N: int, cost: torch.Tensor, root: int, S: int = 0,
+                    D: int = 0, ld: int = 0, tail=None, head=None, plus=_native.SX_PLUS_IS_HEAD) -> torch.Tensor:
+    """y with y[root] = 0 and y[plus] - y[minus] = cost on every tree arc.
+    Raises SxError(SX_ERR_NOT_SPANNING) if the arcs are not a spanning tree."""
+    y = torch.zeros(N, dtype=torch.float64, device=cost.device)
+    status = torch.zeros(1, dtype=torch.int32, device=cost.device)
+    ws = _ws(lib.sx_tree_potentials_workspace_bytes(N), cost.device)
+    check(lib.sx_tree_potentials(_ptr(tree), n_tree, _ptr(tail), _ptr(head), S, D, N, _ptr(cost), ld or D,
+                                 plus, root, _ptr(y), _ptr(status), _ptr(ws), ws.numel(), _stream()),
+          "sx_tree_potentials")
+    check(int(status.item()), "sx_tree_potentials")
+    return y
+
+
+# ---- K4 ------------------------------------------------------------------------------------
+@dataclass
+class PriceResult:
+    n_violating: int
+    min_rc: float
+    topk_id: np.ndarray     # int64, ascending (rc, id)
+    topk_rc: np.ndarray     # float64
+    rc: torch.Tensor | None = None   # full reduced costs if requested (device)
+
+    @property
+    def optimal(self) -> bool:       # net_manager.py:318,496
+        return self.n_violating == 0
+
+
+class Pricer:
+    """Reusable buffers for repeated pricing passes over one problem (one CG loop)."""
+
+    def __init__(self, device, K: int, cand_cap: int | None = None):
+        _require_cuda()
+        self.device = device
+        self.K = int(K)
+        if cand_cap is None:
+            cand_cap = max(64 * self.K, 1 << 20) if self.K > 0 else 0
+        self.cap = int(cand_cap)
+        self._alloc()
+        self.header = torch.zeros(4, dtype=torch.int64, device=device)
+        self.out_rc = torch.empty(max(self.K, 1), dtype=torch.float64, device=device)
+        self.out_id = torch.empty(max(self.K, 1), dtype=torch.int64, device=device)
+        self.out_n = torch.zeros(1, dtype=torch.int64, device=device)
+        # pinned staging for the per-pass host round trip
+        self.h_header = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.h_rc = torch.empty(max(self.K, 1), dtype=torch.float64).pin_memory()
+        self.h_id = torch.empty(max(self.K, 1), dtype=torch.int64).pin_memory()
+        self.h_n = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+    def _alloc(self):
+        self.cand_rc = torch.empty(max(self.cap, 1), dtype=torch.float64, device=self.device)
+        self.cand_id = torch.empty(max(self.cap, 1), dtype=torch.int64, device=self.device)
+        self.ws = _ws(lib.sx_topk_workspace_bytes(self.cap, max(self.K, 1)), self.device)
+
+    def reset(self):
+        check(lib.sx_price_header_reset(_ptr(self.header), _stream()), "sx_price_header_reset")
+
+    def price_dense(self, M, ld, row0, S_loc, D, y_src, y_dst, tol=TOL_RC, rc_out=None, variant=-1):
+        check(lib.sx_price_dense_ot(_ptr(M), ld, row0, S_loc, D, _ptr(y_src), _ptr(y_dst), float(tol),
+                                    _ptr(self.header), _ptr(self.cand_rc), _ptr(self.cand_id), self.cap,
+                                    _ptr(rc_out), D if rc_out is not None else 0, variant, _stream()),
+              "sx_price_dense_ot")
+
+    def price_arcs(self, c, tail, head, vbasis, y, id0=0, tol=TOL_RC, rc_out=None):
+        check(lib.sx_price_arcs(_ptr(c), _ptr(tail), _ptr(head), _ptr(vbasis), _ptr(y), c.numel(), id0,
+                                float(tol), _ptr(self.header), _ptr(self.cand_rc), _ptr(self.cand_id),
+                                self.cap, _ptr(rc_out), _stream()), "sx_price_arcs")
+
+    def select(self):
+        """Enqueue the top-K selection over the compacted candidates (device only)."""
+        if self.K > 0:
+            check(lib.sx_topk_select(_ptr(self.cand_rc), _ptr(self.cand_id), _ptr(self.header), self.cap,
+                                     self.K, _ptr(self.out_rc), _ptr(self.out_id), _ptr(self.out_n),
+                                     _ptr(self.ws), self.ws.numel(), _stream()), "sx_topk_select")
+
+    def fetch(self) -> PriceResult:
+        """Device -> pinned host copy of the header and the top-K block; one synchronisation."""
+        self.h_header.copy_(self.header, non_blocking=True)
+        if self.K > 0:
+            self.h_rc.copy_(self.out_rc, non_blocking=True)
+            self.h_id.copy_(self.out_id, non_blocking=True)
+            self.h_n.copy_(self.out_n, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        nviol = int(self.h_header[0].item()) & 0xFFFFFFFFFFFFFFFF
+        min_rc = float(lib.sx_key_to_f64(int(self.h_header[1].item())))
+        k = int(self.h_n[0].item()) if self.K > 0 else 0
+        return PriceResult(nviol, min_rc, self.h_id[:k].numpy().copy(), self.h_rc[:k].numpy().copy())
+
+    def overflowed(self, res: PriceResult) -> bool:
+        return self.K > 0 and res.n_violating > self.cap
+
+    def grow(self, n_violating: int):
+        self.cap = int(n_violating)
+        self._alloc()
+
+
+def price_dense_ot(M: torch.Tensor, y: torch.Tensor, K: int = 0, tol: float = TOL_RC, want_rc=False,
+                   variant=-1, pricer: Pricer | None = None) -> PriceResult:
+    """One pricing pass over a device-resident S x D cost matrix with duals y (S + D).
+    rc_ij = M_ij - (y[S+j] - y[i]); reference net_manager.py:474-497."""
+    S, D = M.shape
+    pr = pricer or Pricer(M.device, K)
+    rc = torch.empty(S * D, dtype=torch.float64, device=M.device) if want_rc else None
+    while True:
+        pr.reset()
+        pr.price_dense(M, M.stride(0), 0, S, D, y[:S], y[S:S + D], tol, rc, variant)
+        pr.select()
+        res = pr.fetch()
+        if not pr.overflowed(res):
+            break
+        pr.grow(res.n_violating)   # more violators than candidate slots: size exactly, price again
+    res.rc = rc
+    return res
+
+
+def price_arcs(c, tail, head, y, vbasis=None, K: int = 0, tol: float = TOL_RC, want_rc=False,
+               pricer: Pricer | None = None) -> PriceResult:
+    """Arc-list pricing rc_k = c_k - (y[tail_k] - y[head_k]), negated where vbasis == -2;
+    reference net_manager.py:293-319."""
+    pr = pricer or Pricer(c.device, K)
+    rc = torch.empty(c.numel(), dtype=torch.float64, device=c.device) if want_rc else None
+    while True:
+        pr.reset()
+        pr.price_arcs(c, tail, head, vbasis, y, 0, tol, rc)
+        pr.select()
+        res = pr.fetch()
+        if not pr.overflowed(res):
+            break
+        pr.grow(res.n_violating)
+    res.rc = rc
+    return res
+
+
+def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor):
+    """Merge G sorted, padded top-K blocks (G x K) into one (rc, id, n) triple on the device."""
+    G, K = blocks_rc.shape
+    out_rc = torch.empty(K, dtype=torch.float64, device=blocks_rc.device)
+    out_id = torch.empty(K, dtype=torch.int64, device=blocks_rc.device)
+    out_n = torch.zeros(1, dtype=torch.int64, device=blocks_rc.device)
+    check(lib.sx_topk_merge(_ptr(blocks_rc), _ptr(blocks_id), G, K, _ptr(out_rc), _ptr(out_id), _ptr(out_n),
+                            _stream()), "sx_topk_merge")
+    return out_rc, out_id, out_n

@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI of libsxcross) against the CPU oracle and the
+golden vectors produced by the reference.  Run on a B200: `pytest -m gpu`.
+
+Bars (BASELINE.json north_star): sorted arc order, tree arc set and selected column set
+bit-exact; reduced costs bitwise for the same duals; potentials within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import cases
+from golden_util import MCF_FULL, OT_FULL, Fixture, c2_inputs, digests, mcf_mid_inputs
+from oracle import network_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from smart_crossover import device
+    return device
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def u32(t):
+    """uint32 bit patterns stored in an int32 tensor -> int64 numpy."""
+    return t.cpu().numpy().view(np.uint32).astype(np.int64)
+
+
+def sort_pipeline(dev, key_t):
+    order, skey = dev.argsort_f64(key_t)
+    queue = dev.queue_from_order(order)
+    korder = dev.kruskal_order(skey, order)
+    return order, skey, queue, korder
+
+
+# ---- K1a + K1c ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", OT_FULL + ["ot_zero_3x3"])
+def test_ot_scores_and_orders_golden(dev, name):
+    fx = Fixture(name)
+    s, d, x = fx.inp["s"], fx.inp["d"], fx.inp["x"]
+    F = dev.score_ot(cu(x), cu(s), cu(d))
+    assert F.cpu().numpy().tobytes() == fx.out["scores"].tobytes()
+    order, skey, queue, korder = sort_pipeline(dev, F)
+    assert np.array_equal(queue.cpu().numpy(), fx.out["queue"])
+    assert np.array_equal(u32(korder), orc.kruskal_order(fx.out["scores"]))
+    assert skey.cpu().numpy().tobytes() == np.sort(fx.out["scores"], kind="stable").tobytes()
+
+
+def test_c2_784_scores_queue_tree_potentials(dev):
+    s, d, M, x = c2_inputs()
+    dg = digests()["ot_c2_784"]["digests"]
+    small = Fixture("ot_c2_784_small").out
+    S, D = M.shape
+    F = dev.score_ot(cu(x), cu(s), cu(d))
+    assert cases.digest(F.cpu().numpy()) == dg["scores"]
+    order, skey, queue, korder = sort_pipeline(dev, F)
+    assert cases.digest(queue.cpu().numpy()) == dg["queue"]
+    tree, n_tree = dev.kruskal(korder, S + D, S=S, D=D)
+    nt = int(n_tree.item())
+    assert nt == S + D - 1
+    assert np.array_equal(tree[:nt].cpu().numpy(), small["tree"])
+    y = dev.tree_potentials(tree, nt, S + D, cu(M), S + D - 1, S=S, D=D)
+    np.testing.assert_allclose(y.cpu().numpy(), small["y_tree"], rtol=RTOL, atol=RTOL * M.max())
+    # pricing against the stored perturbed duals: digest of the full rc vector, count, min, top-k
+    res = dev.price_dense_ot(cu(M), cu(small["y_pert"]), K=256, want_rc=True)
+    assert cases.digest(res.rc.cpu().numpy()) == dg["rc_pert"]
+    assert res.n_violating == int(small["count_pert"])
+    assert res.min_rc == float(small["min_rc_pert"])
+    assert np.array_equal(res.topk_id, small["topk_ids_pert"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 70001, 1 << 20])
+def test_argsort_edge_sizes_and_special_values(dev, n):
+    rng = np.random.default_rng(n)
+    key = rng.integers(-3, 4, size=n).astype(np.float64) * rng.choice([0.5, 1.0, 1e-300], size=n)
+    if n > 8:
+        key[::7] = 0.0
+        key[3::11] = -0.0
+        key[5::13] = np.inf
+        key[6::17] = -np.inf
+        key[2::19] = np.nan
+    order, skey, queue, korder = sort_pipeline(dev, cu(key))
+    ref = np.argsort(key, kind="stable")
+    assert np.array_equal(u32(order), ref)
+    assert np.array_equal(queue.cpu().numpy(), ref[::-1])
+    got = skey.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(key[ref]))
+    assert np.array_equal(got[~np.isnan(got)], key[ref][~np.isnan(got)])
+    if not np.isnan(key).any():
+        assert np.array_equal(u32(korder), orc.kruskal_order(key))
+
+
+def test_kruskal_order_long_runs(dev):
+    """Tie runs longer than a thread block and crossing block boundaries."""
+    n = 50000
+    key = np.repeat(np.array([3.0, 1.0, 2.0, 2.0, 0.5]), n // 5)
+    key[12345] = 7.0
+    order, skey, queue, korder = sort_pipeline(dev, cu(key))
+    assert np.array_equal(u32(korder), orc.kruskal_order(key))
+    key = np.zeros(20000)
+    order, skey, queue, korder = sort_pipeline(dev, cu(key))
+    assert np.array_equal(u32(korder), np.arange(20000))
+
+
+# ---- K2 / K3 -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", OT_FULL + ["ot_zero_3x3"])
+def test_tree_and_potentials_golden(dev, name):
+    fx = Fixture(name)
+    M = fx.inp["M"]
+    S, D = M.shape
+    F = cu(fx.out["scores"])
+    order, skey, queue, korder = sort_pipeline(dev, F)
+    tree, n_tree = dev.kruskal(korder, S + D, S=S, D=D)
+    nt = int(n_tree.item())
+    got = tree[:nt].cpu().numpy()
+    assert nt == S + D - 1
+    # the reference drops zero-weight tree arcs; the host mirror applies the same filter
+    assert np.array_equal(got[fx.out["scores"][got] != 0], fx.out["tree"])
+    assert np.array_equal(got, orc.max_weight_spanning_tree(fx.out["scores"], S, D, drop_zero_weight=False))
+    if "y_tree" in fx.out:
+        y = dev.tree_potentials(tree, nt, S + D, cu(M), S + D - 1, S=S, D=D)
+        np.testing.assert_allclose(y.cpu().numpy(), fx.out["y_tree"], rtol=RTOL, atol=RTOL * np.abs(M).max())
+
+
+@pytest.mark.parametrize("N,E,seed", [(50, 49, 1), (300, 2000, 2), (5000, 40000, 3), (20000, 25000, 4)])
+def test_kruskal_general_graph(dev, N, E, seed):
+    """Arc-list endpoints (C3 shape), possibly disconnected: forest equals sequential Kruskal."""
+    rng = np.random.default_rng(seed)
+    tail = rng.integers(0, N, size=E)
+    head = (tail + 1 + rng.integers(0, N - 1, size=E)) % N
+    w = rng.integers(1, 50, size=E).astype(np.float64)       # heavy ties
+    order, skey, queue, korder = sort_pipeline(dev, cu(w))
+    tree, n_tree = dev.kruskal(korder, N, tail=cu(tail, torch.int32), head=cu(head, torch.int32))
+    nt = int(n_tree.item())
+    ref = orc.spanning_forest(orc.kruskal_order(w), N, tail=tail, head=head)
+    assert nt == ref.size
+    assert np.array_equal(tree[:nt].cpu().numpy(), ref)
+    if nt == N - 1:
+        cost = rng.integers(1, 100, size=E).astype(np.float64)
+        y = dev.tree_potentials(tree, nt, N, cu(cost), N - 1, tail=cu(tail, torch.int32),
+                                head=cu(head, torch.int32), plus=1)
+        yr = orc.tree_potentials(tail[ref], head[ref], cost[ref], N, N - 1)
+        np.testing.assert_allclose(y.cpu().numpy(), yr, rtol=RTOL, atol=RTOL * 100)
+
+
+def test_tree_potentials_rejects_non_spanning(dev):
+    from smart_crossover._native import SxError, SX_ERR_NOT_SPANNING
+    S = D = 4
+    M = np.arange(16, dtype=np.float64).reshape(4, 4)
+    # 7 arcs containing a 4-cycle (0,0),(0,1),(1,0),(1,1): not a tree
+    tree = np.array([0, 1, 4, 5, 10, 11, 15], dtype=np.int64)
+    with pytest.raises(SxError) as ei:
+        dev.tree_potentials(cu(tree), 7, S + D, cu(M), S + D - 1, S=S, D=D)
+    assert ei.value.code == SX_ERR_NOT_SPANNING
+    with pytest.raises(SxError):
+        dev.tree_potentials(cu(tree[:5]), 5, S + D, cu(M), S + D - 1, S=S, D=D)
+
+
+# ---- K4 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", OT_FULL)
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2])
+def test_price_dense_golden(dev, name, variant):
+    fx = Fixture(name)
+    M = fx.inp["M"]
+    S, D = M.shape
+    if variant in (0, 1) and D % 2:
+        from smart_crossover._native import SxError
+        with pytest.raises(SxError):
+            dev.price_dense_ot(cu(M), cu(fx.out["y_pert"]), K=8, variant=variant)
+        return
+    for tag in ("tree", "pert"):
+        res = dev.price_dense_ot(cu(M), cu(fx.out["y_" + tag]), K=64, want_rc=True, variant=variant)
+        rc_ref = fx.out["rc_" + tag]
+        assert res.rc.cpu().numpy().tobytes() == rc_ref.tobytes()      # bitwise
+        cnt, mn, ids, vals = orc.price_summary(rc_ref, K=64)
+        assert res.n_violating == cnt and res.min_rc == mn
+        assert res.optimal == bool(fx.out["optimal_" + tag])
+        assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+
+
+@pytest.mark.parametrize("S,D,K,noise", [(1, 1, 4, 0.5), (3, 700, 16, 0.3), (257, 513, 1024, 0.2),
+                                         (1000, 1002, 5000, 0.05), (2049, 4100, 100, 0.01),
+                                         (4096, 4096, 1024, 0.0)])
+@pytest.mark.parametrize("variant", [-1, 1, 2])
+def test_price_dense_random_shapes(dev, S, D, K, noise, variant):
+    if variant == 1 and D % 2:
+        pytest.skip("vector loads need an even leading dimension")
+    s, d, M = cases.ot_points(S, D, 1000 + S)
+    y = cases.planted_duals(M, S, noise)
+    rc_ref = orc.reduced_costs_ot(M, y)
+    cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
+    res = dev.price_dense_ot(cu(M), cu(y), K=K, want_rc=(S * D < 2_000_000), variant=variant)
+    assert res.n_violating == cnt and res.min_rc == mn
+    assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+    if res.rc is not None:
+        assert res.rc.cpu().numpy().tobytes() == rc_ref.tobytes()
+    if noise == 0.0:
+        assert res.optimal
+
+
+def test_price_tied_reduced_costs_and_overflow(dev):
+    """Integer costs and duals: massive rc ties (broken by arc id); candidate buffer smaller
+    than the violator count forces the exact re-pricing path."""
+    s, d, M = cases.ot_grid(12, 5)          # 144 x 144, integer costs
+    rng = np.random.default_rng(5)
+    y = rng.integers(-40, 40, size=288).astype(np.float64)
+    rc_ref = orc.reduced_costs_ot(M, y)
+    for K in (7, 512, 3000):
+        cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
+        pr = dev.Pricer(torch.device("cuda"), K, cand_cap=100)
+        res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
+        assert cnt > 100 and pr.cap >= cnt
+        assert res.n_violating == cnt and np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+
+
+def test_price_row_slabs_and_merge(dev):
+    """Row-sharded pricing: G slabs priced separately, per-slab top-K merged == single pass."""
+    S, D, K, G = 1000, 768, 128, 4
+    s, d, M = cases.ot_points(S, D, 77)
+    y = cases.planted_duals(M, 77, 0.05)
+    Mt, yt = cu(M), cu(y)
+    whole = dev.price_dense_ot(Mt, yt, K=K)
+    blocks_rc, blocks_id, total = [], [], 0
+    rows = S // G
+    for g in range(G):
+        pr = dev.Pricer(torch.device("cuda"), K)
+        pr.reset()
+        pr.price_dense(Mt[g * rows:(g + 1) * rows], D, g * rows, rows, D, yt[g * rows:(g + 1) * rows], yt[S:])
+        pr.select()
+        r = pr.fetch()
+        total += r.n_violating
+        blocks_rc.append(pr.out_rc.clone())
+        blocks_id.append(pr.out_id.clone())
+    out_rc, out_id, out_n = dev.topk_merge(torch.stack(blocks_rc), torch.stack(blocks_id))
+    k = int(out_n.item())
+    assert total == whole.n_violating
+    assert np.array_equal(out_id[:k].cpu().numpy(), whole.topk_id)
+    assert np.array_equal(out_rc[:k].cpu().numpy(), whole.topk_rc)
+
+
+@pytest.mark.parametrize("name", MCF_FULL)
+def test_mcf_scores_queue_and_arc_pricing_golden(dev, name):
+    import scipy.sparse as sp
+    fx = Fixture(name)
+    tail, head, b, c, u, x = (fx.inp[k] for k in ("tail", "head", "b", "c", "u", "x"))
+    N, E = b.size, c.size
+    A = sp.csr_matrix((np.concatenate([np.ones(E), -np.ones(E)]),
+                       (np.concatenate([tail, head]), np.concatenate([np.arange(E)] * 2))), shape=(N, E))
+    A.sort_indices()
+    ind = dev.score_mcf(cu(x), cu(u), cu(tail, torch.int32), cu(head, torch.int32), cu(A.indptr, torch.int64),
+                        cu(A.indices, torch.int32), cu(A.data, torch.int8))
+    assert ind.cpu().numpy().tobytes() == fx.out["scores"].tobytes()
+    order, skey, queue, korder = sort_pipeline(dev, ind)
+    assert np.array_equal(queue.cpu().numpy(), fx.out["queue"])
+    res = dev.price_arcs(cu(c), cu(tail, torch.int32), cu(head, torch.int32), cu(fx.out["y"]),
+                         vbasis=cu(fx.out["vbasis"], torch.int8), K=32, want_rc=True)
+    assert res.rc.cpu().numpy().tobytes() == fx.out["rc"].tobytes()
+    cnt, mn, ids, vals = orc.price_summary(fx.out["rc"], K=32)
+    assert res.n_violating == cnt and res.min_rc == mn and res.optimal == bool(fx.out["optimal"])
+    assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+
+
+def test_mcf_mid_digests(dev):
+    import scipy.sparse as sp
+    tail, head, b, c, u, x = mcf_mid_inputs()
+    dg = digests()["mcf_mid_20k"]["digests"]
+    N, E = b.size, c.size
+    A = sp.csr_matrix((np.concatenate([np.ones(E), -np.ones(E)]),
+                       (np.concatenate([tail, head]), np.concatenate([np.arange(E)] * 2))), shape=(N, E))
+    A.sort_indices()
+    ind = dev.score_mcf(cu(x), cu(u), cu(tail, torch.int32), cu(head, torch.int32), cu(A.indptr, torch.int64),
+                        cu(A.indices, torch.int32), cu(A.data, torch.int8))
+    assert cases.digest(ind.cpu().numpy()) == dg["scores"]
+    order, skey, queue, korder = sort_pipeline(dev, ind)
+    assert cases.digest(queue.cpu().numpy()) == dg["queue"]
+    small = Fixture("mcf_mid_20k_small").out
+    vb = np.zeros(E, dtype=np.int8)   # digest of rc was taken with the stored vbasis; count only here
+    res = dev.price_arcs(cu(c), cu(tail, torch.int32), cu(head, torch.int32), cu(small["y"]), K=0)
+    rc = orc.reduced_costs_arcs(c, tail, head, small["y"])
+    assert res.n_violating == int((rc < -1e-6).sum())
+
+
+# ---- full-size property tests (BASELINE.json configs[3]: 20 000 x 20 000, 3.2 GB) -------------------
+def test_c4_full_size_planted_violators(dev):
+    """No oracle pass at this size: plant a known set of violators into a dual-feasible instance
+    and require the pricing pass to return exactly that set, in order."""
+    S = D = 20000
+    g = torch.Generator(device="cuda").manual_seed(20260004)
+    P = torch.rand(S, 2, generator=g, device="cuda", dtype=torch.float64)
+    Q = torch.rand(D, 2, generator=g, device="cuda", dtype=torch.float64)
+    M = torch.empty(S, D, dtype=torch.float64, device="cuda")
+    for r0 in range(0, S, 2000):
+        dx = P[r0:r0 + 2000, 0:1] - Q[None, :, 0]
+        dy = P[r0:r0 + 2000, 1:2] - Q[None, :, 1]
+        M[r0:r0 + 2000] = dx * dx + dy * dy
+    a = torch.rand(S, generator=g, device="cuda", dtype=torch.float64)
+    b = torch.full((D,), float("inf"), dtype=torch.float64, device="cuda")
+    for r0 in range(0, S, 2000):
+        b = torch.minimum(b, (M[r0:r0 + 2000] + a[r0:r0 + 2000, None]).min(dim=0).values)
+    b = b - 1e-3                                  # strictly feasible: rc >= 1e-3 everywhere
+    y = torch.cat([a, b])
+    res = dev.price_dense_ot(M, y, K=512)
+    assert res.optimal and res.n_violating == 0 and res.min_rc >= 1e-3 - 1e-12
+    # plant 300 violators with distinct, known reduced costs
+    rng = np.random.default_rng(4)
+    ids = np.sort(rng.choice(S * D, size=300, replace=False))
+    i, j = ids // D, ids % D
+    want_rc = -(1.0 + rng.permutation(300).astype(np.float64))      # -1 .. -300
+    yi, yj = a[cu(i)], b[cu(j)]
+    M[cu(i), cu(j)] = cu(want_rc) + (yj - yi)
+    got = dev.price_dense_ot(M, y, K=512)
+    rc_exact = (M[cu(i), cu(j)] - (yj - yi)).cpu().numpy()
+    o = np.lexsort((ids, rc_exact))
+    assert got.n_violating == 300
+    assert np.array_equal(got.topk_id, ids[o]) and np.array_equal(got.topk_rc, rc_exact[o])
+    assert got.min_rc == rc_exact.min()
+    for variant in (1, 2):
+        alt = dev.price_dense_ot(M, y, K=512, variant=variant)
+        assert alt.n_violating == 300 and np.array_equal(alt.topk_id, got.topk_id)
+
+
+def test_large_sort_properties(dev):
+    """2^25 keys: output is a permutation, keys non-decreasing, ties in ascending id."""
+    n = 1 << 25
+    g = torch.Generator(device="cuda").manual_seed(7)
+    key = torch.randint(0, 1 << 20, (n,), generator=g, device="cuda").to(torch.float64) / 1024.0
+    order, skey = dev.argsort_f64(key)
+    idx = order.to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(key[idx], skey)
+    assert bool((skey[1:] >= skey[:-1]).all())
+    same = skey[1:] == skey[:-1]
+    assert bool((idx[1:][same] > idx[:-1][same]).all())
+    assert int(torch.bincount(idx, minlength=n).max().item()) == 1
