@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the network-crossover hot path on B200.
+
+Metric (BASELINE.json): OT arcs priced/s (with % of the HBM roofline) + tree-basis build ms.
+Workload: dense synthetic OT 60 000 x 60 000 (3.6e9 arcs, 28.8 GB fp64 cost; BASELINE.json
+configs[4], the largest configuration the metric is quoted on and it fits one 180 GB GPU),
+row-sharded over N ranks (strong scaling: the matrix is fixed, each rank prices S/N rows).
+A "step" is one column-generation pricing pass over the whole matrix: reduced costs of every
+arc against the duals, violator count, min reduced cost and the global top-K most violating
+arcs (NCCL all-gather + merge when N > 1).
+
+    python bench.py --gpus 1 --steps 200 --warmup 10
+    python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 ...
+    python bench.py --impl reference ...        # CPU arm: the oracle port on all host cores
+
+`value`   : arcs/s with everything resident in HBM (duals included), device-timed.
+`e2e`     : the same pass through the public call (`ShardedDensePricer.price`) with the duals in
+            pinned host memory: H2D of y and D2H of (count, min, top-K) inside every step.
+            The cost matrix is uploaded once per problem (manager state, like `ot.M` in the
+            reference's `OTManager`), not per pricing pass; `e2e_cold` adds that upload.
+`roofline`: achieved HBM GB/s of the pricing kernel alone (8 B per arc / CUDA-event time).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "smart-crossover_b200"), os.path.join(ROOT, "tests", "golden")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ot_arcs_priced_per_s"
+UNIT = "arcs/s"
+TOL = 1e-6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=60000, help="S = D of the dense OT instance")
+    ap.add_argument("--topk", type=int, default=1024)
+    ap.add_argument("--variant", type=int, default=-1, help="-1 auto (TMA), 0 TMA, 1 vector loads, 2 scalar loads")
+    ap.add_argument("--violators", type=float, default=1e-4, help="target fraction of violating arcs")
+    ap.add_argument("--no-tree", action="store_true", help="skip the tree-basis build timings")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    sm.append(float(c[0])); mx.append(float(c[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, c[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic instance: squared-Euclidean cost between uniform points, planted duals
+# ------------------------------------------------------------------------------------------------
+def make_points(S, D, device, seed=20260005):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    P = torch.rand(S, 2, generator=g, device=device, dtype=torch.float64)
+    Q = torch.rand(D, 2, generator=g, device=device, dtype=torch.float64)
+    a = torch.rand(S, generator=g, device=device, dtype=torch.float64)
+    return P, Q, a
+
+
+def cost_rows(P, Q, r0, r1):
+    dx = P[r0:r1, 0:1] - Q[None, :, 0]
+    dy = P[r0:r1, 1:2] - Q[None, :, 1]
+    return dx * dx + dy * dy
+
+
+def make_slab(P, Q, row0, S_loc, out=None, block=1000):
+    import torch
+    D = Q.shape[0]
+    M = out if out is not None else torch.empty(S_loc, D, dtype=torch.float64, device=P.device)
+    for r in range(0, S_loc, block):
+        e = min(S_loc, r + block)
+        M[r:e] = cost_rows(P, Q, row0 + r, row0 + e)
+    return M
+
+
+def planted_duals(P, Q, a, M_loc, row0, frac, world, sample_rows=1500):
+    """y = (a, b + delta): b_j = min_i (M_ij + a_i) makes every reduced cost >= 0 and tight once per
+    column; delta >= 0 is bisected so that about `frac` of the arcs end up with rc < -tol."""
+    import torch
+    import torch.distributed as dist
+    S_loc, D = M_loc.shape
+    b = torch.full((D,), float("inf"), dtype=torch.float64, device=M_loc.device)
+    for r in range(0, S_loc, 1000):
+        e = min(S_loc, r + 1000)
+        b = torch.minimum(b, (M_loc[r:e] + a[row0 + r:row0 + e, None]).min(dim=0).values)
+    if world > 1:
+        dist.all_reduce(b, op=dist.ReduceOp.MIN)
+    if frac <= 0:
+        return torch.cat([a, b - 1e-3])
+    R = min(sample_rows, P.shape[0])
+    rc0 = cost_rows(P, Q, 0, R) - (b[None, :] - a[:R, None])       # same rows on every rank
+    lo, hi = 0.0, 1.0
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        f = float((rc0 < mid - TOL).sum().item()) / rc0.numel()
+        lo, hi = (mid, hi) if f < frac else (lo, mid)
+    return torch.cat([a, b + hi])
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port): cpu_baseline (1 thread, rank 0) and --impl reference (all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_price_rate(M_h, y_h, K, threads, reps):
+    from oracle import network_oracle as orc
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.price_dense_ot_blocked(M_h, y_h, K, TOL, threads=threads, block_rows=64)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return M_h.size / best, best
+
+
+def run_reference(args):
+    """Reference arm: the reference's pricing pass (`c - A.T @ y`, `np.all(rc >= -tol)`,
+    net_manager.py:474-497) as restated by the oracle (bitwise-equal dense form),
+    on all host threads, over a bounded row sample of the same 60 000-column instance."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S = D = args.size
+    threads = os.cpu_count() or 1
+    rng = np.random.default_rng(20260005)
+    rows = 512
+    Q = rng.random((D, 2)); P = rng.random((rows, 2)); a = rng.random(rows)
+    M = (P[:, 0:1] - Q[None, :, 0]) ** 2 + (P[:, 1:2] - Q[None, :, 1]) ** 2
+    b = (M + a[:, None]).min(axis=0) + 2e-3
+    y = np.concatenate([a, b])
+    rate, dt = cpu_price_rate(M, y, args.topk, threads, 1)
+    # size the per-step sample so that steps + warmup take about two minutes
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    rows2 = int(min(S, max(256, rows * budget / dt)))
+    rows2 = min(rows2, 8192)
+    if rows2 != rows:
+        P = rng.random((rows2, 2)); a = rng.random(rows2)
+        M = (P[:, 0:1] - Q[None, :, 0]) ** 2 + (P[:, 1:2] - Q[None, :, 1]) ** 2
+        b = (M + a[:, None]).min(axis=0) + 2e-3
+        y = np.concatenate([a, b])
+    from oracle import network_oracle as orc
+    for _ in range(args.warmup):
+        orc.price_dense_ot_blocked(M, y, args.topk, TOL, threads=threads, block_rows=64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.price_dense_ot_blocked(M, y, args.topk, TOL, threads=threads, block_rows=64)
+    dt = time.perf_counter() - t0
+    value = M.size * args.steps / dt
+    sample = f"{rows2} of {S} rows x {D} cols per step ({M.size:.3g} arcs), oracle port, NumPy row blocks"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"dense synthetic OT {S}x{D} pricing pass (row sample)", "S": S, "D": D,
+                       "topk": args.topk, "tol": TOL},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# tree-basis build timing (single GPU): scores -> argsort -> Kruskal order -> tree -> potentials
+# ------------------------------------------------------------------------------------------------
+def time_tree_build(S, D, device, reps=3):
+    import torch
+    from smart_crossover import device as dev
+    P, Q, a = make_points(S, D, device, seed=20260002)
+    M = make_slab(P, Q, 0, S)
+    g = torch.Generator(device=device).manual_seed(99)
+    s = torch.rand(S, generator=g, device=device, dtype=torch.float64) + 0.1
+    d = torch.rand(D, generator=g, device=device, dtype=torch.float64) + 0.1
+    s /= s.sum(); d /= d.sum()
+    t = 1.0 + 40.0 * (M / 0.33)
+    x = ((s[:, None] * d[None, :]) / (t * t * t * t)).reshape(-1)
+    x *= 1.0 + 1e-3 * torch.rand(x.shape, generator=g, device=device, dtype=torch.float64)
+    del t
+    best = None
+    for _ in range(reps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        F = dev.score_ot(x, s, d)
+        ev[1].record()
+        order, skey = dev.argsort_f64(F)
+        ev[2].record()
+        korder = dev.kruskal_order(skey, order)
+        ev[3].record()
+        tree, n_tree = dev.kruskal(korder, S + D, S=S, D=D)
+        ev[4].record()
+        nt = S + D - 1
+        y = dev.tree_potentials(tree, nt, S + D, M, S + D - 1, S=S, D=D)
+        ev[5].record()
+        torch.cuda.synchronize()
+        parts = [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
+        assert int(n_tree.item()) == nt
+        if best is None or sum(parts) < sum(best):
+            best = parts
+        del F, order, skey, korder, tree, y
+    names = ["score", "argsort", "kruskal_order", "kruskal", "potentials"]
+    return {"workload": f"OT {S}x{D} ({S * D} arcs)", "ms": round(sum(best), 4),
+            "breakdown_ms": {n: round(v, 4) for n, v in zip(names, best)}}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the device path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    from smart_crossover import device as dev
+    from smart_crossover._native import lib
+    from smart_crossover.network_methods.sharded import ShardedDensePricer, row_partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S = D = args.size
+    K = args.topk
+    row0, S_loc = row_partition(S, world, rank)
+    P, Q, a = make_points(S, D, device)
+    M_loc = make_slab(P, Q, row0, S_loc)
+    y_dev = planted_duals(P, Q, a, M_loc, row0, args.violators, world)
+    y_host = y_dev.cpu().numpy()
+    sp = ShardedDensePricer(M_loc, S, row0, K, TOL, variant=args.variant)
+
+    if args.sweep:
+        sweep(args, sp, y_dev, S_loc, D, lib, dev)
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # ---- device-resident arm ---------------------------------------------------------------------
+    for _ in range(warmup):
+        sp.enqueue(y_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sp.launches
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        out = sp.enqueue(y_dev, kernel_events=(k0[i], k1[i]))
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = sp.launches - launches0
+    kern_ms = float(np.mean([k0[i].elapsed_time(k1[i]) for i in range(steps)]))
+    count_dev = int(out[3].item())
+    value = S * D * steps / (ms_total * 1e-3)
+
+    # ---- end-to-end arm: duals from pinned host memory, result back to the host every step ---------
+    for _ in range(3):
+        res = sp.price(y_host)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        res = sp.price(y_host)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = S * D * steps / (e2e_ms * 1e-3)
+    assert res.n_violating == count_dev
+
+    # ---- cold end-to-end: also upload this rank's slab of M from pinned host memory (once per problem)
+    cold = None
+    if rank == 0 or world > 1:
+        rows_c = min(S_loc, 4000)                       # bounded pinned sample; scaled to the slab
+        h_M = torch.empty(rows_c, D, dtype=torch.float64).pin_memory()
+        h_M.copy_(M_loc[:rows_c])
+        barrier()
+        e0.record()
+        M_loc[:rows_c].copy_(h_M, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        up_ms = e0.elapsed_time(e1) * (S_loc / rows_c)
+        cold = {"value": S * D / ((max_over_ranks(up_ms) + e2e_ms / steps) * 1e-3), "unit": UNIT,
+                "h2d_bytes": 8 * S_loc * D, "note": f"upload time scaled from a {rows_c}-row pinned sample"}
+        del h_M
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    achieved = 8.0 * S_loc * D / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel": "price_dense_tma_kernel" if args.variant in (-1, 0) else "price_dense_direct_kernel",
+                "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_arc": 8,
+                "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
+
+    cpu_baseline = None
+    if not args.no_cpu:
+        rows_h = min(S_loc, 2048)
+        M_h = M_loc[:rows_h].cpu().numpy()
+        y_h = np.concatenate([y_host[row0:row0 + rows_h], y_host[S:]])
+        rate, dt = cpu_price_rate(M_h, y_h, K, 1, 2)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"first {rows_h} of {S} rows x {D} cols ({M_h.size:.3g} arcs), best of 2, "
+                                  f"oracle NumPy restatement of net_manager.py:474-497, host has {os.cpu_count()} cpus"}
+        del M_h
+
+    tree = None
+    if world == 1 and not args.no_tree:
+        del sp, M_loc
+        torch.cuda.empty_cache()
+        tree = [time_tree_build(784, 784, device), time_tree_build(20000, 20000, device, reps=1)]
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"dense synthetic OT {S}x{D} ({S * D:.3g} arcs, {8 * S * D / 1e9:.1f} GB fp64 cost) "
+                                   f"column-generation pricing pass, row-sharded over {world} GPU(s)",
+                       "S": S, "D": D, "topk": K, "tol": TOL, "violating_arcs": count_dev,
+                       "rows_per_gpu": S_loc, "variant": args.variant,
+                       "l2": f"inputs larger than L2 ({8 * S_loc * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sp_h2d(S, D),
+                    "d2h_bytes_per_step": 8 * (2 * max(K, 1) + 4), "ms_per_step": e2e_ms / steps,
+                    "inputs": "duals y (S+D fp64) from pinned host memory every step; cost matrix resident "
+                              "(uploaded once per problem, see e2e_cold)"},
+            "e2e_cold": cold, "gpu_launches": launches, "clocks": clocks, "tree_build": tree}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sp_h2d(S, D):
+    return 8 * (S + D)
+
+
+def sweep(args, sp, y_dev, S_loc, D, lib, dev):
+    """Pricing-kernel variants and tunings, kernel-only GB/s (CUDA events, 20 reps after 3 warm-ups)."""
+    import torch
+    res = []
+    confs = [("tma", 0, (16, 6, 0)), ("tma", 0, (16, 4, 0)), ("tma", 0, (8, 8, 0)), ("tma", 0, (8, 12, 0)),
+             ("tma", 0, (32, 3, 0)), ("vec", 1, (0, 0, 4)), ("vec", 1, (0, 0, 8)), ("vec", 1, (0, 0, 16)),
+             ("scalar", 2, (0, 0, 8)), ("scalar", 2, (0, 0, 16))]
+    for name, variant, tune in confs:
+        lib.sx_price_set_tuning(*tune)
+        sp.variant = variant
+        for _ in range(3):
+            sp.enqueue(y_dev)
+        torch.cuda.synchronize()
+        k0 = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
+        k1 = [torch.cuda.Event(enable_timing=True) for _ in range(20)]
+        for i in range(20):
+            sp.enqueue(y_dev, kernel_events=(k0[i], k1[i]))
+        torch.cuda.synchronize()
+        ms = [k0[i].elapsed_time(k1[i]) for i in range(20)]
+        gbs = 8.0 * S_loc * D / (np.median(ms) * 1e-3) / 1e9
+        res.append({"variant": name, "tuning": tune, "kernel_ms_median": round(float(np.median(ms)), 4),
+                    "kernel_ms_min": round(float(min(ms)), 4), "GBs": round(gbs, 1)})
+        print(json.dumps(res[-1]), flush=True)
+    lib.sx_price_set_tuning(16, 6, 8)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,132 @@
+"""Row-sharded dense OT pricing across GPUs (one process per GPU, `torch.distributed` / NCCL).
+
+BASELINE.json north_star: "Dense OT pricing is row-sharded across the 8 B200s, with the
+local top-k candidates merged by an NCCL allgather over NVLink, while the tree build and
+potentials stay on one GPU."  Rank g owns rows [row0, row0 + S_loc) of the S x D cost matrix
+as one contiguous slab in its HBM; a pricing pass is
+
+    y (S + D fp64, <= 1 MB) on every rank
+      -> sx_price_dense_ot over the slab   (count, min, violator compaction)
+      -> sx_topk_select                    (local K best, padded block)
+      -> all_gather of one packed block per rank: K rc + K ids + (count, min key) = 16 K + 16 B
+      -> sx_topk_merge over the G blocks   (rank merge; result independent of G)
+
+With world size 1 the collective and the merge are skipped.  The reference has no
+counterpart (single process, `net_manager.py:485-497` prices every arc on one core).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import device as dev
+from .._native import lib
+
+
+def row_partition(S: int, world: int, rank: int):
+    """Contiguous, balanced row range of `rank`: rows [S*rank/world, S*(rank+1)/world)."""
+    lo = S * rank // world
+    hi = S * (rank + 1) // world
+    return lo, hi - lo
+
+
+def pack_block(out_rc: torch.Tensor, out_id: torch.Tensor, header: torch.Tensor, buf: torch.Tensor):
+    """[K rc bits | K ids | n_violating | min key] as int64 (bit-preserving)."""
+    K = out_rc.numel()
+    buf[:K].copy_(out_rc.view(torch.int64))
+    buf[K:2 * K].copy_(out_id)
+    buf[2 * K:2 * K + 2].copy_(header[:2])
+    return buf
+
+
+def unpack_blocks(gathered: torch.Tensor, K: int):
+    """(G, 2K+2) int64 -> contiguous (G, K) rc, (G, K) ids, total count, min key and the largest
+    per-rank count (device tensors)."""
+    rc = gathered[:, :K].contiguous().view(torch.float64)
+    ids = gathered[:, K:2 * K].contiguous()
+    count = gathered[:, 2 * K].sum()
+    minkey = gathered[:, 2 * K + 1].min()
+    return rc, ids, count, minkey, gathered[:, 2 * K].max()
+
+
+class ShardedDensePricer:
+    """Pricing of one row slab per rank + global top-K.  `M_loc` is this rank's slab (S_loc x D,
+    row-major, device resident for the life of the problem, like the reference keeps `ot.M`)."""
+
+    def __init__(self, M_loc: torch.Tensor, S: int, row0: int, K: int, tol: float = dev.TOL_RC,
+                 group=None, variant: int = -1):
+        self.M = M_loc
+        self.S, self.D = int(S), int(M_loc.shape[1])
+        self.S_loc, self.row0 = int(M_loc.shape[0]), int(row0)
+        self.K, self.tol, self.variant = int(K), float(tol), variant
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.pricer = dev.Pricer(M_loc.device, self.K)
+        self.y_dev = torch.empty(self.S + self.D, dtype=torch.float64, device=M_loc.device)
+        self.h_y = torch.empty(self.S + self.D, dtype=torch.float64).pin_memory()
+        Kp = max(self.K, 1)
+        self.block = torch.empty(2 * Kp + 2, dtype=torch.int64, device=M_loc.device)
+        self.gathered = torch.empty(self.world, 2 * Kp + 2, dtype=torch.int64, device=M_loc.device)
+        self.h_out = torch.empty(2 * Kp + 4, dtype=torch.int64).pin_memory()
+        self.d_out = torch.empty(2 * Kp + 4, dtype=torch.int64, device=M_loc.device)
+        self.launches = 0     # kernels of libsxcross enqueued by this object
+
+    # -- device-only step: everything stays on the GPU(s) --------------------------------------
+    def enqueue(self, y_dev: torch.Tensor, kernel_events=None):
+        """Enqueue one pricing pass; returns device tensors
+        (rc[K], id[K], n_out, count, min key, largest per-rank count).  `kernel_events` = (start, end)
+        CUDA events recorded around the pricing kernel launch (bench.py's roofline measurement)."""
+        p = self.pricer
+        p.reset()
+        if kernel_events is not None:
+            kernel_events[0].record()
+        p.price_dense(self.M, self.M.stride(0), self.row0, self.S_loc, self.D,
+                      y_dev[self.row0:self.row0 + self.S_loc], y_dev[self.S:self.S + self.D],
+                      self.tol, None, self.variant)
+        if kernel_events is not None:
+            kernel_events[1].record()
+        p.select()
+        self.launches += 3 + (3 if self.K > 0 else 0)
+        if self.world == 1:
+            return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0]
+        pack_block(p.out_rc, p.out_id, p.header, self.block)
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.block, group=self.group)
+        rc, ids, count, minkey, cmax = unpack_blocks(self.gathered, max(self.K, 1))
+        out_rc, out_id, out_n = dev.topk_merge(rc, ids)
+        self.launches += 2
+        return out_rc, out_id, out_n[0], count, minkey, cmax
+
+    # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
+    def price(self, y_host: np.ndarray) -> dev.PriceResult:
+        """Upload y from pinned host memory, price, read the result back (one sync)."""
+        self.h_y.numpy()[:] = y_host
+        self.y_dev.copy_(self.h_y, non_blocking=True)
+        K = max(self.K, 1)
+        while True:
+            out_rc, out_id, out_n, count, minkey, cmax = self.enqueue(self.y_dev)
+            self.d_out[:K].copy_(out_rc.view(torch.int64))
+            self.d_out[K:2 * K].copy_(out_id)
+            self.d_out[2 * K] = out_n
+            self.d_out[2 * K + 1] = count
+            self.d_out[2 * K + 2] = minkey
+            self.d_out[2 * K + 3] = cmax
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            h = self.h_out.numpy()
+            n_out = int(h[2 * K]) if self.K > 0 else 0
+            # If some rank saw more violators than its candidate buffer holds, every rank (they all
+            # read the same gathered counts) grows to that size and the pass is priced again.
+            if self.K == 0 or int(h[2 * K + 3]) <= self.pricer.cap:
+                break
+            self.pricer.grow(int(h[2 * K + 3]))
+        return dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
+                               h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
+
+    @property
+    def h2d_bytes(self):
+        return 8 * (self.S + self.D)
+
+    @property
+    def d2h_bytes(self):
+        return 8 * (2 * max(self.K, 1) + 4)
