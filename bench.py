@@ -439,9 +439,10 @@ def sweep(args, sp, y_dev, S_loc, D, lib, dev):
     """Pricing-kernel variants and tunings, kernel-only GB/s (CUDA events, 20 reps after 3 warm-ups)."""
     import torch
     res = []
-    confs = [("tma", 0, (16, 6, 0)), ("tma", 0, (16, 4, 0)), ("tma", 0, (8, 8, 0)), ("tma", 0, (8, 12, 0)),
-             ("tma", 0, (32, 3, 0)), ("vec", 1, (0, 0, 4)), ("vec", 1, (0, 0, 8)), ("vec", 1, (0, 0, 16)),
-             ("scalar", 2, (0, 0, 8)), ("scalar", 2, (0, 0, 16))]
+    shapes = ["16x6 8w", "16x6 16w", "32x3 8w", "32x3 16w", "16x7 16w", "8x12 16w", "16x3 8w x2cta", "8x6 8w x2cta"]
+    confs = [(f"tma {nm}", 0, (i, 0)) for i, nm in enumerate(shapes)]
+    confs += [("vec", 1, (-1, 4)), ("vec", 1, (-1, 8)), ("vec", 1, (-1, 16)), ("scalar", 2, (-1, 8)),
+              ("scalar", 2, (-1, 16))]
     for name, variant, tune in confs:
         lib.sx_price_set_tuning(*tune)
         sp.variant = variant
@@ -458,7 +459,7 @@ def sweep(args, sp, y_dev, S_loc, D, lib, dev):
         res.append({"variant": name, "tuning": tune, "kernel_ms_median": round(float(np.median(ms)), 4),
                     "kernel_ms_min": round(float(min(ms)), 4), "GBs": round(gbs, 1)})
         print(json.dumps(res[-1]), flush=True)
-    lib.sx_price_set_tuning(16, 6, 8)
+    lib.sx_price_set_tuning(3, 16)
 
 
 if __name__ == "__main__":

@@ -161,10 +161,10 @@ SX_API int    sx_price_arcs(const double *c, const int32_t *tail, const int32_t 
                      sx_price_header *header, double *cand_rc, int64_t *cand_id,
                      int64_t cand_cap, double *rc_out, void *stream);
 
-/* Tuning knobs of sx_price_dense_ot (bench sweeps): rows per TMA box / pipeline stages of
- * variant 0 -- supported pairs (8,8) (8,12) (16,4) (16,6) (32,3) -- and CTAs per SM of the
- * direct-load variants.  Values <= 0 leave a knob unchanged. */
-SX_API int    sx_price_set_tuning(int tma_rows, int tma_stages, int direct_ctas_per_sm);
+/* Tuning knobs of sx_price_dense_ot (bench sweeps): index into the table of TMA pipeline shapes
+ * {rows per box, stages, consumer warps, CTAs per SM} of variant 0 (see sx_price.cu), and the
+ * CTAs per SM of the direct-load variants.  Negative / zero values leave a knob unchanged. */
+SX_API int    sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm);
 
 /* ---- top-k most violating arcs (north_star extension) -------
  * Among the candidates (rc, id) select the K smallest by (rc ascending, id ascending).

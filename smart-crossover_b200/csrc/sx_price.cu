@@ -66,6 +66,21 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// acc || (a < b) as ONE predicated compare (setp.lt.or.f64).  Written in PTX because the compiler
+// otherwise rewrites an OR of "x_i < lim" into "min(x_i) < lim", and an fp64 min is ~8 instructions.
+__device__ __forceinline__ bool lt_or(double a, double b, bool acc) {
+    int r;
+    asm("{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.s32 q, %3, 0;\n"
+        "setp.lt.or.f64 p, %1, %2, q;\n"
+        "selp.s32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(r)
+        : "d"(a), "d"(b), "r"((int)acc));
+    return r != 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // Candidate compaction shared by all pricing kernels.
 // A warp reserves slots for all violators of its tile with ONE atomicAdd on
@@ -126,10 +141,7 @@ __device__ __forceinline__ void block_min_commit(double tmin, sx_price_header *h
 // ---------------------------------------------------------------------------------------
 // K4a, variant 0: TMA pipeline
 // ---------------------------------------------------------------------------------------
-constexpr int kBoxCols      = 256;                  // fp64 elements per box row (TMA max box dim)
-constexpr int kConsWarps    = 8;                    // 4 warps across the 256 columns x 2 row halves
-constexpr int kConsThreads  = kConsWarps * 32;
-constexpr int kTmaThreads   = kConsThreads + 32;    // + 1 producer warp
+constexpr int kBoxCols = 256;   // fp64 elements per box row (TMA max box dim)
 
 struct DenseParams {
     const double *y_src;   // S_loc
@@ -142,11 +154,61 @@ struct DenseParams {
     long long     n_col_blocks, n_row_tiles;
 };
 
-template <int ROWS, int STAGES, bool WRITE_RC>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+// Epilogue of one warp's share of a tile: RPT rows x 2 adjacent columns per thread already in
+// registers as reduced costs (+inf where masked).  Counts, reserves and stores the violators.
+template <int RPT>
+__device__ __forceinline__ void emit_violators(const DenseParams &p, WarpTally &tally, const double (&rc0)[RPT],
+                                               const double (&rc1)[RPT], long long gid0, long long row_stride,
+                                               int col_gap = 1) {
+    unsigned nviol = 0;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+        nviol += __popc(__ballot_sync(0xffffffffu, rc0[r] < p.thr)) + __popc(__ballot_sync(0xffffffffu, rc1[r] < p.thr));
+    long long slot = warp_reserve(p.sink, tally, nviol);
+    if (slot < 0) return;
+    const unsigned lt = (1u << lane_id()) - 1u;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const long long gid = gid0 + r * row_stride;
+        const unsigned b0 = __ballot_sync(0xffffffffu, rc0[r] < p.thr);
+        if (rc0[r] < p.thr) cand_store(p.sink, slot + __popc(b0 & lt), rc0[r], gid);
+        slot += __popc(b0);
+        const unsigned b1 = __ballot_sync(0xffffffffu, rc1[r] < p.thr);
+        if (rc1[r] < p.thr) cand_store(p.sink, slot + __popc(b1 & lt), rc1[r], gid + col_gap);
+        slot += __popc(b1);
+    }
+}
+
+// Lazy epilogue.  The hot loop does ONE compare per reduced cost, against lim = max(running min,
+// -tol): a hit means "new minimum or violator", both rare, and only then are the exact minimum
+// updated and the violators counted and stored (fp64 min costs ~8 SASS instructions on sm_100a).
+template <int RPT>
+__device__ __forceinline__ void tile_epilogue(const DenseParams &p, WarpTally &tally, double &tmin, double &lim,
+                                              const double (&rc0)[RPT], const double (&rc1)[RPT], bool hit,
+                                              long long gid0, long long row_stride, int col_gap = 1) {
+    if (!__any_sync(0xffffffffu, hit)) return;
+    bool viol = false;
+    if (hit) {
+        double mn = tmin;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            mn = rc0[r] < mn ? rc0[r] : mn;
+            mn = rc1[r] < mn ? rc1[r] : mn;
+            viol = viol || (rc0[r] < p.thr) || (rc1[r] < p.thr);
+        }
+        tmin = mn;
+        lim = tmin > p.thr ? tmin : p.thr;
+    }
+    if (__any_sync(0xffffffffu, viol)) emit_violators<RPT>(p, tally, rc0, rc1, gid0, row_stride, col_gap);
+}
+
+// CWARPS consumer warps: 4 warps span the 256 box columns (2 adjacent columns per thread, so a
+// warp reads 512 contiguous bytes of a box row: conflict-free LDS.128), CWARPS/4 row groups.
+template <int ROWS, int STAGES, int CWARPS, int MINB, bool WRITE_RC>
+__global__ void __launch_bounds__((CWARPS + 1) * 32, MINB)
 price_dense_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p) {
-    constexpr int      kRowsPerHalf = ROWS / 2;
-    constexpr uint32_t kStageBytes  = ROWS * kBoxCols * sizeof(double);
+    constexpr int      RPT         = ROWS / (CWARPS / 4);      // rows per consumer thread
+    constexpr uint32_t kStageBytes = ROWS * kBoxCols * sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double   *stage_base = reinterpret_cast<double *>(smem_raw);
     uint64_t *full_bar   = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * kStageBytes);
@@ -157,129 +219,114 @@ price_dense_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DensePara
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsWarps);
+            mbar_init(&empty_bar[s], CWARPS);
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    // contiguous, balanced range of tiles; tile t = row_tile * n_col_blocks + col_block so a
-    // CTA walks along the rows of one row tile (16 sequential DRAM streams per CTA)
+    // Grid-stride tile walk, tile t = row_tile * n_col_blocks + col_block: at any time the CTAs of
+    // the grid read neighbouring 2 KB segments of the same few matrix rows (DRAM page locality).
     const long long total = p.n_row_tiles * p.n_col_blocks;
-    const long long t_beg = total * (long long)blockIdx.x / (long long)gridDim.x;
-    const long long t_end = total * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+    const long long G = gridDim.x;
+    long long rt = (long long)blockIdx.x / p.n_col_blocks;
+    long long cb = (long long)blockIdx.x - rt * p.n_col_blocks;
+    const long long d_rt = G / p.n_col_blocks, d_cb = G - d_rt * p.n_col_blocks;
 
-    if (warp == kConsWarps) {
+    if (warp == CWARPS) {
         // ===== producer warp: one elected lane issues the TMA loads =====
         if (lane_id() == 0) {
             const uint64_t pol = l2_evict_first_policy();
-            long long rt = t_beg / p.n_col_blocks;
-            long long cb = t_beg - rt * p.n_col_blocks;
-            uint32_t  it = 0;
-            for (long long t = t_beg; t < t_end; ++t, ++it) {
+            uint32_t it = 0;
+            for (long long t = blockIdx.x; t < total; t += G, ++it) {
                 const int s = it % STAGES;
                 if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
                 mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                 tma_load_2d(stage_base + (size_t)s * ROWS * kBoxCols, &tmap, &full_bar[s],
                             (int)(cb * kBoxCols), (int)(rt * ROWS), pol);
-                if (++cb == p.n_col_blocks) { cb = 0; ++rt; }
+                rt += d_rt; cb += d_cb;
+                if (cb >= p.n_col_blocks) { cb -= p.n_col_blocks; ++rt; }
             }
         }
     } else {
         // ===== consumer warps =====
-        const int c    = threadIdx.x & 127;           // column pair inside the box
-        const int half = threadIdx.x >> 7;             // row half
-        long long rt = t_beg / p.n_col_blocks;
-        long long cb = t_beg - rt * p.n_col_blocks;
-        double    tmin = INFINITY;
+        const int c  = threadIdx.x & 127;            // column pair inside the box
+        const int rg = threadIdx.x >> 7;             // row group
+        double    tmin = INFINITY, lim = INFINITY;
         WarpTally tally;
-        double    u[kRowsPerHalf];
-        long long rt_loaded = -1;
-        // software-prefetched sink potentials of this thread's two columns
-        auto load_v = [&](long long cbx, double &a, double &b) {
-            const long long j = cbx * kBoxCols + 2 * c;
-            a = (j < p.D) ? __ldg(p.y_dst + j) : 0.0;
-            b = (j + 1 < p.D) ? __ldg(p.y_dst + j + 1) : 0.0;
-        };
-        double v0n = 0.0, v1n = 0.0;
-        if (t_beg < t_end) load_v(cb, v0n, v1n);
-        uint32_t it = 0;
-        for (long long t = t_beg; t < t_end; ++t, ++it) {
-            const int    s  = it % STAGES;
-            const double v0 = v0n, v1 = v1n;
+        uint32_t  it = 0;
+        for (long long t = blockIdx.x; t < total; t += G, ++it) {
+            const int s = it % STAGES;
             const long long j0 = cb * kBoxCols + 2 * c;
-            const long long i0 = rt * ROWS + (long long)half * kRowsPerHalf;
-            long long cb_next = cb + 1, rt_next = rt;
-            if (cb_next == p.n_col_blocks) { cb_next = 0; ++rt_next; }
-            if (t + 1 < t_end) load_v(cb_next, v0n, v1n);
-            if (rt != rt_loaded) {
+            const long long i0 = rt * ROWS + (long long)rg * RPT;
+            const bool interior = (cb + 1) * kBoxCols <= p.D && (rt + 1) * ROWS <= p.S_loc;   // CTA-uniform
+            // potentials of this thread's columns / rows: issued before the wait so their latency
+            // hides behind the TMA transfer
+            double v0, v1, u[RPT];
+            if (interior) {
+                const double2 vv = make_double2(__ldg(p.y_dst + j0), __ldg(p.y_dst + j0 + 1));
+                v0 = vv.x; v1 = vv.y;
 #pragma unroll
-                for (int r = 0; r < kRowsPerHalf; ++r)
-                    u[r] = (i0 + r < p.S_loc) ? __ldg(p.y_src + i0 + r) : 0.0;
-                rt_loaded = rt;
+                for (int r = 0; r < RPT; ++r) u[r] = __ldg(p.y_src + i0 + r);
+            } else {
+                v0 = (j0 < p.D) ? __ldg(p.y_dst + j0) : 0.0;
+                v1 = (j0 + 1 < p.D) ? __ldg(p.y_dst + j0 + 1) : 0.0;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) u[r] = (i0 + r < p.S_loc) ? __ldg(p.y_src + i0 + r) : 0.0;
             }
             mbar_wait(&full_bar[s], (it / STAGES) & 1);
             const double2 *tile = reinterpret_cast<const double2 *>(stage_base + (size_t)s * ROWS * kBoxCols) +
-                                  (size_t)half * kRowsPerHalf * (kBoxCols / 2) + c;
-            double2 m[kRowsPerHalf];
+                                  (size_t)rg * RPT * (kBoxCols / 2) + c;
+            double2 m[RPT];
 #pragma unroll
-            for (int r = 0; r < kRowsPerHalf; ++r) m[r] = tile[(size_t)r * (kBoxCols / 2)];
+            for (int r = 0; r < RPT; ++r) m[r] = tile[(size_t)r * (kBoxCols / 2)];
             // all shared reads of this stage are in registers: release the slot
             __syncwarp();
             if (lane_id() == 0) mbar_arrive(&empty_bar[s]);
 
-            const bool ok0 = j0 < p.D, ok1 = j0 + 1 < p.D;
-            double   rc0[kRowsPerHalf], rc1[kRowsPerHalf];
-            unsigned nviol = 0;
+            double rc0[RPT], rc1[RPT];
+            bool   hit = false;
+            if (interior) {
 #pragma unroll
-            for (int r = 0; r < kRowsPerHalf; ++r) {
-                const bool rok = i0 + r < p.S_loc;
-                const double a = m[r].x - (v0 - u[r]);
-                const double b = m[r].y - (v1 - u[r]);
-                rc0[r] = (rok && ok0) ? a : INFINITY;
-                rc1[r] = (rok && ok1) ? b : INFINITY;
-                tmin = fmin(tmin, fmin(rc0[r], rc1[r]));
-                nviol += __popc(__ballot_sync(0xffffffffu, rc0[r] < p.thr)) +
-                         __popc(__ballot_sync(0xffffffffu, rc1[r] < p.thr));
+                for (int r = 0; r < RPT; ++r) {
+                    rc0[r] = m[r].x - (v0 - u[r]);
+                    rc1[r] = m[r].y - (v1 - u[r]);
+                    hit = lt_or(rc1[r], lim, lt_or(rc0[r], lim, hit));
+                }
+            } else {
+                const bool ok0 = j0 < p.D, ok1 = j0 + 1 < p.D;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const bool rok = i0 + r < p.S_loc;
+                    const double a = m[r].x - (v0 - u[r]);
+                    const double b = m[r].y - (v1 - u[r]);
+                    rc0[r] = (rok && ok0) ? a : INFINITY;
+                    rc1[r] = (rok && ok1) ? b : INFINITY;
+                    hit = lt_or(rc1[r], lim, lt_or(rc0[r], lim, hit));
+                }
             }
             if (WRITE_RC) {
 #pragma unroll
-                for (int r = 0; r < kRowsPerHalf; ++r) {
+                for (int r = 0; r < RPT; ++r) {
                     if (i0 + r < p.S_loc) {
                         double *o = p.rc_out + (i0 + r) * p.ld_out + j0;
-                        if (ok0) o[0] = rc0[r];
-                        if (ok1) o[1] = rc1[r];
+                        if (j0 < p.D) o[0] = rc0[r];
+                        if (j0 + 1 < p.D) o[1] = rc1[r];
                     }
                 }
             }
-            if (nviol) {   // warp-uniform, rare
-                long long slot = warp_reserve(p.sink, tally, nviol);
-                if (slot >= 0) {
-                    const unsigned lt = (1u << lane_id()) - 1u;
-#pragma unroll
-                    for (int r = 0; r < kRowsPerHalf; ++r) {
-                        const long long gid = (p.row0 + i0 + r) * p.D + j0;
-                        const unsigned b0 = __ballot_sync(0xffffffffu, rc0[r] < p.thr);
-                        if (rc0[r] < p.thr) cand_store(p.sink, slot + __popc(b0 & lt), rc0[r], gid);
-                        slot += __popc(b0);
-                        const unsigned b1 = __ballot_sync(0xffffffffu, rc1[r] < p.thr);
-                        if (rc1[r] < p.thr) cand_store(p.sink, slot + __popc(b1 & lt), rc1[r], gid + 1);
-                        slot += __popc(b1);
-                    }
-                }
-            }
-            cb = cb_next;
-            rt = rt_next;
+            tile_epilogue<RPT>(p, tally, tmin, lim, rc0, rc1, hit, (p.row0 + i0) * p.D + j0, p.D);
+            rt += d_rt; cb += d_cb;
+            if (cb >= p.n_col_blocks) { cb -= p.n_col_blocks; ++rt; }
         }
         warp_flush(p.sink, tally);
-        // stash the per-thread min for the block reduction below
-        long long k = warp_min(f64_to_min_key(tmin));
+        const long long k = warp_min(f64_to_min_key(tmin));
         if (lane_id() == 0) scratch[warp] = k;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         long long m = scratch[0];
-        for (int w = 1; w < kConsWarps; ++w) m = scratch[w] < m ? scratch[w] : m;
+        for (int w = 1; w < CWARPS; ++w) m = scratch[w] < m ? scratch[w] : m;
         atomicMin(&p.sink.hdr->min_rc_key, m);
     }
 }
@@ -313,66 +360,66 @@ price_dense_direct_kernel(const double *__restrict__ M, long long ld, const Dens
     __shared__ long long scratch[kDirectThreads / 32];
     const int warp = threadIdx.x >> 5;
     const long long total = p.n_row_tiles * p.n_col_blocks;
+    const long long G = gridDim.x;
     const uint64_t pol = l2_evict_first_policy();
-    double    tmin = INFINITY;
+    double    tmin = INFINITY, lim = INFINITY;
     WarpTally tally;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        const long long rt = t / p.n_col_blocks;
-        const long long cb = t - rt * p.n_col_blocks;
+    long long rt = (long long)blockIdx.x / p.n_col_blocks;
+    long long cb = (long long)blockIdx.x - rt * p.n_col_blocks;
+    const long long d_rt = G / p.n_col_blocks, d_cb = G - d_rt * p.n_col_blocks;
+    constexpr int kGap = VEC ? 1 : 128;
+    for (long long t = blockIdx.x; t < total; t += G) {
         const long long i0 = rt * kDirectRows;
         // VEC: columns (2c, 2c+1); scalar: columns (c, c + 128) so each load is coalesced
         const long long j0 = cb * kBoxCols + (VEC ? 2 * threadIdx.x : threadIdx.x);
-        const long long j1 = VEC ? j0 + 1 : j0 + 128;
-        const bool ok0 = j0 < p.D, ok1 = j1 < p.D;
-        const double v0 = ok0 ? __ldg(p.y_dst + j0) : 0.0;
-        const double v1 = ok1 ? __ldg(p.y_dst + j1) : 0.0;
-        double a[kDirectRows], b[kDirectRows];
+        const long long j1 = j0 + kGap;
+        const bool interior = (cb + 1) * kBoxCols <= p.D && (rt + 1) * kDirectRows <= p.S_loc;
+        double rc0[kDirectRows], rc1[kDirectRows];
+        bool   hit = false;
+        if (interior) {
+            const double *src = M + i0 * ld + j0;
+            double a[kDirectRows], b[kDirectRows];
 #pragma unroll
-        for (int r = 0; r < kDirectRows; ++r) {
-            const bool rok = i0 + r < p.S_loc;
-            const double *src = M + (i0 + r) * ld;
-            if (VEC) {
-                if (rok && ok1) { double2 q = ldg_stream_v2(src + j0, pol); a[r] = q.x; b[r] = q.y; }
-                else { a[r] = (rok && ok0) ? ldg_stream(src + j0, pol) : 0.0; b[r] = 0.0; }
-            } else {
-                a[r] = (rok && ok0) ? ldg_stream(src + j0, pol) : 0.0;
-                b[r] = (rok && ok1) ? ldg_stream(src + j1, pol) : 0.0;
+            for (int r = 0; r < kDirectRows; ++r) {
+                if (VEC) { const double2 q = ldg_stream_v2(src + r * ld, pol); a[r] = q.x; b[r] = q.y; }
+                else { a[r] = ldg_stream(src + r * ld, pol); b[r] = ldg_stream(src + r * ld + kGap, pol); }
+            }
+            const double v0 = __ldg(p.y_dst + j0), v1 = __ldg(p.y_dst + j1);
+#pragma unroll
+            for (int r = 0; r < kDirectRows; ++r) {
+                const double ui = __ldg(p.y_src + i0 + r);
+                rc0[r] = a[r] - (v0 - ui);
+                rc1[r] = b[r] - (v1 - ui);
+                hit = lt_or(rc1[r], lim, lt_or(rc0[r], lim, hit));
+            }
+        } else {
+            const bool ok0 = j0 < p.D, ok1 = j1 < p.D;
+            const double v0 = ok0 ? __ldg(p.y_dst + j0) : 0.0;
+            const double v1 = ok1 ? __ldg(p.y_dst + j1) : 0.0;
+#pragma unroll
+            for (int r = 0; r < kDirectRows; ++r) {
+                const bool rok = i0 + r < p.S_loc;
+                const double *src = M + (i0 + r) * ld;
+                const double a = (rok && ok0) ? ldg_stream(src + j0, pol) : 0.0;
+                const double b = (rok && ok1) ? ldg_stream(src + j1, pol) : 0.0;
+                const double ui = rok ? __ldg(p.y_src + i0 + r) : 0.0;
+                rc0[r] = (rok && ok0) ? a - (v0 - ui) : INFINITY;
+                rc1[r] = (rok && ok1) ? b - (v1 - ui) : INFINITY;
+                hit = lt_or(rc1[r], lim, lt_or(rc0[r], lim, hit));
             }
         }
-        double   rc0[kDirectRows], rc1[kDirectRows];
-        unsigned nviol = 0;
+        if (WRITE_RC) {
 #pragma unroll
-        for (int r = 0; r < kDirectRows; ++r) {
-            const bool rok = i0 + r < p.S_loc;
-            const double ui = rok ? __ldg(p.y_src + i0 + r) : 0.0;
-            const double x0 = a[r] - (v0 - ui);
-            const double x1 = b[r] - (v1 - ui);
-            rc0[r] = (rok && ok0) ? x0 : INFINITY;
-            rc1[r] = (rok && ok1) ? x1 : INFINITY;
-            tmin = fmin(tmin, fmin(rc0[r], rc1[r]));
-            nviol += __popc(__ballot_sync(0xffffffffu, rc0[r] < p.thr)) +
-                     __popc(__ballot_sync(0xffffffffu, rc1[r] < p.thr));
-            if (WRITE_RC && rok) {
-                if (ok0) p.rc_out[(i0 + r) * p.ld_out + j0] = rc0[r];
-                if (ok1) p.rc_out[(i0 + r) * p.ld_out + j1] = rc1[r];
-            }
-        }
-        if (nviol) {
-            long long slot = warp_reserve(p.sink, tally, nviol);
-            if (slot >= 0) {
-                const unsigned lt = (1u << lane_id()) - 1u;
-#pragma unroll
-                for (int r = 0; r < kDirectRows; ++r) {
-                    const long long gbase = (p.row0 + i0 + r) * p.D;
-                    const unsigned b0 = __ballot_sync(0xffffffffu, rc0[r] < p.thr);
-                    if (rc0[r] < p.thr) cand_store(p.sink, slot + __popc(b0 & lt), rc0[r], gbase + j0);
-                    slot += __popc(b0);
-                    const unsigned b1 = __ballot_sync(0xffffffffu, rc1[r] < p.thr);
-                    if (rc1[r] < p.thr) cand_store(p.sink, slot + __popc(b1 & lt), rc1[r], gbase + j1);
-                    slot += __popc(b1);
+            for (int r = 0; r < kDirectRows; ++r) {
+                if (i0 + r < p.S_loc) {
+                    if (j0 < p.D) p.rc_out[(i0 + r) * p.ld_out + j0] = rc0[r];
+                    if (j1 < p.D) p.rc_out[(i0 + r) * p.ld_out + j1] = rc1[r];
                 }
             }
         }
+        tile_epilogue<kDirectRows>(p, tally, tmin, lim, rc0, rc1, hit, (p.row0 + i0) * p.D + j0, p.D, kGap);
+        rt += d_rt; cb += d_cb;
+        if (cb >= p.n_col_blocks) { cb -= p.n_col_blocks; ++rt; }
     }
     warp_flush(p.sink, tally);
     block_min_commit(tmin, p.sink.hdr, scratch, kDirectThreads / 32, warp);
@@ -391,14 +438,14 @@ price_arcs_kernel(const double *__restrict__ c, const int32_t *__restrict__ tail
                   CandSink sink, double *rc_out) {
     __shared__ long long scratch[kArcThreads / 32];
     const int warp = threadIdx.x >> 5;
-    double    tmin = INFINITY;
+    double    tmin = INFINITY, lim = INFINITY;
     WarpTally tally;
     const long long chunk = (long long)kArcThreads * kArcPerThread;
     const long long n_chunks = (E + chunk - 1) / chunk;
     const uint64_t pol = l2_evict_first_policy();
     for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        double   rc[kArcPerThread];
-        unsigned nviol = 0;
+        double rc[kArcPerThread];
+        bool   hit = false;
 #pragma unroll
         for (int q = 0; q < kArcPerThread; ++q) {
             const long long k = ch * chunk + (long long)q * kArcThreads + threadIdx.x;
@@ -412,20 +459,31 @@ price_arcs_kernel(const double *__restrict__ c, const int32_t *__restrict__ tail
                 if (rc_out != nullptr) rc_out[k] = v;
             }
             rc[q] = v;
-            tmin = fmin(tmin, v);
-            nviol += __popc(__ballot_sync(0xffffffffu, v < thr));
+            hit = lt_or(v, lim, hit);
         }
-        if (nviol) {
-            long long slot = warp_reserve(sink, tally, nviol);
-            if (slot >= 0) {
-                const unsigned lt = (1u << lane_id()) - 1u;
+        if (!__any_sync(0xffffffffu, hit)) continue;
+        bool viol = false;
+        if (hit) {
 #pragma unroll
-                for (int q = 0; q < kArcPerThread; ++q) {
-                    const long long k = ch * chunk + (long long)q * kArcThreads + threadIdx.x;
-                    const unsigned b = __ballot_sync(0xffffffffu, rc[q] < thr);
-                    if (rc[q] < thr) cand_store(sink, slot + __popc(b & lt), rc[q], id0 + k);
-                    slot += __popc(b);
-                }
+            for (int q = 0; q < kArcPerThread; ++q) {
+                tmin = rc[q] < tmin ? rc[q] : tmin;
+                viol = viol || (rc[q] < thr);
+            }
+            lim = tmin > thr ? tmin : thr;
+        }
+        if (!__any_sync(0xffffffffu, viol)) continue;
+        unsigned nviol = 0;
+#pragma unroll
+        for (int q = 0; q < kArcPerThread; ++q) nviol += __popc(__ballot_sync(0xffffffffu, rc[q] < thr));
+        long long slot = warp_reserve(sink, tally, nviol);
+        if (slot >= 0) {
+            const unsigned lt = (1u << lane_id()) - 1u;
+#pragma unroll
+            for (int q = 0; q < kArcPerThread; ++q) {
+                const long long k = ch * chunk + (long long)q * kArcThreads + threadIdx.x;
+                const unsigned b = __ballot_sync(0xffffffffu, rc[q] < thr);
+                if (rc[q] < thr) cand_store(sink, slot + __popc(b & lt), rc[q], id0 + k);
+                slot += __popc(b);
             }
         }
     }
@@ -463,43 +521,52 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// tunables of the TMA variant (overridable for bench sweeps through sx_price_set_tuning)
-static int g_tma_rows = 16, g_tma_stages = 6, g_ctas_per_sm_direct = 8;
+// TMA pipeline shapes selectable at run time (bench sweeps): {rows per box, stages, consumer
+// warps, CTAs per SM}.  Shared memory = stages * rows * 2 KB per CTA.
+struct TmaShape { int rows, stages, cwarps, ctas_per_sm; };
+static const TmaShape kTmaShapes[] = {
+    {16, 6, 8, 1}, {16, 6, 16, 1}, {32, 3, 8, 1}, {32, 3, 16, 1}, {16, 7, 16, 1}, {8, 12, 16, 1},
+    {16, 3, 8, 2}, {8, 6, 8, 2},
+};
+constexpr int kNumTmaShapes = sizeof(kTmaShapes) / sizeof(kTmaShapes[0]);
+static int g_tma_shape = 3, g_ctas_per_sm_direct = 16;
 
-template <int ROWS, int STAGES, bool WRITE_RC>
+template <int ROWS, int STAGES, int CWARPS, int MINB, bool WRITE_RC>
 static int launch_tma(const CUtensorMap &map, const DenseParams &p, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * ROWS * kBoxCols * sizeof(double) + 2 * STAGES * sizeof(uint64_t) +
-                            kConsWarps * sizeof(long long) + 128;
-    auto kern = price_dense_tma_kernel<ROWS, STAGES, WRITE_RC>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+                            CWARPS * sizeof(long long) + 64;
+    auto kern = price_dense_tma_kernel<ROWS, STAGES, CWARPS, MINB, WRITE_RC>;
+    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = p.n_row_tiles * p.n_col_blocks;
-    int grid = (int)(total < kNumSMs ? total : kNumSMs);
+    long long grid = (long long)kNumSMs * MINB;
+    if (grid > total) grid = total;
     if (grid < 1) grid = 1;
-    kern<<<grid, kTmaThreads, smem, st>>>(map, p);
+    kern<<<(int)grid, (CWARPS + 1) * 32, smem, st>>>(map, p);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }
 
 template <bool WRITE_RC>
-static int dispatch_tma(const CUtensorMap &map, const DenseParams &p, cudaStream_t st) {
-    if (g_tma_rows == 8 && g_tma_stages == 8) return launch_tma<8, 8, WRITE_RC>(map, p, st);
-    if (g_tma_rows == 8 && g_tma_stages == 12) return launch_tma<8, 12, WRITE_RC>(map, p, st);
-    if (g_tma_rows == 16 && g_tma_stages == 4) return launch_tma<16, 4, WRITE_RC>(map, p, st);
-    if (g_tma_rows == 32 && g_tma_stages == 3) return launch_tma<32, 3, WRITE_RC>(map, p, st);
-    return launch_tma<16, 6, WRITE_RC>(map, p, st);
+static int dispatch_tma(int shape, const CUtensorMap &map, const DenseParams &p, cudaStream_t st) {
+    switch (shape) {
+        case 0: return launch_tma<16, 6, 8, 1, WRITE_RC>(map, p, st);
+        case 1: return launch_tma<16, 6, 16, 1, WRITE_RC>(map, p, st);
+        case 2: return launch_tma<32, 3, 8, 1, WRITE_RC>(map, p, st);
+        case 4: return launch_tma<16, 7, 16, 1, WRITE_RC>(map, p, st);
+        case 5: return launch_tma<8, 12, 16, 1, WRITE_RC>(map, p, st);
+        case 6: return launch_tma<16, 3, 8, 2, WRITE_RC>(map, p, st);
+        case 7: return launch_tma<8, 6, 8, 2, WRITE_RC>(map, p, st);
+        default: return launch_tma<32, 3, 16, 1, WRITE_RC>(map, p, st);
+    }
 }
 
 }  // namespace sx
 
 using namespace sx;
 
-extern "C" int sx_price_set_tuning(int tma_rows, int tma_stages, int direct_ctas_per_sm) {
-    if (tma_rows > 0) g_tma_rows = tma_rows;
-    if (tma_stages > 0) g_tma_stages = tma_stages;
+extern "C" int sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm) {
+    if (tma_shape >= kNumTmaShapes) return SX_ERR_INVALID;
+    if (tma_shape >= 0) g_tma_shape = tma_shape;
     if (direct_ctas_per_sm > 0) g_ctas_per_sm_direct = direct_ctas_per_sm;
     return SX_OK;
 }
@@ -537,7 +604,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
     if (variant == 0) {
         EncodeTiledFn enc = get_encode_fn();
         if (!enc) return SX_ERR_NO_DEVICE;
-        const int rows = g_tma_rows;
+        const int rows = kTmaShapes[g_tma_shape].rows;
         p.n_row_tiles = (S_loc + rows - 1) / rows;
         CUtensorMap map;
         cuuint64_t gdim[2]    = {(cuuint64_t)D, (cuuint64_t)S_loc};
@@ -548,7 +615,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return SX_ERR_CUDA; }
-        rc = rc_out ? dispatch_tma<true>(map, p, st) : dispatch_tma<false>(map, p, st);
+        rc = rc_out ? dispatch_tma<true>(g_tma_shape, map, p, st) : dispatch_tma<false>(g_tma_shape, map, p, st);
     } else {
         p.n_row_tiles = (S_loc + kDirectRows - 1) / kDirectRows;
         const long long total = p.n_row_tiles * p.n_col_blocks;
