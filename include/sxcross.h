@@ -180,8 +180,10 @@ SX_API int    sx_topk_select(const double *cand_rc, const int64_t *cand_id,
                       const unsigned long long *n_cand_dev, int64_t cand_cap, int64_t K,
                       double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
                       void *stream);
+SX_API size_t sx_topk_merge_workspace_bytes(int64_t G);
 SX_API int    sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t G, int64_t K,
-                     double *out_rc, int64_t *out_id, int64_t *out_n, void *stream);
+                     double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
+                     void *stream);
 
 /* ---- host-buffer entry point (what a reference-side binding calls with NumPy arrays) ----
  * One pricing pass with HOST buffers: uploads y (and M if M_dev == NULL), prices, selects

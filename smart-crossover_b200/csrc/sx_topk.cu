@@ -69,7 +69,11 @@ topk_slice_sort_kernel(const double *__restrict__ cand_rc, const long long *__re
         const long long g = base + q * kTkThreads + threadIdx.x;
         e[q] = (g < n) ? Cand{cand_rc[g], cand_id[g]} : cand_pad();
     }
+    // both loops have compile-time trip counts and are fully unrolled, so every e[] index is static
+    // (a dynamic index would push e[] to local memory)
+#pragma unroll
     for (int k = 2; k <= kTkSlice; k <<= 1) {
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             if (j >= kTkThreads) {
                 // partner lives in another register slot of the same thread
@@ -120,12 +124,23 @@ topk_slice_sort_kernel(const double *__restrict__ cand_rc, const long long *__re
     }
 }
 
-__device__ __forceinline__ int lower_bound_list(const double *rc, const long long *id, int K, const Cand &x) {
-    int lo = 0, hi = K;
+// number of elements of a sorted, padded list prefix [0, len) that are  < x  (strict)
+__device__ __forceinline__ int lower_bound_list(const double *rc, const long long *id, int len, const Cand &x) {
+    int lo = 0, hi = len;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         const Cand m{rc[mid], id[mid]};
         if (cand_less_p(m, x)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// number of elements <= x
+__device__ __forceinline__ int upper_bound_list(const double *rc, const long long *id, int len, const Cand &x) {
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const Cand m{rc[mid], id[mid]};
+        if (!cand_less_p(x, m)) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -136,49 +151,147 @@ __global__ void topk_fill_kernel(double *out_rc, long long *out_id, long long *o
     if (i == 0) *out_n = 0;
 }
 
-// lists: L sorted, padded lists of length K.  Writes the K globally smallest to out.
-__global__ void __launch_bounds__(256)
-topk_rank_merge_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, int L, int K,
-                       const unsigned long long *n_cand_dev, long long cand_cap,
-                       double *__restrict__ out_rc, long long *__restrict__ out_id, long long *out_n) {
-    __shared__ Cand s_thr[256];
-    // lists that can hold data (select path: only the first ceil(n / 4096) slices are non-empty)
+// Rank merge, step 1 (one CTA).  lists: L sorted, padded lists of length K.
+//   thr      = smallest last element over the lists: the global K-th best is <= it, so only the
+//              prefix of each list with elements <= thr can be in the answer;
+//   plen[l]  = length of that prefix;  poff[l] = exclusive prefix sum;  poff[L] = work total.
+__global__ void __launch_bounds__(1024)
+topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, int L, int K,
+                 const unsigned long long *n_cand_dev, long long cand_cap, int *__restrict__ plen,
+                 int *__restrict__ poff, long long *out_n) {
+    __shared__ Cand s_thr[32];
+    __shared__ int  s_warp[32];
+    __shared__ int  s_carry;
     int Lu = L;
-    if (n_cand_dev) {
+    long long n_real = -1;
+    if (n_cand_dev) {   // select path: only the first ceil(n / 4096) slices hold data
         unsigned long long n64 = *n_cand_dev;
-        const long long n = n64 > (unsigned long long)cand_cap ? cand_cap : (long long)n64;
-        Lu = (int)((n + kTkSlice - 1) / kTkSlice);
+        n_real = n64 > (unsigned long long)cand_cap ? cand_cap : (long long)n64;
+        Lu = (int)((n_real + kTkSlice - 1) / kTkSlice);
         if (Lu > L) Lu = L;
     }
-    // threshold: the smallest last element over lists (padding = +inf => no constraint)
-    Cand thr = cand_pad();
-    for (int l = threadIdx.x; l < Lu; l += blockDim.x) {
-        const Cand c{lists_rc[(long long)l * K + K - 1], lists_id[(long long)l * K + K - 1]};
-        if (cand_less_p(c, thr)) thr = c;
-    }
-    s_thr[threadIdx.x] = thr;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o && cand_less_p(s_thr[threadIdx.x + o], s_thr[threadIdx.x]))
-            s_thr[threadIdx.x] = s_thr[threadIdx.x + o];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    __shared__ long long s_red[32];
+    auto block_sum = [&](long long v) -> long long {
+        v = warp_sum(v);
         __syncthreads();
-    }
-    thr = s_thr[0];
-    const long long total = (long long)Lu * K;
-    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
-         w += (long long)gridDim.x * blockDim.x) {
-        const int l = (int)(w / K), i = (int)(w - (long long)l * K);
-        const Cand c{lists_rc[w], lists_id[w]};
-        if (c.id < 0) continue;                 // padding
-        if (cand_less_p(thr, c)) continue;      // cannot be among the K best
-        int rank = i;
-        for (int m = 0; m < Lu && rank < K; ++m)
-            if (m != l) rank += lower_bound_list(lists_rc + (long long)m * K, lists_id + (long long)m * K, K, c);
-        if (rank < K) {
-            out_rc[rank] = c.rc;
-            out_id[rank] = c.id;
-            atomicAdd((unsigned long long *)out_n, 1ull);
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        long long t = 0;
+        for (int w = 0; w < 32; ++w) t += s_red[w];
+        return t;
+    };
+    auto block_min_cand = [&](Cand c, bool want_max) -> Cand {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const Cand other = shfl_xor_cand(c, o);
+            if (cand_less_p(other, c) != want_max) c = other;
         }
+        __syncthreads();
+        if (lane == 0) s_thr[warp] = c;
+        __syncthreads();
+        Cand r = s_thr[0];
+        for (int w = 1; w < 32; ++w) if (cand_less_p(s_thr[w], r) != want_max) r = s_thr[w];
+        return r;
+    };
+    if (threadIdx.x == 0) s_carry = 0;
+    // bound 1: the smallest "last element of a list" (padding = +inf: no constraint)
+    Cand thr = cand_pad();
+    long long n_real_lists = 0;
+    for (int l = threadIdx.x; l < Lu; l += blockDim.x) {
+        const long long *ids = lists_id + (long long)l * K;
+        const Cand c{lists_rc[(long long)l * K + K - 1], ids[K - 1]};
+        if (cand_less_p(c, thr)) thr = c;
+        int lo = 0, hi = K;                              // real length of the list: first padding entry
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (ids[mid] >= 0) lo = mid + 1; else hi = mid; }
+        plen[l] = lo;
+        n_real_lists += lo;
+    }
+    thr = block_min_cand(thr, false);
+    // bound 2: the smallest depth i with sum_l min(len_l, i) >= K; the union of the depth-i prefixes
+    // already holds K elements, so the global K-th best is <= the largest element among them.  Much
+    // tighter than bound 1 when there are many lists.
+    const long long all_real = block_sum(n_real_lists);
+    if (all_real >= K) {
+        int lo = 1, hi = K;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            long long part = 0;
+            for (int l = threadIdx.x; l < Lu; l += blockDim.x) part += plen[l] < mid ? plen[l] : mid;
+            if (block_sum(part) >= K) hi = mid; else lo = mid + 1;
+        }
+        Cand deep = Cand{-INFINITY, 0};
+        for (int l = threadIdx.x; l < Lu; l += blockDim.x) {
+            const int take = plen[l] < lo ? plen[l] : lo;
+            if (take > 0) {
+                const Cand c{lists_rc[(long long)l * K + take - 1], lists_id[(long long)l * K + take - 1]};
+                if (cand_less_p(deep, c)) deep = c;
+            }
+        }
+        deep = block_min_cand(deep, true);
+        if (cand_less_p(deep, thr)) thr = deep;
+    }
+    __syncthreads();
+    // prefix lengths and their exclusive scan, 1024 lists per sweep
+    long long real_total = 0;
+    for (int base = 0; base < L; base += blockDim.x) {
+        const int l = base + threadIdx.x;
+        int len = 0;
+        if (l < Lu) len = upper_bound_list(lists_rc + (long long)l * K, lists_id + (long long)l * K, K, thr);
+        // do not count padding (id < 0) that ties with an all-padding threshold
+        if (l < Lu && len > 0) {
+            int lo = 0, hi = len;                       // first padding entry within [0, len)
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (lists_id[(long long)l * K + mid] >= 0) lo = mid + 1; else hi = mid; }
+            len = lo;
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int add = s_carry;
+        for (int w = 0; w < warp; ++w) add += s_warp[w];
+        if (l < L) { plen[l] = len; poff[l] = add + incl - len; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = add + incl;
+        __syncthreads();
+        real_total = s_carry;
+    }
+    if (threadIdx.x == 0) {
+        poff[L] = (int)real_total;
+        long long n_out = n_real >= 0 ? n_real : real_total;   // merge path: every real entry below thr counts
+        *out_n = n_out < K ? n_out : K;
+    }
+}
+
+// Rank merge, step 2: one WARP per surviving element; lanes split the lists, each does a binary
+// search in that list's prefix, a shuffle reduction gives the global rank.
+__global__ void __launch_bounds__(256)
+topk_rank_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, int L, int K,
+                 const int *__restrict__ plen, const int *__restrict__ poff,
+                 double *__restrict__ out_rc, long long *__restrict__ out_id) {
+    const int lane = lane_id();
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int total = poff[L];
+    for (long long w = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < total; w += n_warps) {
+        // list owning work item w: last l with poff[l] <= w
+        int lo = 0, hi = L;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (poff[mid] <= w) lo = mid; else hi = mid; }
+        const int l = lo, i = (int)(w - poff[l]);
+        const Cand c{lists_rc[(long long)l * K + i], lists_id[(long long)l * K + i]};
+        int rank = 0;
+        for (int m = lane; m < L; m += 32) {
+            if (m == l) rank += i;
+            else {
+                const int len = plen[m];
+                if (len) rank += lower_bound_list(lists_rc + (long long)m * K, lists_id + (long long)m * K, len, c);
+            }
+        }
+        rank = warp_sum(rank);
+        if (lane == 0 && rank < K) { out_rc[rank] = c.rc; out_id[rank] = c.id; }
     }
 }
 
@@ -218,7 +331,7 @@ extern "C" size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K) {
     if (cand_cap < 0 || K < 0) return 0;
     if (K <= SX_TOPK_MAX_K) {
         const size_t L = ((size_t)cand_cap + kTkSlice - 1) / kTkSlice + 1;
-        return carve_bytes(L * (size_t)(K > 0 ? K : 1), 8) * 2 + 256;
+        return carve_bytes(L * (size_t)(K > 0 ? K : 1), 8) * 2 + 2 * carve_bytes(L + 2, 4) + 256;
     }
     return 2 * carve_bytes((size_t)cand_cap, 8) + 2 * carve_bytes((size_t)cand_cap, 4) +
            sx_argsort_workspace_bytes(cand_cap) + 256;
@@ -245,8 +358,12 @@ extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id,
         topk_slice_sort_kernel<<<L, kTkThreads, smem, st>>>(cand_rc, (const long long *)cand_id, n_cand_dev, cand_cap,
                                                             (int)K, lists_rc, lists_id);
         SX_LAUNCH_CHECK();
-        topk_rank_merge_kernel<<<tk_grid((long long)L * K, 256), 256, 0, st>>>(
-            lists_rc, lists_id, L, (int)K, n_cand_dev, cand_cap, out_rc, (long long *)out_id, (long long *)out_n);
+        int *plen = cv.take<int>(L + 2), *poff = cv.take<int>(L + 2);
+        topk_prep_kernel<<<1, 1024, 0, st>>>(lists_rc, lists_id, L, (int)K, n_cand_dev, cand_cap, plen, poff,
+                                             (long long *)out_n);
+        SX_LAUNCH_CHECK();
+        topk_rank_kernel<<<kNumSMs * 4, 256, 0, st>>>(lists_rc, lists_id, L, (int)K, plen, poff, out_rc,
+                                                      (long long *)out_id);
         SX_LAUNCH_CHECK();
         return SX_OK;
     }
@@ -274,15 +391,27 @@ extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id,
     return SX_OK;
 }
 
+extern "C" size_t sx_topk_merge_workspace_bytes(int64_t G) {
+    if (G < 0) return 0;
+    return 2 * carve_bytes((size_t)G + 2, 4) + 256;
+}
+
 extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t G, int64_t K,
-                             double *out_rc, int64_t *out_id, int64_t *out_n, void *stream) {
+                             double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
+                             void *stream) {
     if (G <= 0 || K <= 0 || !blocks_rc || !blocks_id || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
     if (G > (1 << 20) || K > (1ll << 30)) return SX_ERR_TOO_LARGE;
+    if (!ws || ws_bytes < sx_topk_merge_workspace_bytes(G)) return SX_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(ws);
+    int *plen = cv.take<int>(G + 2), *poff = cv.take<int>(G + 2);
     topk_fill_kernel<<<(int)((K + 255) / 256), 256, 0, st>>>(out_rc, (long long *)out_id, (long long *)out_n, (int)K);
     SX_LAUNCH_CHECK();
-    topk_rank_merge_kernel<<<tk_grid(G * K, 256), 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, (int)G, (int)K,
-                                                               nullptr, 0, out_rc, (long long *)out_id, (long long *)out_n);
+    topk_prep_kernel<<<1, 1024, 0, st>>>(blocks_rc, (const long long *)blocks_id, (int)G, (int)K, nullptr, 0, plen, poff,
+                                         (long long *)out_n);
+    SX_LAUNCH_CHECK();
+    topk_rank_kernel<<<kNumSMs * 4, 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, (int)G, (int)K, plen, poff,
+                                                  out_rc, (long long *)out_id);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }

@@ -244,6 +244,7 @@ def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor):
     out_rc = torch.empty(K, dtype=torch.float64, device=blocks_rc.device)
     out_id = torch.empty(K, dtype=torch.int64, device=blocks_rc.device)
     out_n = torch.zeros(1, dtype=torch.int64, device=blocks_rc.device)
+    ws = _ws(lib.sx_topk_merge_workspace_bytes(G), blocks_rc.device)
     check(lib.sx_topk_merge(_ptr(blocks_rc), _ptr(blocks_id), G, K, _ptr(out_rc), _ptr(out_id), _ptr(out_n),
-                            _stream()), "sx_topk_merge")
+                            _ptr(ws), ws.numel(), _stream()), "sx_topk_merge")
     return out_rc, out_id, out_n
