@@ -1,0 +1,429 @@
+"""Problem managers of the network crossover: `OTManager`, `MCFManagerStd`, `NetworkManager`.
+
+Same public surface as the reference (`network_methods/net_manager.py:14-509`): the nine
+protocol methods plus the concrete extras the driver uses (`get_mcf`, `extend_by_bigM`,
+`set_initial_basis`, `rescale_cost`, `fix_variables`, `get_reduced_cost_for_original_OT/_mcf`,
+`get_sub_problem`, `get_X`) and the public fields (`ot`, `mcf`, `mask_sub_ot`,
+`artificial_vars`, `var_info`, `c_rescaling_factor`).  What changed is where the arithmetic
+runs:
+
+  get_sorted_flows                      -> sx_score_ot / sx_score_mcf + sx_argsort_f64 (device)
+  get_reduced_cost_for_original_* and
+  check_optimality_condition            -> sx_price_dense_ot / sx_price_arcs (device), fused count
+  price (new; north_star top-k)         -> + sx_topk_select
+
+The problem data (cost matrix or arc list) is uploaded to the GPU once, on first use, and stays
+resident; per call only the duals go up and a few hundred bytes come back.  Sub-problem
+extraction, basis bookkeeping and the LP re-solve stay on the host, as in the reference; the
+restricted master is assembled directly from arc ids instead of slicing the full 2n-nonzero
+incidence matrix every round (`net_manager.py:450-455`).  There is no CPU fallback for the
+device steps: without a CUDA device they raise.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import scipy.sparse as sp
+from typing_extensions import Protocol
+
+from smart_crossover.formats import MinCostFlow, OptTransport
+from smart_crossover.output import Basis, Output
+from smart_crossover.parameters import TOLERANCE_FOR_ARTIFICIAL_VARS, TOLERANCE_FOR_REDUCED_COSTS
+from smart_crossover.solver_caller.caller import SolverSettings
+from smart_crossover.solver_caller.solving import solve_mcf
+
+
+class NetworkManager(Protocol):
+    """What `column_generation` needs from a manager (reference `net_manager.py:14-113`)."""
+
+    m: int
+    n: int
+    basis: Basis
+
+    def get_sorted_flows(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]: ...
+    def recover_x_from_sub_x(self, x_sub: np.ndarray) -> np.ndarray: ...
+    def recover_basis_from_sub_basis(self, basis_sub: Basis) -> Basis: ...
+    def solve_subproblem(self, solver: str, solver_settings: SolverSettings) -> Output: ...
+    def recover_obj_val(self, obj_val: float) -> float: ...
+    def check_optimality_condition(self, x: np.ndarray, y: np.ndarray) -> bool: ...
+    def add_free_variables(self, ind_free: np.ndarray) -> None: ...
+    def update_subproblem(self) -> None: ...
+    def set_basis(self, basis: Basis) -> None: ...
+
+
+def _dev():
+    """The device operators; importing them needs torch + libsxcross and fails loudly otherwise."""
+    from smart_crossover import device
+    return device
+
+
+def _cuda(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+class _SortedFlows:
+    """Device-resident result of one `get_sorted_flows` call, kept so that the tree build
+    (`tree_BI.max_weight_spanning_tree`) can reuse the sort instead of repeating it."""
+
+    def __init__(self, scores_t, scores_np):
+        dev = _dev()
+        self.scores_t = scores_t
+        self.scores_np = scores_np
+        self.order, self.sorted_key = dev.argsort_f64(scores_t)
+
+    def queue(self) -> np.ndarray:
+        return _dev().queue_from_order(self.order).cpu().numpy()
+
+    def kruskal_order(self):
+        return _dev().kruskal_order(self.sorted_key, self.order)
+
+    def matches(self, weights: np.ndarray) -> bool:
+        return weights is self.scores_np or (weights.shape == self.scores_np.shape
+                                             and np.array_equal(weights, self.scores_np, equal_nan=True))
+
+
+# =================================================================================================
+class OTManager:
+    """Optimal-transport manager (reference `net_manager.py:322-509`).
+
+    After `extend_by_bigM` the host-side `ot` is the (S+1) x (D+1) extended problem exactly as in
+    the reference, but the device keeps the original S x D cost matrix: the S + D + 1 artificial
+    arcs are priced on the host from their closed form (bigM on the border, 0 in the corner).
+    """
+
+    def __init__(self, ot: OptTransport) -> None:
+        self.ot = ot
+        self.m = ot.s.size + ot.d.size
+        self.n = ot.s.size * ot.d.size
+        self.mask_sub_ot = np.zeros(self.n, dtype=bool)
+        self.artificial_vars = np.array([])
+        self._S0, self._D0 = ot.s.size, ot.d.size       # shape of the device-resident block
+        self._M_dev = None
+        self._mcf = None
+        self._sorted = None
+        self._bigM = None
+
+    # ---- lazily built host / device state ---------------------------------------------------------
+    @property
+    def mcf(self) -> MinCostFlow:
+        """MCF form of the current OT (`get_mcf`, reference :353-355); built on first access."""
+        if self._mcf is None:
+            self._mcf = self.ot.to_MCF()
+        return self._mcf
+
+    @mcf.setter
+    def mcf(self, value) -> None:
+        self._mcf = value
+
+    def get_mcf(self) -> None:
+        self._mcf = self.ot.to_MCF()
+
+    def _device_cost(self):
+        if self._M_dev is None:
+            M = np.asarray(self.ot.M, dtype=np.float64)
+            self._M_dev = _cuda(M[:self._S0, :self._D0])
+        return self._M_dev
+
+    def get_X(self, x: np.ndarray) -> np.ndarray:
+        return x.reshape((self.ot.s.size, self.ot.d.size))
+
+    # ---- K1: scores + sorted queue --------------------------------------------------------------------
+    def get_sorted_flows(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Flow indicators max(x_ij/s_i, x_ij/d_j) and the arcs sorted by them, largest first
+        (stable sort: ties by descending arc id).  Reference :368-379."""
+        dev = _dev()
+        scores_t = dev.score_ot(_cuda(np.asarray(x, dtype=np.float64).ravel()),
+                                _cuda(np.asarray(self.ot.s, dtype=np.float64)),
+                                _cuda(np.asarray(self.ot.d, dtype=np.float64)))
+        scores = scores_t.cpu().numpy()
+        self._sorted = _SortedFlows(scores_t, scores)
+        return self._sorted.queue(), scores
+
+    # ---- big-M extension ----------------------------------------------------------------------------------
+    def extend_by_bigM(self, bigM: float) -> None:
+        """Artificial source and sink joined to everything at cost bigM (reference :381-400)."""
+        S, D = self.ot.s.size, self.ot.d.size
+        M_ext = np.full((S + 1, D + 1), float(bigM))
+        M_ext[:S, :D] = self.ot.M
+        M_ext[S, D] = 0.0
+        mask = np.zeros((S + 1, D + 1), dtype=np.bool_)
+        mask[S, :] = True
+        mask[:, D] = True
+        self.mask_sub_ot = mask
+        self.artificial_vars = np.where(mask.ravel())[0]
+        self._device_cost()                                   # keep the S x D block resident
+        self._bigM = float(bigM)
+        self.ot = OptTransport(np.append(self.ot.s, np.sum(self.ot.d)),
+                               np.append(self.ot.d, np.sum(self.ot.s)), M_ext)
+        self._mcf = None
+        self._sorted = None
+
+    # ---- sub-problem bookkeeping (host) ---------------------------------------------------------------------
+    def add_free_variables(self, ind_free: np.ndarray) -> None:
+        """Open columns of the restricted master.  Accepts arc ids of the ORIGINAL problem or, as the
+        `tnet` driver passes (algorithms.py:58), a boolean mask over them.  Reference :402-414."""
+        if self.artificial_vars.size > 0:
+            inner = self.mask_sub_ot[:-1, :-1]
+            rows, cols = np.unravel_index(ind_free, inner.shape)
+            inner[rows, cols] = True
+        else:
+            self.mask_sub_ot[np.asarray(ind_free).ravel()] = True
+
+    def set_basis(self, basis: Basis) -> None:
+        self.basis = basis
+
+    def recover_x_from_sub_x(self, x_sub: np.ndarray) -> np.ndarray:
+        x = np.zeros(self.ot.s.size * self.ot.d.size)
+        x[self.mask_sub_ot.ravel()] = x_sub
+        return x
+
+    def recover_basis_from_sub_basis(self, basis_sub: Basis) -> Basis:
+        vbasis = -np.ones(self.ot.s.size * self.ot.d.size)
+        vbasis[self.mask_sub_ot.ravel()] = basis_sub.vbasis
+        return Basis(vbasis, basis_sub.cbasis)
+
+    def get_sub_problem(self) -> MinCostFlow:
+        """Restricted master over the open columns (ascending arc id), assembled straight from the
+        arc ids: column k = (i, j) has -1 at row i and +1 at row S + j.  Equals the reference's
+        `self.mcf.A.tocsc()[:, mask]` (:450-455) without touching the full matrix."""
+        S, D = self.ot.s.size, self.ot.d.size
+        ids = np.flatnonzero(self.mask_sub_ot.ravel())
+        k = ids.size
+        rows = np.empty(2 * k, dtype=np.int64)
+        rows[0::2] = ids // D
+        rows[1::2] = S + ids % D
+        vals = np.empty(2 * k)
+        vals[0::2] = -1.0
+        vals[1::2] = 1.0
+        A = sp.csc_matrix((vals, rows, np.arange(0, 2 * k + 1, 2)), shape=(S + D, k))
+        return MinCostFlow(A=A, b=np.hstack([-self.ot.s, self.ot.d]),
+                           c=np.asarray(self.ot.M).ravel()[ids], u=np.full(k, np.inf))
+
+    def solve_subproblem(self, solver: str, solver_settings: SolverSettings) -> Output:
+        method = "network_simplex" if solver == "CPL" else "default"
+        warm = Basis(self.basis.vbasis[self.mask_sub_ot.ravel()], self.basis.cbasis)
+        return solve_mcf(self.get_sub_problem(), solver=solver, method=method, warm_start_basis=warm,
+                         settings=solver_settings)
+
+    def recover_obj_val(self, obj_val):
+        return obj_val
+
+    def update_subproblem(self):
+        """Nothing to rebuild for OT: the open columns live in `mask_sub_ot` (reference :499-501)."""
+
+    def set_initial_basis(self) -> None:
+        vbasis = -np.ones(self.ot.s.size * self.ot.d.size)
+        vbasis[self.artificial_vars] = 0
+        self.basis = Basis(vbasis, np.concatenate([-np.ones(self.m + 1), np.zeros(1)]))
+
+    # ---- K4: pricing ---------------------------------------------------------------------------------------------
+    def _split_duals(self, y: np.ndarray):
+        """(source duals, sink duals) of the device block inside the current node numbering."""
+        y = np.asarray(y, dtype=np.float64)
+        S_cur = self.ot.s.size
+        return y[:self._S0], y[S_cur:S_cur + self._D0]
+
+    def _border_reduced_costs(self, y: np.ndarray):
+        """Reduced costs of the artificial arcs (last row and last column of the extended matrix)."""
+        S, D = self._S0, self._D0
+        y = np.asarray(y, dtype=np.float64)
+        row = np.append(np.full(D, self._bigM), 0.0) - (y[S + 1:S + D + 2] - y[S])      # arcs (S, j), j = 0..D
+        col = np.full(S, self._bigM) - (y[S + 1 + D] - y[:S])                            # arcs (i, D), i < S
+        return row, col
+
+    def price(self, y: np.ndarray, K: int = 0, want_rc: bool = False):
+        """One pricing pass: violator count, min reduced cost and the K most violating arcs
+        (ids in the current arc numbering).  north_star extension; see `device.PriceResult`."""
+        dev = _dev()
+        import torch
+        M = self._device_cost()
+        u, v = self._split_duals(y)
+        y_dev = _cuda(np.concatenate([u, v]))
+        res = dev.price_dense_ot(M, y_dev, K=K, tol=TOLERANCE_FOR_REDUCED_COSTS, want_rc=want_rc)
+        if self._bigM is None:
+            return res
+        # extended problem: re-index the block's arcs into (S+1) x (D+1) and add the border arcs
+        S, D = self._S0, self._D0
+        row, col = self._border_reduced_costs(y)
+        ids = res.topk_id // D * (D + 1) + res.topk_id % D
+        b_ids = np.concatenate([S * (D + 1) + np.arange(D + 1), np.arange(S) * (D + 1) + D])
+        b_rc = np.concatenate([row, col])
+        viol = b_rc < -TOLERANCE_FOR_REDUCED_COSTS
+        all_ids = np.concatenate([ids, b_ids[viol]])
+        all_rc = np.concatenate([res.topk_rc, b_rc[viol]])
+        o = np.lexsort((all_ids, all_rc))[:K] if K > 0 else np.zeros(0, dtype=np.int64)
+        out = dev.PriceResult(res.n_violating + int(viol.sum()), float(min(res.min_rc, b_rc.min())),
+                              all_ids[o].astype(np.int64), all_rc[o])
+        if want_rc:
+            full = np.empty((S + 1, D + 1))
+            full[:S, :D] = res.rc.cpu().numpy().reshape(S, D)
+            full[S, :] = row
+            full[:S, D] = col
+            out.rc = torch.from_numpy(full.ravel())
+        return out
+
+    def get_reduced_cost_for_original_OT(self, y: np.ndarray) -> np.ndarray:
+        """rc = c - A^T y over every arc of the current OT (reference :474-483)."""
+        return self.price(y, K=0, want_rc=True).rc.cpu().numpy()
+
+    def check_optimality_condition(self, x: np.ndarray, y: np.ndarray) -> bool:
+        """All reduced costs >= -1e-6 and no flow left on artificial arcs (reference :485-497)."""
+        art_ok = bool(np.all(x[self.artificial_vars][:-1] < TOLERANCE_FOR_ARTIFICIAL_VARS)) \
+            if self.artificial_vars.size > 0 else True
+        return bool(art_ok and self.price(y, K=0).n_violating == 0)
+
+
+# =================================================================================================
+class MCFManagerStd:
+    """Min-cost-flow manager (reference `net_manager.py:116-319`)."""
+
+    def __init__(self, mcf: MinCostFlow) -> None:
+        self.mcf = mcf
+        self.m = self.mcf.b.size
+        self.n = self.mcf.c.size
+        self.var_info = {"non_fix": np.arange(self.n, dtype=np.int64)}
+        self.artificial_vars = np.array([])
+        self.c_rescaling_factor = None
+        self._arcs_dev = None
+        self._sorted = None
+
+    # ---- arc list of the current incidence matrix (host scan once per matrix, then device resident) ------
+    @staticmethod
+    def _endpoints(A) -> Tuple[np.ndarray, np.ndarray]:
+        """tail = row of the +1, head = row of the -1 of every column (`scripts/min2mcf.py:36-37`);
+        -1 where a column lacks that entry."""
+        A = sp.csc_matrix(A)
+        E = A.shape[1]
+        cols = np.repeat(np.arange(E, dtype=np.int64), np.diff(A.indptr))
+        tail = np.full(E, -1, dtype=np.int64)
+        head = np.full(E, -1, dtype=np.int64)
+        tail[cols[A.data > 0]] = A.indices[A.data > 0]
+        head[cols[A.data < 0]] = A.indices[A.data < 0]
+        return tail, head
+
+    def _device_arcs(self):
+        import torch
+        if self._arcs_dev is None or self._arcs_dev["A"] is not self.mcf.A:
+            tail, head = self._endpoints(self.mcf.A)
+            if (tail < 0).any() or (head < 0).any():
+                raise ValueError("every column of A must have one +1 and one -1 entry")
+            self._arcs_dev = {"A": self.mcf.A, "tail": _cuda(tail, torch.int32), "head": _cuda(head, torch.int32),
+                              "c": None, "c_src": None}
+        d = self._arcs_dev
+        if d["c_src"] is not self.mcf.c:
+            d["c"] = _cuda(np.asarray(self.mcf.c, dtype=np.float64))
+            d["c_src"] = self.mcf.c
+        return d
+
+    # ---- K1 -----------------------------------------------------------------------------------------------------
+    def get_sorted_flows(self, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Flow indicators after reversing arcs with x > u/2, and the arcs sorted by them, largest
+        first (stable).  Reference :156-184; needs finite capacities (u = inf gives NaN there too)."""
+        import torch
+        dev = _dev()
+        A = self.mcf.A.tocsr()
+        if not A.has_sorted_indices:
+            A = A.sorted_indices()
+        arcs = self._device_arcs()
+        scores_t = dev.score_mcf(_cuda(np.asarray(x, dtype=np.float64)), _cuda(np.asarray(self.mcf.u, dtype=np.float64)),
+                                 arcs["tail"], arcs["head"], _cuda(A.indptr, torch.int64),
+                                 _cuda(A.indices, torch.int32), _cuda(np.sign(A.data), torch.int8))
+        scores = scores_t.cpu().numpy()
+        self._sorted = _SortedFlows(scores_t, scores)
+        return self._sorted.queue(), scores
+
+    # ---- big-M extension, rescaling, fixing (host) -----------------------------------------------------------------
+    def extend_by_bigM(self, bigM: float) -> None:
+        """One artificial node joined to every node by an arc of cost bigM, oriented so that it can
+        absorb that node's residual supply once the fixed-at-upper arcs are accounted for
+        (reference :135-154)."""
+        at_up = np.zeros(self.n, dtype=bool)
+        at_up[self.var_info["fix_up"]] = True
+        b_true = self.mcf.b - self.mcf.A.multiply(at_up) @ (self.mcf.u * at_up)
+        sign = np.sign(b_true)
+        sign[sign == 0] = 1
+        A_ext = sp.vstack((sp.hstack((self.mcf.A, sp.diags(sign))),
+                           sp.csr_matrix(np.concatenate([np.zeros(self.n), -sign]))))
+        # the reference sizes the artificial capacities with n instead of m (:148, harmless); m is used here
+        self.mcf = MinCostFlow(A_ext, np.append(self.mcf.b, 0.0),
+                               np.concatenate([self.mcf.c, bigM * np.ones(self.m)]),
+                               np.concatenate([self.mcf.u, np.inf * np.ones(self.m)]))
+        new_ids = np.arange(self.n, self.n + self.m, dtype=np.int64)
+        self.artificial_vars = new_ids.astype(int)
+        self.var_info["non_fix"] = np.append(self.var_info["non_fix"], new_ids)
+
+    def rescale_cost(self, factor: float) -> None:
+        """c <- c / factor.  Like the reference (:282) this rebinds `mcf.c` on the caller's object."""
+        self.mcf.c = self.mcf.c / factor
+        self.c_rescaling_factor = factor
+
+    def recover_obj_val(self, obj_val: float) -> float:
+        return obj_val * self.c_rescaling_factor
+
+    def fix_variables(self, ind_fix_to_low: np.ndarray, ind_fix_to_up: np.ndarray) -> None:
+        everything = np.arange(len(self.mcf.c))
+        self.var_info["fix_low"] = ind_fix_to_low
+        self.var_info["fix_up"] = ind_fix_to_up
+        self.var_info["non_fix"] = np.setdiff1d(everything, np.append(ind_fix_to_low, ind_fix_to_up))
+        self.var_info["fix"] = np.setdiff1d(everything, self.var_info["non_fix"])
+
+    def add_free_variables(self, ind_free_new: np.ndarray) -> None:
+        """Append the new columns in queue order and drop them from the fixed sets (reference :236-245)."""
+        self.var_info["non_fix"] = np.append(self.var_info["non_fix"], ind_free_new)
+        for key in ("fix", "fix_low", "fix_up"):
+            self.var_info[key] = np.setdiff1d(self.var_info[key], ind_free_new)
+
+    def set_initial_basis(self) -> None:
+        vbasis = np.concatenate((-np.ones(self.n), np.zeros(self.m)))
+        vbasis[self.var_info["fix_up"]] = -2
+        self.set_basis(Basis(vbasis, np.concatenate([-np.ones(self.m), np.zeros(1)])))
+
+    def set_basis(self, basis: Basis) -> None:
+        self.basis = basis
+
+    def update_subproblem(self) -> None:
+        nf, up = self.var_info["non_fix"], self.var_info["fix_up"]
+        self.mcf_sub = MinCostFlow(A=self.mcf.A[:, nf], b=self.mcf.b - self.mcf.A[:, up] @ self.mcf.u[up],
+                                   c=self.mcf.c[nf], u=self.mcf.u[nf])
+
+    def solve_subproblem(self, solver: str, solver_settings: SolverSettings) -> Output:
+        method = "network_simplex" if solver == "CPL" else "default"
+        warm = Basis(self.basis.vbasis[self.var_info["non_fix"]], self.basis.cbasis)
+        return solve_mcf(self.mcf_sub, solver=solver, method=method, warm_start_basis=warm, settings=solver_settings)
+
+    def recover_x_from_sub_x(self, x_sub: np.ndarray) -> np.ndarray:
+        x = np.zeros(self.mcf.c.size)
+        x[self.var_info["non_fix"]] = x_sub
+        x[self.var_info["fix_up"]] = self.mcf.u[self.var_info["fix_up"]]
+        return x
+
+    def recover_basis_from_sub_basis(self, basis_sub: Basis) -> Basis:
+        vbasis = -np.ones(self.mcf.c.size, dtype=int)
+        vbasis[self.var_info["non_fix"]] = basis_sub.vbasis
+        vbasis[self.var_info["fix_up"]] = -2
+        return Basis(vbasis, basis_sub.cbasis)
+
+    # ---- K4 ------------------------------------------------------------------------------------------------------
+    def price(self, y: np.ndarray, K: int = 0, want_rc: bool = False):
+        """Arc-list pricing: rc_k = c_k - (y_tail - y_head), negated for arcs at their upper bound."""
+        import torch
+        dev = _dev()
+        arcs = self._device_arcs()
+        vb = _cuda(np.asarray(self.basis.vbasis).astype(np.int8)) if getattr(self, "basis", None) is not None else None
+        return dev.price_arcs(arcs["c"], arcs["tail"], arcs["head"], _cuda(np.asarray(y, dtype=np.float64)), vbasis=vb,
+                              K=K, tol=TOLERANCE_FOR_REDUCED_COSTS, want_rc=want_rc)
+
+    def get_reduced_cost_for_original_mcf(self, y: np.ndarray) -> np.ndarray:
+        """Reference :293-304."""
+        return self.price(y, K=0, want_rc=True).rc.cpu().numpy()
+
+    def check_optimality_condition(self, x: np.ndarray, y: np.ndarray) -> bool:
+        """Reference :306-319."""
+        art_ok = bool(np.all(x[self.artificial_vars] < TOLERANCE_FOR_ARTIFICIAL_VARS)) \
+            if self.artificial_vars.size > 0 else True
+        return bool(art_ok and self.price(y, K=0).n_violating == 0)

@@ -1,0 +1,135 @@
+"""Tree basis identification for optimal transport (TNET), reference `network_methods/tree_BI.py`.
+
+  max_weight_spanning_tree  -> device: stable radix argsort of the weights, Kruskal order,
+                               chunked Kruskal with a lock-free union-find (sx_kruskal)
+  tree_potentials           -> device: Euler tour + list ranking (sx_tree_potentials); new, the
+                               reference reads duals from the LP solver instead
+  push_tree_to_bfs          -> host: the tree primal solve uses the same (N-1) x (N-1) sparse system
+                               as the reference (`B x = b[:-1]`, tree_BI.py:74-76) but builds B from the
+                               tree arcs directly, and the sequential push loop (tree_BI.py:81-110)
+                               walks the O(N + pushes) non-zeros instead of a dense S x D scratch.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg
+
+from smart_crossover.formats import OptTransport
+from smart_crossover.network_methods.net_manager import OTManager, _SortedFlows, _cuda, _dev
+from smart_crossover.output import Basis
+
+
+def tree_basis_identify(ot_manager: OTManager, flow_weights: np.ndarray) -> Tuple[Basis, int]:
+    """Max-weight spanning tree of the flow weights, pushed to a basic feasible solution.
+    Returns the basis (last node's row is the redundant one: cbasis = [-1]*(m-1) + [0]) and the
+    number of push iterations.  Reference `tree_BI.py:12-29`."""
+    tree = max_weight_spanning_tree(ot_manager.ot, flow_weights, _sorted=ot_manager._sorted)
+    vbasis, push_iter = push_tree_to_bfs(ot_manager, tree)
+    cbasis = np.concatenate([-np.ones(ot_manager.m - 1), np.array([0])])
+    return Basis(vbasis, cbasis), push_iter
+
+
+def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlows = None):
+    """(tree arc ids on the device, their number) for the complete bipartite graph of `ot`."""
+    dev = _dev()
+    S, D = np.asarray(ot.M).shape
+    flow_weights = np.asarray(flow_weights, dtype=np.float64)
+    if _sorted is None or not _sorted.matches(flow_weights):
+        _sorted = _SortedFlows(_cuda(flow_weights), flow_weights)
+    if np.isnan(_sorted.scores_np).any():
+        raise ValueError("flow weights contain NaN (a zero marginal?): the spanning tree is undefined")
+    tree_t, n_t = dev.kruskal(_sorted.kruskal_order(), S + D, S=S, D=D)
+    return tree_t, int(n_t.item())
+
+
+def max_weight_spanning_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlows = None) -> np.ndarray:
+    """Arc ids (ascending) of the maximum-weight spanning tree of K_{S,D}: Kruskal in the order
+    'descending weight, ties by ascending arc id'.  Like the reference, tree arcs whose weight is
+    exactly zero are dropped from the result (`np.flatnonzero` on the dense tree, tree_BI.py:56)."""
+    tree_t, nt = _device_tree(ot, flow_weights, _sorted)
+    tree = tree_t[:nt].cpu().numpy()
+    return tree[np.asarray(flow_weights)[tree] != 0]
+
+
+def tree_potentials(ot: OptTransport, tree: np.ndarray) -> np.ndarray:
+    """Duals y of the tree basis: y[S+j] - y[i] = M[i, j] on tree arcs, y[last node] = 0
+    (B^T y[:-1] = c[tree]; reference gets these from the solver, algorithms.py:132)."""
+    dev = _dev()
+    M = np.asarray(ot.M, dtype=np.float64)
+    S, D = M.shape
+    y = dev.tree_potentials(_cuda(np.asarray(tree, dtype=np.int64)), int(len(tree)), S + D, _cuda(M), S + D - 1, S=S, D=D)
+    return y.cpu().numpy()
+
+
+def push_tree_to_bfs(ot_manager: OTManager, tree: np.ndarray) -> Tuple[np.ndarray, int]:
+    """Tree primal flows, then 'irrigation' pushes until no tree flow is negative.
+    Returns (vbasis, push_iter) with vbasis = 0 on arcs carrying positive flow, -1 elsewhere."""
+    ot = ot_manager.ot
+    S, D = ot.s.size, ot.d.size
+    tree = np.asarray(tree, dtype=np.int64)
+    T = tree.size
+    ti, tj = tree // D, tree % D
+    # B = A[:-1, tree]: -1 at row i, +1 at row S + j, last node row dropped
+    rows = np.concatenate([ti, S + tj])
+    cols = np.concatenate([np.arange(T), np.arange(T)])
+    vals = np.concatenate([-np.ones(T), np.ones(T)])
+    keep = rows < S + D - 1
+    B = sp.csc_matrix((vals[keep], (rows[keep], cols[keep])), shape=(S + D - 1, T))
+    b = np.hstack([-ot.s, ot.d])[:-1]
+    flow = sp.linalg.spsolve(B, b)
+
+    row_nz = [dict() for _ in range(S)]
+    col_nz = [dict() for _ in range(D)]
+    for i, j, f in zip(ti.tolist(), tj.tolist(), flow.tolist()):
+        row_nz[i][j] = f
+        col_nz[j][i] = f
+
+    def get(i, j):
+        return row_nz[i].get(j, 0.0)
+
+    def put(i, j, val):
+        row_nz[i][j] = val
+        col_nz[j][i] = val
+
+    def argmax(entries, what):
+        """First index of the maximum, as np.argmax over the dense row/column would give; the
+        maximum must be positive (the reference asserts it, tree_BI.py:93)."""
+        best, best_val = -1, 0.0
+        for idx, val in entries.items():
+            if val > best_val or (val == best_val and best >= 0 and idx < best):
+                best, best_val = idx, val
+        assert best >= 0, f"push_tree_to_bfs: no positive flow in this {what}"
+        return best
+
+    negative = [(i, j) for i, j, f in zip(ti.tolist(), tj.tolist(), flow.tolist()) if f < 0]
+    push_iter = 0
+    for I1, J1 in negative:                      # row-major order, fixed before pushing (tree_BI.py:82)
+        if get(I1, J1) >= 0:
+            continue
+        J2 = argmax(row_nz[I1], "row")
+        I2 = argmax(col_nz[J1], "column")
+        while get(I1, J1) < 0:
+            assert get(I2, J1) > 0 and get(I1, J2) > 0
+            assert get(I2, J2) == 0
+            cands = (-get(I1, J1), get(I1, J2), get(I2, J1))
+            flag = int(np.argmin(cands))
+            theta = cands[flag]
+            put(I1, J1, get(I1, J1) + theta)
+            put(I2, J1, get(I2, J1) - theta)
+            put(I1, J2, get(I1, J2) - theta)
+            put(I2, J2, get(I2, J2) + theta)
+            if flag == 1:
+                J2 = argmax(row_nz[I1], "row")
+            elif flag == 2:
+                I2 = argmax(col_nz[J1], "column")
+            push_iter += 1
+
+    vbasis = -np.ones(ot_manager.n)
+    for i in range(S):
+        for j, f in row_nz[i].items():
+            if f > 0:
+                vbasis[i * D + j] = 0
+    return vbasis, push_iter

@@ -1,0 +1,121 @@
+"""End-to-end drop-in check on a B200: `network_crossover` (tnet / cnet_ot / cnet_mcf) through the
+device-backed managers + HiGHS, against the objective and basis the reference produced for the same
+inputs (golden fixtures), and the manager-level calls against the reference's own outputs."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from golden_util import MCF_FULL, OT_FULL, Fixture
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _quiet():
+    from smart_crossover.solver_caller.caller import SolverSettings
+    return SolverSettings(log_console=0)
+
+
+@pytest.mark.parametrize("name", OT_FULL)
+@pytest.mark.parametrize("method", ["tnet", "cnet_ot"])
+def test_network_crossover_ot(name, method):
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.algorithms import network_crossover
+    fx = Fixture(name)
+    ot = OptTransport(fx.inp["s"].copy(), fx.inp["d"].copy(), fx.inp["M"].copy())
+    out = network_crossover(x=fx.inp["x"].copy(), ot=ot, method=method, solver="HGS", solver_settings=_quiet())
+    ref_obj = float(fx.out[f"{method}_obj"])
+    assert abs(out.obj_val - ref_obj) <= 1e-9 * max(1.0, abs(ref_obj))
+    if name != "ot_ties_12x9":
+        # generic inputs: the optimal basis is unique and the simplex path is reproducible.  The
+        # tie-heavy instance (x = s d^T) is degenerate: HiGHS may stop at another optimal basis /
+        # take a different pivot count on another host, so only the objective is pinned there.
+        assert np.array_equal(np.flatnonzero(out.basis.vbasis == 0), fx.out[f"{method}_basic"])
+        assert out.iter_count == int(fx.out[f"{method}_iters"])
+
+
+def test_network_crossover_mcf():
+    from smart_crossover.formats import MinCostFlow
+    from smart_crossover.network_methods.algorithms import network_crossover
+    fx = Fixture("mcf_small_200")
+    tail, head, b, c, u, x = (fx.inp[k] for k in ("tail", "head", "b", "c", "u", "x"))
+    E, N = c.size, b.size
+    A = sp.lil_matrix((N, E), dtype=int)
+    A[head, np.arange(E)] = -1
+    A[tail, np.arange(E)] = 1
+    mcf = MinCostFlow(A=A.tocsr(), b=b.copy(), c=c.copy(), u=u.copy())
+    out = network_crossover(x=x.copy(), mcf=mcf, method="cnet_mcf", solver="HGS", solver_settings=_quiet())
+    ref = float(fx.out["cnet_mcf_obj"])
+    assert abs(out.obj_val - ref) <= 1e-9 * abs(ref)
+    assert abs(out.obj_val - float(fx.out["direct_obj"])) <= 1e-9 * abs(ref)
+    assert out.iter_count == int(fx.out["cnet_mcf_iters"])
+    assert mcf.c.max() == 1.0            # documented side effect: the caller's costs are rescaled
+
+
+@pytest.mark.parametrize("name", OT_FULL)
+def test_manager_calls_match_the_reference(name):
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.net_manager import OTManager
+    from smart_crossover.network_methods.tree_BI import (max_weight_spanning_tree, tree_basis_identify,
+                                                         tree_potentials)
+    fx = Fixture(name)
+    ot = OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"])
+    mgr = OTManager(ot)
+    queue, scores = mgr.get_sorted_flows(fx.inp["x"])
+    assert queue.dtype == np.int64 and np.array_equal(queue, fx.out["queue"])
+    assert scores.tobytes() == fx.out["scores"].tobytes()
+    assert np.array_equal(max_weight_spanning_tree(ot, scores), fx.out["tree"])
+    basis, push_iter = tree_basis_identify(mgr, scores)
+    assert push_iter == int(fx.out["push_iter"]) and np.array_equal(basis.vbasis, fx.out["vbasis_tree"])
+    assert basis.cbasis[-1] == 0 and (basis.cbasis[:-1] == -1).all()
+    y = tree_potentials(ot, fx.out["tree"])
+    np.testing.assert_allclose(y, fx.out["y_tree"], rtol=1e-9, atol=1e-9 * np.abs(fx.inp["M"]).max())
+    for tag in ("tree", "pert"):
+        rc = mgr.get_reduced_cost_for_original_OT(fx.out["y_" + tag])
+        assert rc.tobytes() == fx.out["rc_" + tag].tobytes()
+        assert mgr.check_optimality_condition(fx.inp["x"], fx.out["y_" + tag]) == bool(fx.out["optimal_" + tag])
+
+
+def test_extended_ot_pricing_matches_explicit_extension():
+    """cnet_ot prices the (S+1) x (D+1) big-M problem without copying M to the device: compare with
+    the reference formula applied to the explicitly extended matrix."""
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.net_manager import OTManager
+    from oracle import network_oracle as orc
+    fx = Fixture("ot_rational_30x51")
+    S, D = fx.inp["M"].shape
+    mgr = OTManager(OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"]))
+    mgr.extend_by_bigM(mgr.m * fx.inp["M"].max())
+    rng = np.random.default_rng(3)
+    y = rng.random(S + D + 2) * 0.3
+    rc_ref = orc.reduced_costs_ot(mgr.ot.M, y)
+    assert mgr.get_reduced_cost_for_original_OT(y).tobytes() == rc_ref.tobytes()
+    cnt, mn, ids, vals = orc.price_summary(rc_ref, K=40)
+    res = mgr.price(y, K=40)
+    assert (res.n_violating, res.min_rc) == (cnt, mn)
+    assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+
+
+@pytest.mark.parametrize("name", MCF_FULL)
+def test_mcf_manager_calls_match_the_reference(name):
+    from smart_crossover.formats import MinCostFlow
+    from smart_crossover.network_methods.net_manager import MCFManagerStd
+    from smart_crossover.output import Basis
+    fx = Fixture(name)
+    tail, head, b, c, u, x = (fx.inp[k] for k in ("tail", "head", "b", "c", "u", "x"))
+    E, N = c.size, b.size
+    A = sp.lil_matrix((N, E), dtype=int)
+    A[head, np.arange(E)] = -1
+    A[tail, np.arange(E)] = 1
+    mgr = MCFManagerStd(MinCostFlow(A=A.tocsr(), b=b.copy(), c=c.copy(), u=u.copy()))
+    queue, scores = mgr.get_sorted_flows(x)
+    assert np.array_equal(queue, fx.out["queue"]) and scores.tobytes() == fx.out["scores"].tobytes()
+    mgr.set_basis(Basis(fx.out["vbasis"], -np.ones(N)))
+    assert mgr.get_reduced_cost_for_original_mcf(fx.out["y"]).tobytes() == fx.out["rc"].tobytes()
+    assert mgr.check_optimality_condition(x, fx.out["y"]) == bool(fx.out["optimal"])

@@ -1,0 +1,118 @@
+"""Host-side logic of the drop-in package (no GPU): problem classes, sub-problem assembly, the
+push phase of the tree basis, the HiGHS backend, and the column-generation bookkeeping."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from golden_util import OT_FULL, Fixture
+from smart_crossover.formats import MinCostFlow, OptTransport, ot_incidence
+from smart_crossover.network_methods.net_manager import MCFManagerStd, OTManager
+from smart_crossover.network_methods.tree_BI import push_tree_to_bfs
+from smart_crossover.output import Basis, Output
+from smart_crossover.solver_caller.caller import SolverSettings
+from smart_crossover.solver_caller.solving import generate_solver_caller, solve_mcf, solve_ot
+
+
+def test_problem_classes_validate_like_the_reference():
+    with pytest.raises(ValueError):
+        OptTransport(np.array([0.5, 0.5]), np.array([0.5, 0.4]), np.zeros((2, 2)))       # formats.py:144-145
+    A = sp.csr_matrix(np.array([[1.0, -1.0], [-1.0, 1.0]]))
+    with pytest.raises(ValueError):
+        MinCostFlow(A, np.array([1.0, 0.0]), np.ones(2), np.ones(2))                      # formats.py:120-121
+    mcf = MinCostFlow(A.tocsc(), np.array([1.0, -1.0]), np.ones(2), np.ones(2))
+    assert sp.isspmatrix_csr(mcf.A) and np.array_equal(mcf.l, np.zeros(2)) and mcf.name == "mcf_instance"
+    b = Basis(np.array([0.0, -1.0]), np.array([-1.0]))
+    assert b.vbasis.dtype.kind == "i" and b.cbasis.dtype.kind == "i"                      # output.py:15-17
+
+
+def test_to_mcf_matches_the_reference_layout():
+    S, D = 3, 4
+    rng = np.random.default_rng(0)
+    s = np.full(S, 1 / S); d = np.full(D, 1 / D); M = rng.random((S, D))
+    mcf = OptTransport(s, d, M).to_MCF()
+    # reference formats.py:155-160: A = [-kron(I_S, 1_D^T); kron(1_S^T, I_D)], b = [-s, d], c = M.flatten()
+    ref = sp.vstack([-sp.kron(np.eye(S), np.ones((1, D))), sp.kron(np.ones((1, S)), np.eye(D))]).toarray()
+    assert np.array_equal(mcf.A.toarray(), ref)
+    assert np.array_equal(mcf.b, np.hstack([-s, d])) and np.array_equal(mcf.c, M.flatten())
+    assert np.all(np.isinf(mcf.u)) and np.array_equal(ot_incidence(S, D).toarray(), ref)
+
+
+@pytest.mark.parametrize("name", OT_FULL)
+def test_push_tree_to_bfs_matches_golden(name):
+    fx = Fixture(name)
+    mgr = OTManager(OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"]))
+    vbasis, push_iter = push_tree_to_bfs(mgr, fx.out["tree"])
+    assert push_iter == int(fx.out["push_iter"])
+    assert np.array_equal(vbasis.astype(np.int64), fx.out["vbasis_tree"])
+
+
+@pytest.mark.parametrize("name", OT_FULL)
+def test_sub_problem_assembly_equals_slicing_the_full_matrix(name):
+    fx = Fixture(name)
+    ot = OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"])
+    mgr = OTManager(ot)
+    mgr.add_free_variables(fx.out["queue"][:50])
+    mgr.add_free_variables(fx.out["vbasis_tree"] == 0)          # boolean mask, as the tnet driver passes
+    sub = mgr.get_sub_problem()
+    mask = mgr.mask_sub_ot.ravel()
+    full = ot.to_MCF()
+    assert np.array_equal(sub.A.toarray(), full.A.tocsc()[:, mask].toarray())     # net_manager.py:452
+    assert np.array_equal(sub.c, full.c[mask]) and np.array_equal(sub.b, full.b)
+    x_sub = np.arange(mask.sum(), dtype=float)
+    assert np.array_equal(mgr.recover_x_from_sub_x(x_sub)[mask], x_sub)
+    # big-M extension keeps the reference's host-side layout
+    mgr2 = OTManager(OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"]))
+    mgr2._device_cost = lambda: None                              # no GPU in this test
+    S, D = fx.inp["M"].shape
+    mgr2.extend_by_bigM(7.0)
+    assert mgr2.ot.M.shape == (S + 1, D + 1) and mgr2.ot.M[S, D] == 0 and mgr2.ot.M[0, D] == 7.0
+    assert mgr2.artificial_vars.size == S + D + 1 and mgr2.mask_sub_ot.sum() == S + D + 1
+    mgr2.add_free_variables(np.array([0, D + 1]))                 # original ids -> (0,0) and (1,1)
+    assert mgr2.mask_sub_ot[0, 0] and mgr2.mask_sub_ot[1, 1]
+    mgr2.set_initial_basis()
+    assert mgr2.basis.cbasis.size == S + D + 2 and (mgr2.basis.vbasis[mgr2.artificial_vars] == 0).all()
+
+
+def test_highs_backend_solves_and_reports_like_a_solver_caller():
+    fx = Fixture("ot_c1_40x40")
+    ot = OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"])
+    out = solve_ot(ot, solver="HGS", settings=SolverSettings(log_console=0))
+    assert out.status == "OPTIMAL" and isinstance(out, Output)
+    assert abs(out.obj_val - float(fx.out["tnet_obj"])) <= 1e-9 * abs(out.obj_val)
+    mcf = ot.to_MCF()
+    rc = mcf.c - mcf.A.T @ out.y                                   # dual sign = Gurobi Pi (net_manager.py:483)
+    assert rc.min() >= -1e-6
+    assert (out.basis.vbasis == 0).sum() + (out.basis.cbasis == 0).sum() == mcf.b.size
+    warm = solve_mcf(mcf, solver="HGS", warm_start_basis=out.basis, settings=SolverSettings(log_console=0))
+    assert warm.iter_count == 0 and abs(warm.obj_val - out.obj_val) < 1e-12
+    with pytest.raises(ImportError):
+        generate_solver_caller("GRB")
+    with pytest.raises(ValueError):
+        generate_solver_caller("XYZ")
+
+
+def test_mcf_manager_bookkeeping():
+    fx = Fixture("mcf_small_200")
+    tail, head, b, c, u, x = (fx.inp[k] for k in ("tail", "head", "b", "c", "u", "x"))
+    E, N = c.size, b.size
+    A = sp.csr_matrix((np.concatenate([np.ones(E), -np.ones(E)]),
+                       (np.concatenate([tail, head]), np.concatenate([np.arange(E)] * 2))), shape=(N, E))
+    mcf = MinCostFlow(A, b.copy(), c.copy(), u.copy())
+    mgr = MCFManagerStd(mcf)
+    t2, h2 = mgr._endpoints(A)
+    assert np.array_equal(t2, tail) and np.array_equal(h2, head)
+    mgr.rescale_cost(c.max())
+    assert mcf.c.max() == 1.0 and mgr.recover_obj_val(2.0) == 2.0 * c.max()        # caller's object is rebound
+    mgr.fix_variables(ind_fix_to_up=np.where(x >= u / 2)[0], ind_fix_to_low=np.where(x < u / 2)[0])
+    assert mgr.var_info["non_fix"].size == 0 and mgr.var_info["fix"].size == E
+    mgr.extend_by_bigM(N * 1.0)
+    assert mgr.mcf.A.shape == (N + 1, E + N) and mgr.artificial_vars.size == N
+    assert np.allclose(np.asarray(mgr.mcf.A.sum(axis=0)).ravel(), 0)               # every column: one +1, one -1
+    t3, h3 = mgr._endpoints(mgr.mcf.A)
+    assert (t3 >= 0).all() and (h3 >= 0).all()
+    mgr.update_subproblem()
+    mgr.set_initial_basis()
+    assert mgr.mcf_sub.c.size == N and (mgr.basis.vbasis[mgr.var_info["fix_up"]] == -2).all()
+    mgr.add_free_variables(fx.out["queue"][:10])
+    assert np.array_equal(mgr.var_info["non_fix"][-10:], fx.out["queue"][:10])
+    assert not np.isin(fx.out["queue"][:10], mgr.var_info["fix"]).any()
