@@ -172,7 +172,11 @@ SX_API int    sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm);
  *   cand_cap inside).  out_rc / out_id have capacity K; out_n (device int64) = min(K, n).
  *   Entries past out_n are filled with (+inf, -1) so fixed-size blocks can be all-gathered.
  *   K <= SX_TOPK_MAX_K uses the warp-shuffle bitonic path and needs no host round trip.
- * sx_topk_merge merges G such blocks (as gathered from G ranks) into one.
+ * sx_topk_merge merges G such blocks (as gathered from G ranks) into one.  Block g has its rc
+ *   list at blocks_rc + g * block_stride and its ids at blocks_id + g * block_stride (strides in
+ *   8-byte elements, so the all-gathered buffer is consumed in place).  Optionally folds the G
+ *   pricing headers {n_violating, min_rc_key} found at headers + g * block_stride into
+ *   out_summary = {total n_violating, min key, largest single n_violating}.
  */
 #define SX_TOPK_MAX_K 1024
 SX_API size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K);
@@ -181,9 +185,9 @@ SX_API int    sx_topk_select(const double *cand_rc, const int64_t *cand_id,
                       double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
                       void *stream);
 SX_API size_t sx_topk_merge_workspace_bytes(int64_t G);
-SX_API int    sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t G, int64_t K,
-                     double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
-                     void *stream);
+SX_API int    sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t block_stride,
+                     int64_t G, int64_t K, const int64_t *headers, double *out_rc, int64_t *out_id,
+                     int64_t *out_n, int64_t *out_summary, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- host-buffer entry point (what a reference-side binding calls with NumPy arrays) ----
  * One pricing pass with HOST buffers: uploads y (and M if M_dev == NULL), prices, selects

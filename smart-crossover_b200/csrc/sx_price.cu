@@ -126,7 +126,7 @@ __device__ __forceinline__ void warp_flush(const CandSink &sink, const WarpTally
 
 // Block-level min -> one atomicMin per CTA.
 __device__ __forceinline__ void block_min_commit(double tmin, sx_price_header *hdr, long long *smem_scratch,
-                                                 int n_warps, int warp) {
+                                                 int n_warps, int warp, unsigned long long n_priced) {
     long long k = f64_to_min_key(tmin);
     k = warp_min(k);
     if (lane_id() == 0) smem_scratch[warp] = k;
@@ -135,6 +135,7 @@ __device__ __forceinline__ void block_min_commit(double tmin, sx_price_header *h
         long long m = smem_scratch[0];
         for (int w = 1; w < n_warps; ++w) m = smem_scratch[w] < m ? smem_scratch[w] : m;
         atomicMin(&hdr->min_rc_key, m);
+        if (blockIdx.x == 0) atomicAdd(&hdr->n_priced, n_priced);
     }
 }
 
@@ -328,6 +329,7 @@ price_dense_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DensePara
         long long m = scratch[0];
         for (int w = 1; w < CWARPS; ++w) m = scratch[w] < m ? scratch[w] : m;
         atomicMin(&p.sink.hdr->min_rc_key, m);
+        if (blockIdx.x == 0) atomicAdd(&p.sink.hdr->n_priced, (unsigned long long)(p.S_loc * p.D));
     }
 }
 
@@ -422,7 +424,7 @@ price_dense_direct_kernel(const double *__restrict__ M, long long ld, const Dens
         if (cb >= p.n_col_blocks) { cb -= p.n_col_blocks; ++rt; }
     }
     warp_flush(p.sink, tally);
-    block_min_commit(tmin, p.sink.hdr, scratch, kDirectThreads / 32, warp);
+    block_min_commit(tmin, p.sink.hdr, scratch, kDirectThreads / 32, warp, (unsigned long long)(p.S_loc * p.D));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -488,7 +490,7 @@ price_arcs_kernel(const double *__restrict__ c, const int32_t *__restrict__ tail
         }
     }
     warp_flush(sink, tally);
-    block_min_commit(tmin, sink.hdr, scratch, kArcThreads / 32, warp);
+    block_min_commit(tmin, sink.hdr, scratch, kArcThreads / 32, warp, (unsigned long long)E);
 }
 
 __global__ void header_reset_kernel(sx_price_header *h) {
@@ -496,9 +498,6 @@ __global__ void header_reset_kernel(sx_price_header *h) {
     h->min_rc_key  = 0x7fffffffffffffffll;
     h->n_priced    = 0ull;
     h->reserved    = 0ull;
-}
-__global__ void header_add_priced_kernel(sx_price_header *h, unsigned long long n) {
-    atomicAdd(&h->n_priced, n);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -630,10 +629,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
         }
         SX_LAUNCH_CHECK();
     }
-    if (rc != SX_OK) return rc;
-    header_add_priced_kernel<<<1, 1, 0, st>>>(header, (unsigned long long)(S_loc * D));
-    SX_LAUNCH_CHECK();
-    return SX_OK;
+    return rc;
 }
 
 extern "C" int sx_price_arcs(const double *c, const int32_t *tail, const int32_t *head,
@@ -650,8 +646,6 @@ extern "C" int sx_price_arcs(const double *c, const int32_t *tail, const int32_t
     long long grid = (long long)kNumSMs * 8;
     if (grid > n_chunks) grid = n_chunks;
     price_arcs_kernel<<<(int)grid, kArcThreads, 0, st>>>(c, tail, head, vbasis, y, E, id0, -tol, sink, rc_out);
-    SX_LAUNCH_CHECK();
-    header_add_priced_kernel<<<1, 1, 0, st>>>(header, (unsigned long long)E);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }

@@ -156,9 +156,21 @@ __global__ void topk_fill_kernel(double *out_rc, long long *out_id, long long *o
 //              prefix of each list with elements <= thr can be in the answer;
 //   plen[l]  = length of that prefix;  poff[l] = exclusive prefix sum;  poff[L] = work total.
 __global__ void __launch_bounds__(1024)
-topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, int L, int K,
-                 const unsigned long long *n_cand_dev, long long cand_cap, int *__restrict__ plen,
-                 int *__restrict__ poff, long long *out_n) {
+topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, long long LS, int L,
+                 int K, const unsigned long long *n_cand_dev, long long cand_cap, int *__restrict__ plen,
+                 int *__restrict__ poff, double *__restrict__ out_rc, long long *__restrict__ out_id,
+                 long long *out_n, const long long *headers, long long *out_summary) {
+    // outputs start as padding; the rank kernel (next launch) overwrites the first out_n entries
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { out_rc[i] = INFINITY; out_id[i] = -1; }
+    if (headers && out_summary && threadIdx.x == 0) {
+        // fold the per-rank pricing headers {n_violating, min_rc_key}: total, min, largest single count
+        long long tot = 0, mn = 0x7fffffffffffffffll, mx = 0;
+        for (int l = 0; l < L; ++l) {
+            const long long c = headers[(long long)l * LS], k = headers[(long long)l * LS + 1];
+            tot += c; mn = k < mn ? k : mn; mx = c > mx ? c : mx;
+        }
+        out_summary[0] = tot; out_summary[1] = mn; out_summary[2] = mx;
+    }
     __shared__ Cand s_thr[32];
     __shared__ int  s_warp[32];
     __shared__ int  s_carry;
@@ -199,8 +211,8 @@ topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restric
     Cand thr = cand_pad();
     long long n_real_lists = 0;
     for (int l = threadIdx.x; l < Lu; l += blockDim.x) {
-        const long long *ids = lists_id + (long long)l * K;
-        const Cand c{lists_rc[(long long)l * K + K - 1], ids[K - 1]};
+        const long long *ids = lists_id + (long long)l * LS;
+        const Cand c{lists_rc[(long long)l * LS + K - 1], ids[K - 1]};
         if (cand_less_p(c, thr)) thr = c;
         int lo = 0, hi = K;                              // real length of the list: first padding entry
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (ids[mid] >= 0) lo = mid + 1; else hi = mid; }
@@ -224,7 +236,7 @@ topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restric
         for (int l = threadIdx.x; l < Lu; l += blockDim.x) {
             const int take = plen[l] < lo ? plen[l] : lo;
             if (take > 0) {
-                const Cand c{lists_rc[(long long)l * K + take - 1], lists_id[(long long)l * K + take - 1]};
+                const Cand c{lists_rc[(long long)l * LS + take - 1], lists_id[(long long)l * LS + take - 1]};
                 if (cand_less_p(deep, c)) deep = c;
             }
         }
@@ -237,11 +249,11 @@ topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restric
     for (int base = 0; base < L; base += blockDim.x) {
         const int l = base + threadIdx.x;
         int len = 0;
-        if (l < Lu) len = upper_bound_list(lists_rc + (long long)l * K, lists_id + (long long)l * K, K, thr);
+        if (l < Lu) len = upper_bound_list(lists_rc + (long long)l * LS, lists_id + (long long)l * LS, K, thr);
         // do not count padding (id < 0) that ties with an all-padding threshold
         if (l < Lu && len > 0) {
             int lo = 0, hi = len;                       // first padding entry within [0, len)
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (lists_id[(long long)l * K + mid] >= 0) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (lists_id[(long long)l * LS + mid] >= 0) lo = mid + 1; else hi = mid; }
             len = lo;
         }
         int incl = len;
@@ -270,8 +282,8 @@ topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restric
 // Rank merge, step 2: one WARP per surviving element; lanes split the lists, each does a binary
 // search in that list's prefix, a shuffle reduction gives the global rank.
 __global__ void __launch_bounds__(256)
-topk_rank_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, int L, int K,
-                 const int *__restrict__ plen, const int *__restrict__ poff,
+topk_rank_kernel(const double *__restrict__ lists_rc, const long long *__restrict__ lists_id, long long LS, int L,
+                 int K, const int *__restrict__ plen, const int *__restrict__ poff,
                  double *__restrict__ out_rc, long long *__restrict__ out_id) {
     const int lane = lane_id();
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -281,13 +293,13 @@ topk_rank_kernel(const double *__restrict__ lists_rc, const long long *__restric
         int lo = 0, hi = L;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (poff[mid] <= w) lo = mid; else hi = mid; }
         const int l = lo, i = (int)(w - poff[l]);
-        const Cand c{lists_rc[(long long)l * K + i], lists_id[(long long)l * K + i]};
+        const Cand c{lists_rc[(long long)l * LS + i], lists_id[(long long)l * LS + i]};
         int rank = 0;
         for (int m = lane; m < L; m += 32) {
             if (m == l) rank += i;
             else {
                 const int len = plen[m];
-                if (len) rank += lower_bound_list(lists_rc + (long long)m * K, lists_id + (long long)m * K, len, c);
+                if (len) rank += lower_bound_list(lists_rc + (long long)m * LS, lists_id + (long long)m * LS, len, c);
             }
         }
         rank = warp_sum(rank);
@@ -348,9 +360,11 @@ extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id,
     Carver cv(ws);
     if (K <= SX_TOPK_MAX_K) {
         const int L = (int)((cand_cap + kTkSlice - 1) / kTkSlice);
-        topk_fill_kernel<<<(int)((K + 255) / 256), 256, 0, st>>>(out_rc, (long long *)out_id, (long long *)out_n, (int)K);
-        SX_LAUNCH_CHECK();
-        if (L == 0) return SX_OK;
+        if (L == 0) {
+            topk_fill_kernel<<<(int)((K + 255) / 256), 256, 0, st>>>(out_rc, (long long *)out_id, (long long *)out_n, (int)K);
+            SX_LAUNCH_CHECK();
+            return SX_OK;
+        }
         double *lists_rc = cv.take<double>((size_t)(L + 1) * K);
         long long *lists_id = cv.take<long long>((size_t)(L + 1) * K);
         const size_t smem = sizeof(Cand) * kTkSlice;
@@ -359,10 +373,10 @@ extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id,
                                                             (int)K, lists_rc, lists_id);
         SX_LAUNCH_CHECK();
         int *plen = cv.take<int>(L + 2), *poff = cv.take<int>(L + 2);
-        topk_prep_kernel<<<1, 1024, 0, st>>>(lists_rc, lists_id, L, (int)K, n_cand_dev, cand_cap, plen, poff,
-                                             (long long *)out_n);
+        topk_prep_kernel<<<1, 1024, 0, st>>>(lists_rc, lists_id, K, L, (int)K, n_cand_dev, cand_cap, plen, poff, out_rc,
+                                             (long long *)out_id, (long long *)out_n, nullptr, nullptr);
         SX_LAUNCH_CHECK();
-        topk_rank_kernel<<<kNumSMs * 4, 256, 0, st>>>(lists_rc, lists_id, L, (int)K, plen, poff, out_rc,
+        topk_rank_kernel<<<kNumSMs * 4, 256, 0, st>>>(lists_rc, lists_id, K, L, (int)K, plen, poff, out_rc,
                                                       (long long *)out_id);
         SX_LAUNCH_CHECK();
         return SX_OK;
@@ -396,22 +410,22 @@ extern "C" size_t sx_topk_merge_workspace_bytes(int64_t G) {
     return 2 * carve_bytes((size_t)G + 2, 4) + 256;
 }
 
-extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t G, int64_t K,
-                             double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
-                             void *stream) {
+extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t block_stride, int64_t G,
+                             int64_t K, const int64_t *headers, double *out_rc, int64_t *out_id, int64_t *out_n,
+                             int64_t *out_summary, void *ws, size_t ws_bytes, void *stream) {
     if (G <= 0 || K <= 0 || !blocks_rc || !blocks_id || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
+    if (block_stride < K || ((headers == nullptr) != (out_summary == nullptr))) return SX_ERR_INVALID;
     if (G > (1 << 20) || K > (1ll << 30)) return SX_ERR_TOO_LARGE;
     if (!ws || ws_bytes < sx_topk_merge_workspace_bytes(G)) return SX_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     Carver cv(ws);
     int *plen = cv.take<int>(G + 2), *poff = cv.take<int>(G + 2);
-    topk_fill_kernel<<<(int)((K + 255) / 256), 256, 0, st>>>(out_rc, (long long *)out_id, (long long *)out_n, (int)K);
+    topk_prep_kernel<<<1, 1024, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G, (int)K, nullptr,
+                                         0, plen, poff, out_rc, (long long *)out_id, (long long *)out_n,
+                                         (const long long *)headers, (long long *)out_summary);
     SX_LAUNCH_CHECK();
-    topk_prep_kernel<<<1, 1024, 0, st>>>(blocks_rc, (const long long *)blocks_id, (int)G, (int)K, nullptr, 0, plen, poff,
-                                         (long long *)out_n);
-    SX_LAUNCH_CHECK();
-    topk_rank_kernel<<<kNumSMs * 4, 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, (int)G, (int)K, plen, poff,
-                                                  out_rc, (long long *)out_id);
+    topk_rank_kernel<<<kNumSMs * 2, 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G, (int)K,
+                                                  plen, poff, out_rc, (long long *)out_id);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }

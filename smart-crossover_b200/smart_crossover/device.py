@@ -134,7 +134,11 @@ class PriceResult:
 
 
 class Pricer:
-    """Reusable buffers for repeated pricing passes over one problem (one CG loop)."""
+    """Reusable buffers for repeated pricing passes over one problem (one CG loop).
+
+    The top-K rc list, the id list and the pricing header live in ONE int64 tensor
+    `block = [K rc bits | K ids | header (4)]`, so a rank's whole contribution to the multi-GPU
+    all-gather is a single contiguous buffer that needs no packing kernels."""
 
     def __init__(self, device, K: int, cand_cap: int | None = None):
         _require_cuda()
@@ -144,15 +148,17 @@ class Pricer:
             cand_cap = max(64 * self.K, 1 << 20) if self.K > 0 else 0
         self.cap = int(cand_cap)
         self._alloc()
-        self.header = torch.zeros(4, dtype=torch.int64, device=device)
-        self.out_rc = torch.empty(max(self.K, 1), dtype=torch.float64, device=device)
-        self.out_id = torch.empty(max(self.K, 1), dtype=torch.int64, device=device)
+        Kp = max(self.K, 1)
+        self.Kp = Kp
+        self.block = torch.zeros(2 * Kp + 4, dtype=torch.int64, device=device)
+        self.out_rc = self.block[:Kp].view(torch.float64)
+        self.out_id = self.block[Kp:2 * Kp]
+        self.header = self.block[2 * Kp:2 * Kp + 4]
         self.out_n = torch.zeros(1, dtype=torch.int64, device=device)
         # pinned staging for the per-pass host round trip
-        self.h_header = torch.zeros(4, dtype=torch.int64).pin_memory()
-        self.h_rc = torch.empty(max(self.K, 1), dtype=torch.float64).pin_memory()
-        self.h_id = torch.empty(max(self.K, 1), dtype=torch.int64).pin_memory()
+        self.h_block = torch.zeros(2 * Kp + 4, dtype=torch.int64).pin_memory()
         self.h_n = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.launches = 0
 
     def _alloc(self):
         self.cand_rc = torch.empty(max(self.cap, 1), dtype=torch.float64, device=self.device)
@@ -161,17 +167,20 @@ class Pricer:
 
     def reset(self):
         check(lib.sx_price_header_reset(_ptr(self.header), _stream()), "sx_price_header_reset")
+        self.launches += 1
 
     def price_dense(self, M, ld, row0, S_loc, D, y_src, y_dst, tol=TOL_RC, rc_out=None, variant=-1):
         check(lib.sx_price_dense_ot(_ptr(M), ld, row0, S_loc, D, _ptr(y_src), _ptr(y_dst), float(tol),
                                     _ptr(self.header), _ptr(self.cand_rc), _ptr(self.cand_id), self.cap,
                                     _ptr(rc_out), D if rc_out is not None else 0, variant, _stream()),
               "sx_price_dense_ot")
+        self.launches += 1
 
     def price_arcs(self, c, tail, head, vbasis, y, id0=0, tol=TOL_RC, rc_out=None):
         check(lib.sx_price_arcs(_ptr(c), _ptr(tail), _ptr(head), _ptr(vbasis), _ptr(y), c.numel(), id0,
                                 float(tol), _ptr(self.header), _ptr(self.cand_rc), _ptr(self.cand_id),
                                 self.cap, _ptr(rc_out), _stream()), "sx_price_arcs")
+        self.launches += 1
 
     def select(self):
         """Enqueue the top-K selection over the compacted candidates (device only)."""
@@ -179,19 +188,20 @@ class Pricer:
             check(lib.sx_topk_select(_ptr(self.cand_rc), _ptr(self.cand_id), _ptr(self.header), self.cap,
                                      self.K, _ptr(self.out_rc), _ptr(self.out_id), _ptr(self.out_n),
                                      _ptr(self.ws), self.ws.numel(), _stream()), "sx_topk_select")
+            self.launches += 3 if self.K <= _native.SX_TOPK_MAX_K else 6
 
     def fetch(self) -> PriceResult:
-        """Device -> pinned host copy of the header and the top-K block; one synchronisation."""
-        self.h_header.copy_(self.header, non_blocking=True)
+        """Device -> pinned host copy of the block (top-K + header); one synchronisation."""
+        self.h_block.copy_(self.block, non_blocking=True)
         if self.K > 0:
-            self.h_rc.copy_(self.out_rc, non_blocking=True)
-            self.h_id.copy_(self.out_id, non_blocking=True)
             self.h_n.copy_(self.out_n, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        nviol = int(self.h_header[0].item()) & 0xFFFFFFFFFFFFFFFF
-        min_rc = float(lib.sx_key_to_f64(int(self.h_header[1].item())))
+        h = self.h_block.numpy()
+        Kp = self.Kp
+        nviol = int(h[2 * Kp]) & 0xFFFFFFFFFFFFFFFF
+        min_rc = float(lib.sx_key_to_f64(int(h[2 * Kp + 1])))
         k = int(self.h_n[0].item()) if self.K > 0 else 0
-        return PriceResult(nviol, min_rc, self.h_id[:k].numpy().copy(), self.h_rc[:k].numpy().copy())
+        return PriceResult(nviol, min_rc, h[Kp:Kp + k].copy(), h[:k].view(np.float64).copy())
 
     def overflowed(self, res: PriceResult) -> bool:
         return self.K > 0 and res.n_violating > self.cap
@@ -238,13 +248,26 @@ def price_arcs(c, tail, head, y, vbasis=None, K: int = 0, tol: float = TOL_RC, w
     return res
 
 
-def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor):
-    """Merge G sorted, padded top-K blocks (G x K) into one (rc, id, n) triple on the device."""
+def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor, headers: torch.Tensor | None = None):
+    """Merge G sorted, padded top-K lists into one (rc, id, n[, summary]) on the device.
+
+    blocks_rc / blocks_id are (G, K) views that may be strided (e.g. columns of the all-gathered
+    (G, 2K+4) buffer); `headers` (G, >=2) with the same row stride folds the per-rank
+    {n_violating, min key} into summary = {total, min key, largest single count}."""
     G, K = blocks_rc.shape
-    out_rc = torch.empty(K, dtype=torch.float64, device=blocks_rc.device)
-    out_id = torch.empty(K, dtype=torch.int64, device=blocks_rc.device)
-    out_n = torch.zeros(1, dtype=torch.int64, device=blocks_rc.device)
-    ws = _ws(lib.sx_topk_merge_workspace_bytes(G), blocks_rc.device)
-    check(lib.sx_topk_merge(_ptr(blocks_rc), _ptr(blocks_id), G, K, _ptr(out_rc), _ptr(out_id), _ptr(out_n),
-                            _ptr(ws), ws.numel(), _stream()), "sx_topk_merge")
+    stride = blocks_rc.stride(0)
+    assert blocks_id.stride(0) == stride and blocks_rc.stride(1) == 1 and blocks_id.stride(1) == 1
+    dev_ = blocks_rc.device
+    out_rc = torch.empty(K, dtype=torch.float64, device=dev_)
+    out_id = torch.empty(K, dtype=torch.int64, device=dev_)
+    out_n = torch.zeros(1, dtype=torch.int64, device=dev_)
+    summary = torch.zeros(3, dtype=torch.int64, device=dev_) if headers is not None else None
+    if headers is not None:
+        assert headers.stride(0) == stride
+    ws = _ws(lib.sx_topk_merge_workspace_bytes(G), dev_)
+    check(lib.sx_topk_merge(_ptr(blocks_rc), _ptr(blocks_id), stride, G, K, _ptr(headers), _ptr(out_rc),
+                            _ptr(out_id), _ptr(out_n), _ptr(summary), _ptr(ws), ws.numel(), _stream()),
+          "sx_topk_merge")
+    if headers is not None:
+        return out_rc, out_id, out_n, summary
     return out_rc, out_id, out_n

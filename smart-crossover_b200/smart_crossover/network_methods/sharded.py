@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from .. import device as dev
-from .._native import lib
+from .._native import check, lib
 
 
 def row_partition(S: int, world: int, rank: int):
@@ -31,23 +31,10 @@ def row_partition(S: int, world: int, rank: int):
     return lo, hi - lo
 
 
-def pack_block(out_rc: torch.Tensor, out_id: torch.Tensor, header: torch.Tensor, buf: torch.Tensor):
-    """[K rc bits | K ids | n_violating | min key] as int64 (bit-preserving)."""
-    K = out_rc.numel()
-    buf[:K].copy_(out_rc.view(torch.int64))
-    buf[K:2 * K].copy_(out_id)
-    buf[2 * K:2 * K + 2].copy_(header[:2])
-    return buf
-
-
-def unpack_blocks(gathered: torch.Tensor, K: int):
-    """(G, 2K+2) int64 -> contiguous (G, K) rc, (G, K) ids, total count, min key and the largest
-    per-rank count (device tensors)."""
-    rc = gathered[:, :K].contiguous().view(torch.float64)
-    ids = gathered[:, K:2 * K].contiguous()
-    count = gathered[:, 2 * K].sum()
-    minkey = gathered[:, 2 * K + 1].min()
-    return rc, ids, count, minkey, gathered[:, 2 * K].max()
+def block_views(gathered: torch.Tensor, K: int):
+    """Views into the all-gathered (G, 2K+4) int64 buffer: (G, K) rc, (G, K) ids, (G, 4) headers.
+    Each rank's row is its `Pricer.block` = [K rc bits | K ids | n_violating, min key, n_priced, -]."""
+    return gathered[:, :K].view(torch.float64), gathered[:, K:2 * K], gathered[:, 2 * K:2 * K + 4]
 
 
 class ShardedDensePricer:
@@ -63,14 +50,23 @@ class ShardedDensePricer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.pricer = dev.Pricer(M_loc.device, self.K)
+        self._merge_launches = 0
         self.y_dev = torch.empty(self.S + self.D, dtype=torch.float64, device=M_loc.device)
         self.h_y = torch.empty(self.S + self.D, dtype=torch.float64).pin_memory()
         Kp = max(self.K, 1)
-        self.block = torch.empty(2 * Kp + 2, dtype=torch.int64, device=M_loc.device)
-        self.gathered = torch.empty(self.world, 2 * Kp + 2, dtype=torch.int64, device=M_loc.device)
+        self.gathered = torch.empty(self.world, 2 * Kp + 4, dtype=torch.int64, device=M_loc.device)
         self.h_out = torch.empty(2 * Kp + 4, dtype=torch.int64).pin_memory()
         self.d_out = torch.empty(2 * Kp + 4, dtype=torch.int64, device=M_loc.device)
-        self.launches = 0     # kernels of libsxcross enqueued by this object
+        self._merge_ws = dev._ws(lib.sx_topk_merge_workspace_bytes(self.world), M_loc.device)
+        self._m_rc = self.d_out[:Kp].view(torch.float64)
+        self._m_id = self.d_out[Kp:2 * Kp]
+        self._m_n = self.d_out[2 * Kp:2 * Kp + 1]
+        self._m_sum = self.d_out[2 * Kp + 1:2 * Kp + 4]
+
+    @property
+    def launches(self):
+        """Kernels of libsxcross enqueued by this object."""
+        return self.pricer.launches + self._merge_launches
 
     # -- device-only step: everything stays on the GPU(s) --------------------------------------
     def enqueue(self, y_dev: torch.Tensor, kernel_events=None):
@@ -87,15 +83,17 @@ class ShardedDensePricer:
         if kernel_events is not None:
             kernel_events[1].record()
         p.select()
-        self.launches += 3 + (3 if self.K > 0 else 0)
+        Kp = max(self.K, 1)
         if self.world == 1:
             return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0]
-        pack_block(p.out_rc, p.out_id, p.header, self.block)
-        dist.all_gather_into_tensor(self.gathered.view(-1), self.block, group=self.group)
-        rc, ids, count, minkey, cmax = unpack_blocks(self.gathered, max(self.K, 1))
-        out_rc, out_id, out_n = dev.topk_merge(rc, ids)
-        self.launches += 2
-        return out_rc, out_id, out_n[0], count, minkey, cmax
+        # one collective: every rank's block (top-K + header) lands in `gathered`, consumed in place
+        dist.all_gather_into_tensor(self.gathered.view(-1), p.block, group=self.group)
+        rc, ids, hdr = block_views(self.gathered, Kp)
+        check(lib.sx_topk_merge(dev._ptr(rc), dev._ptr(ids), self.gathered.stride(0), self.world, Kp, dev._ptr(hdr),
+                                dev._ptr(self._m_rc), dev._ptr(self._m_id), dev._ptr(self._m_n), dev._ptr(self._m_sum),
+                                dev._ptr(self._merge_ws), self._merge_ws.numel(), dev._stream()), "sx_topk_merge")
+        self._merge_launches += 2
+        return self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2]
 
     # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
     def price(self, y_host: np.ndarray) -> dev.PriceResult:
@@ -104,24 +102,24 @@ class ShardedDensePricer:
         self.y_dev.copy_(self.h_y, non_blocking=True)
         K = max(self.K, 1)
         while True:
-            out_rc, out_id, out_n, count, minkey, cmax = self.enqueue(self.y_dev)
-            self.d_out[:K].copy_(out_rc.view(torch.int64))
-            self.d_out[K:2 * K].copy_(out_id)
-            self.d_out[2 * K] = out_n
-            self.d_out[2 * K + 1] = count
-            self.d_out[2 * K + 2] = minkey
-            self.d_out[2 * K + 3] = cmax
-            self.h_out.copy_(self.d_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            h = self.h_out.numpy()
-            n_out = int(h[2 * K]) if self.K > 0 else 0
+            self.enqueue(self.y_dev)
+            if self.world == 1:
+                res = self.pricer.fetch()                  # block + out_n, two small D2H copies, one sync
+                cmax = res.n_violating
+            else:
+                # d_out = [rc | ids | n_out, total count, min key, largest per-rank count], written by the merge
+                self.h_out.copy_(self.d_out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                h = self.h_out.numpy()
+                n_out = int(h[2 * K]) if self.K > 0 else 0
+                res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
+                                      h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
+                cmax = int(h[2 * K + 3])
             # If some rank saw more violators than its candidate buffer holds, every rank (they all
             # read the same gathered counts) grows to that size and the pass is priced again.
-            if self.K == 0 or int(h[2 * K + 3]) <= self.pricer.cap:
-                break
-            self.pricer.grow(int(h[2 * K + 3]))
-        return dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
-                               h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
+            if self.K == 0 or cmax <= self.pricer.cap:
+                return res
+            self.pricer.grow(cmax)
 
     @property
     def h2d_bytes(self):
