@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-tree", action="store_true", help="skip the tree-basis build timings")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
+    ap.add_argument("--tree-only", type=int, default=0, metavar="S",
+                    help="only time the tree-basis build on an S x S instance and exit")
     return ap.parse_args()
 
 
@@ -313,6 +315,10 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.tree_only:
+        print(json.dumps(time_tree_build(args.tree_only, args.tree_only, device, reps=2)), flush=True)
+        return
 
     S = D = args.size
     K = args.topk

@@ -10,10 +10,7 @@
 
 namespace sx {
 
-constexpr int kRsThreads = 512;
-constexpr int kRsItems   = 8;
-constexpr int kRsTile    = kRsThreads * kRsItems;   // 4096 keys
-constexpr int kRsWarps   = kRsThreads / 32;
+constexpr int kRsItems   = 8;      // keys per thread in the downsweep; tile = threads * 8
 constexpr int kRsMaxGrid = kNumSMs * 6;
 
 enum KeySource { kFromBuffer = 0, kFromF64 = 1, kFromU64 = 2 };
@@ -29,6 +26,20 @@ struct RsDst {
     uint32_t           *vals;
 };
 
+// Lanes of the warp holding the same 8-bit digit, from 8 ballots.  The hardware MATCH.ANY
+// instruction takes time proportional to the number of distinct values in the warp (32 for the
+// random low mantissa bytes); this form costs the same for every distribution.
+__device__ __forceinline__ unsigned match_digit(unsigned d) {
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 template <int SRC>
 __device__ __forceinline__ unsigned long long rs_load_key(const RsSrc &s, long long i) {
     if (SRC == kFromF64) return f64_to_sort_key(s.f64[i]);
@@ -36,93 +47,129 @@ __device__ __forceinline__ unsigned long long rs_load_key(const RsSrc &s, long l
 }
 
 // ---- upsweep: per-block digit histogram ------------------------------------------------
+// Every lane owns a private 16-bit counter per digit (cnt[warp][digit][lane], 64 KB per CTA), so
+// counting a key is a plain shared-memory read-modify-write: no atomics (shared atomics cost ~2
+// cycles per lane on this part and made the histogram 5x slower than the memory system), no
+// warp matching.  A lane sees at most tiles_per_block * 2048 / 128 < 65536 keys.
+constexpr int kUpThreads = 128;
+constexpr int kUpWarps   = kUpThreads / 32;
+constexpr int kUpUnroll  = 8;
+constexpr size_t kUpSmem = (size_t)kUpWarps * 256 * 32 * sizeof(uint16_t);
+
 template <int SRC>
-__global__ void __launch_bounds__(kRsThreads)
-rs_upsweep_kernel(RsSrc src, long long n, int shift, long long tiles_per_block, uint32_t *hist, int grid) {
-    __shared__ uint32_t h[256];
-    if (threadIdx.x < 256) h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(kUpThreads)
+rs_upsweep_kernel(RsSrc src, long long n, int shift, long long keys_per_block, uint32_t *hist, int grid) {
+    extern __shared__ __align__(16) uint16_t up_cnt[];
+    {
+        uint32_t *z = reinterpret_cast<uint32_t *>(up_cnt);
+        for (int i = threadIdx.x; i < (int)(kUpSmem / 4); i += kUpThreads) z[i] = 0;
+    }
     __syncthreads();
-    const long long beg = (long long)blockIdx.x * tiles_per_block * kRsTile;
-    long long end = beg + tiles_per_block * kRsTile;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    uint16_t *mine = up_cnt + (size_t)warp * 256 * 32 + lane;
+    const long long beg = (long long)blockIdx.x * keys_per_block;
+    long long end = beg + keys_per_block;
     if (end > n) end = n;
-    for (long long base = beg; base < end; base += kRsThreads * 4) {
+    const void *base_ptr = (SRC == kFromF64) ? (const void *)src.f64 : (const void *)src.keys;
+    const bool vec = (reinterpret_cast<uintptr_t>(base_ptr) & 15) == 0;   // beg is even
+    for (long long base = beg; base < end; base += (long long)kUpThreads * 2 * kUpUnroll) {
+        unsigned long long k0[kUpUnroll], k1[kUpUnroll];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const long long i = base + (long long)q * kRsThreads + threadIdx.x;
-            const bool ok = i < end;
-            const unsigned d = ok ? (unsigned)((rs_load_key<SRC>(src, i) >> shift) & 0xff) : 256u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            if (ok && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&h[d], (uint32_t)__popc(peers));
+        for (int u = 0; u < kUpUnroll; ++u) {
+            const long long i = base + 2ll * (u * kUpThreads + threadIdx.x);
+            k0[u] = k1[u] = 0;
+            if (i + 1 < end && vec) {
+                if (SRC == kFromF64) {
+                    const double2 q = *reinterpret_cast<const double2 *>(src.f64 + i);
+                    k0[u] = f64_to_sort_key(q.x); k1[u] = f64_to_sort_key(q.y);
+                } else {
+                    const ulonglong2 q = *reinterpret_cast<const ulonglong2 *>(src.keys + i);
+                    k0[u] = q.x; k1[u] = q.y;
+                }
+            } else {
+                if (i < end) k0[u] = rs_load_key<SRC>(src, i);
+                if (i + 1 < end) k1[u] = rs_load_key<SRC>(src, i + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUpUnroll; ++u) {
+            const long long i = base + 2ll * (u * kUpThreads + threadIdx.x);
+            if (i < end) mine[((k0[u] >> shift) & 0xff) * 32] += 1;
+            if (i + 1 < end) mine[((k1[u] >> shift) & 0xff) * 32] += 1;
         }
     }
     __syncthreads();
-    if (threadIdx.x < 256) hist[(size_t)threadIdx.x * grid + blockIdx.x] = h[threadIdx.x];
+    // reduce the 4 x 32 private copies of every digit: a warp sums one (warp, digit) row per step
+    for (int d = warp; d < 256; d += kUpWarps) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < kUpWarps; ++w) s += up_cnt[((size_t)w * 256 + d) * 32 + lane];
+        s = warp_sum(s);
+        if (lane == 0) hist[(size_t)d * grid + blockIdx.x] = s;
+    }
 }
 
-// ---- scan: exclusive prefix over hist[digit][block] (digit-major) -----------------------
+// ---- scan: exclusive prefix over hist[digit][block] (digit-major), one CTA, 8192 entries per sweep ----
 __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *hist, int count) {
     __shared__ uint32_t warp_tot[32];
-    const int per = (count + 1023) / 1024;
-    const int beg = threadIdx.x * per;
-    int end = beg + per;
-    if (end > count) end = count;
-    uint32_t sum = 0;
-    for (int i = beg; i < end; ++i) sum += hist[i];
-    // block exclusive scan of `sum`
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane_id() >= o) incl += t;
-    }
-    if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __shared__ uint32_t carry;
+    constexpr int kPer = 8;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t w = warp_tot[threadIdx.x], wi = w;
+    for (int base = 0; base < count; base += 1024 * kPer) {
+        const int i0 = base + threadIdx.x * kPer;
+        uint32_t v[kPer], sum = 0;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) { v[q] = (i0 + q < count) ? hist[i0 + q] : 0u; sum += v[q]; }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-            if ((int)lane_id() >= o) wi += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        warp_tot[threadIdx.x] = wi - w;
-    }
-    __syncthreads();
-    uint32_t run = warp_tot[threadIdx.x >> 5] + (incl - sum);
-    for (int i = beg; i < end; ++i) {
-        uint32_t v = hist[i];
-        hist[i] = run;
-        run += v;
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t run = carry + incl - sum;
+        for (int w = 0; w < warp; ++w) run += warp_tot[w];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) { if (i0 + q < count) hist[i0 + q] = run; run += v[q]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = run;
+        __syncthreads();
     }
 }
 
 // ---- downsweep: stable scatter ------------------------------------------------------------
+template <int THREADS>
 struct RsSmem {
-    unsigned long long keys[kRsTile];
-    uint32_t           vals[kRsTile];
-    uint32_t           cnt[kRsWarps][256];
+    unsigned long long keys[THREADS * kRsItems];
+    uint32_t           vals[THREADS * kRsItems];
+    uint32_t           cnt[THREADS / 32][256];
     uint32_t           digit_base[256];
     uint32_t           tile_cnt[256];
     uint32_t           tile_start[256];
     uint32_t           warp_tot[8];
 };
 
-template <int SRC, bool LAST_F64>
-__global__ void __launch_bounds__(kRsThreads)
+template <int THREADS, int SRC, bool LAST_F64>
+__global__ void __launch_bounds__(THREADS)
 rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tiles_per_block,
                     const uint32_t *hist, int grid) {
     extern __shared__ __align__(16) unsigned char rs_raw[];
-    RsSmem &sm = *reinterpret_cast<RsSmem *>(rs_raw);
+    constexpr int kTile = THREADS * kRsItems, kWarps = THREADS / 32;
+    RsSmem<THREADS> &sm = *reinterpret_cast<RsSmem<THREADS> *>(rs_raw);
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const unsigned lt = (1u << lane) - 1u;
     if (threadIdx.x < 256) sm.digit_base[threadIdx.x] = hist[(size_t)threadIdx.x * grid + blockIdx.x];
 
     const long long tile0 = (long long)blockIdx.x * tiles_per_block;
     for (long long tl = tile0; tl < tile0 + tiles_per_block; ++tl) {
-        const long long tbase = tl * kRsTile;
+        const long long tbase = tl * kTile;
         if (tbase >= n) break;
-        const long long valid = (n - tbase < kRsTile) ? (n - tbase) : kRsTile;
+        const long long valid = (n - tbase < kTile) ? (n - tbase) : kTile;
         // zero the per-warp counters
-        for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&sm.cnt[0][0])[i] = 0;
+        for (int i = threadIdx.x; i < kWarps * 256; i += THREADS) (&sm.cnt[0][0])[i] = 0;
         unsigned long long key[kRsItems];
         uint32_t           val[kRsItems];
 #pragma unroll
@@ -142,7 +189,7 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
 #pragma unroll
         for (int r = 0; r < kRsItems; ++r) {
             const unsigned d = (unsigned)((key[r] >> shift) & 0xff);
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const unsigned peers = match_digit(d);
             const int leader = __ffs(peers) - 1;
             uint32_t old = 0;
             if (lane == leader) {
@@ -158,7 +205,7 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
         if (threadIdx.x < 256) {
             uint32_t s = 0;
 #pragma unroll
-            for (int w = 0; w < kRsWarps; ++w) {
+            for (int w = 0; w < kWarps; ++w) {
                 uint32_t t = sm.cnt[w][threadIdx.x];
                 sm.cnt[w][threadIdx.x] = s;
                 s += t;
@@ -191,7 +238,7 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kRsItems; ++k) {
-            const int i = threadIdx.x + k * kRsThreads;
+            const int i = threadIdx.x + k * THREADS;
             if (i < valid) {
                 const unsigned long long kk = sm.keys[i];
                 const unsigned d = (unsigned)((kk >> shift) & 0xff);
@@ -211,11 +258,14 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
 
 struct RsPlan {
     long long tiles, tiles_per_block;
-    int       grid;
+    int       grid, threads;
 };
+static int g_rs_threads = 512;
 static RsPlan rs_plan(long long n) {
     RsPlan p;
-    p.tiles = (n + kRsTile - 1) / kRsTile;
+    p.threads = g_rs_threads;
+    const long long tile = (long long)p.threads * kRsItems;
+    p.tiles = (n + tile - 1) / tile;
     if (p.tiles < 1) p.tiles = 1;
     p.tiles_per_block = (p.tiles + kRsMaxGrid - 1) / kRsMaxGrid;
     p.grid = (int)((p.tiles + p.tiles_per_block - 1) / p.tiles_per_block);
@@ -225,13 +275,25 @@ static RsPlan rs_plan(long long n) {
 template <int SRC, bool LAST_F64>
 static int rs_pass(const RsSrc &src, const RsDst &dst, long long n, int shift, const RsPlan &pl,
                    uint32_t *hist, cudaStream_t st) {
-    rs_upsweep_kernel<SRC><<<pl.grid, kRsThreads, 0, st>>>(src, n, shift, pl.tiles_per_block, hist, pl.grid);
+    auto up = rs_upsweep_kernel<SRC>;
+    SX_CUDA(cudaFuncSetAttribute(up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpSmem));
+    up<<<pl.grid, kUpThreads, kUpSmem, st>>>(src, n, shift, pl.tiles_per_block * pl.threads * kRsItems, hist, pl.grid);
     SX_LAUNCH_CHECK();
     rs_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * pl.grid);
     SX_LAUNCH_CHECK();
-    auto kern = rs_downsweep_kernel<SRC, LAST_F64>;
-    SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-    kern<<<pl.grid, kRsThreads, sizeof(RsSmem), st>>>(src, dst, n, shift, pl.tiles_per_block, hist, pl.grid);
+    if (pl.threads == 256) {
+        auto kern = rs_downsweep_kernel<256, SRC, LAST_F64>;
+        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<256>)));
+        kern<<<pl.grid, 256, sizeof(RsSmem<256>), st>>>(src, dst, n, shift, pl.tiles_per_block, hist, pl.grid);
+    } else if (pl.threads == 1024) {
+        auto kern = rs_downsweep_kernel<1024, SRC, LAST_F64>;
+        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<1024>)));
+        kern<<<pl.grid, 1024, sizeof(RsSmem<1024>), st>>>(src, dst, n, shift, pl.tiles_per_block, hist, pl.grid);
+    } else {
+        auto kern = rs_downsweep_kernel<512, SRC, LAST_F64>;
+        SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<512>)));
+        kern<<<pl.grid, 512, sizeof(RsSmem<512>), st>>>(src, dst, n, shift, pl.tiles_per_block, hist, pl.grid);
+    }
     SX_LAUNCH_CHECK();
     return SX_OK;
 }
@@ -420,6 +482,12 @@ ko_scatter_kernel(const double *__restrict__ key, const uint32_t *__restrict__ o
 }  // namespace sx
 
 using namespace sx;
+
+extern "C" int sx_sort_set_tuning(int downsweep_threads) {
+    if (downsweep_threads != 256 && downsweep_threads != 512 && downsweep_threads != 1024) return SX_ERR_INVALID;
+    g_rs_threads = downsweep_threads;
+    return SX_OK;
+}
 
 extern "C" size_t sx_argsort_workspace_bytes(int64_t n) {
     if (n < 0) return 0;
