@@ -395,8 +395,15 @@ def main():
         return
 
     achieved = 8.0 * S_loc * D / (kern_ms * 1e-3) / 1e9
+    traffic = None            # dram read+write bytes per launch from the committed ncu capture, same shape only
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "price_traffic.json")))
+        if (tj["S_loc"], tj["D"]) == (S_loc, D):
+            traffic = tj["traffic_bytes"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel": "price_dense_tma_kernel" if args.variant in (-1, 0) else "price_dense_direct_kernel",
                 "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_arc": 8,
                 "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
@@ -428,7 +435,7 @@ def main():
                        "l2": f"inputs larger than L2 ({8 * S_loc * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sp_h2d(S, D),
-                    "d2h_bytes_per_step": 8 * (2 * max(K, 1) + 4), "ms_per_step": e2e_ms / steps,
+                    "d2h_bytes_per_step": 8 * (2 * max(K, 1) + 5), "ms_per_step": e2e_ms / steps,
                     "inputs": "duals y (S+D fp64) from pinned host memory every step; cost matrix resident "
                               "(uploaded once per problem, see e2e_cold)"},
             "e2e_cold": cold, "gpu_launches": launches, "clocks": clocks, "tree_build": tree}
