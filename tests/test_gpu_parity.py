@@ -342,3 +342,40 @@ def test_large_sort_properties(dev):
     same = skey[1:] == skey[:-1]
     assert bool((idx[1:][same] > idx[:-1][same]).all())
     assert int(torch.bincount(idx, minlength=n).max().item()) == 1
+
+
+# ---- full-size MCF (BASELINE.json configs[2]: NETGEN-style 1M nodes / 10M arcs) ------------------------
+def test_c3_full_size_mcf_path(dev):
+    """Scores, queue, spanning forest, potentials and arc pricing on the 1M-node / 10M-arc instance,
+    against the oracle (bit-exact scores / order / forest / reduced costs; potentials 1e-9)."""
+    import scipy.sparse as sp
+    N, E = 1_000_000, 10_000_000
+    tail, head, b, c, u = cases.netgen_like(N, E, 20260003)
+    x = cases.mcf_interior_flow(u, 20260003)
+    A = sp.csr_matrix((np.concatenate([np.ones(E, np.int8), -np.ones(E, np.int8)]),
+                       (np.concatenate([tail, head]), np.concatenate([np.arange(E)] * 2))), shape=(N, E))
+    A.sort_indices()
+    t32, h32 = cu(tail, torch.int32), cu(head, torch.int32)
+    ind = dev.score_mcf(cu(x), cu(u), t32, h32, cu(A.indptr, torch.int64), cu(A.indices, torch.int32),
+                        cu(A.data, torch.int8))
+    ind_ref = orc.mcf_flow_scores(x, u, A)
+    assert ind.cpu().numpy().tobytes() == ind_ref.tobytes()
+    order, skey, queue, korder = sort_pipeline(dev, ind)
+    assert np.array_equal(queue.cpu().numpy(), orc.stable_queue(ind_ref))
+    ko_ref = orc.kruskal_order(ind_ref)
+    assert np.array_equal(u32(korder), ko_ref)
+    tree, n_tree = dev.kruskal(korder, N, tail=t32, head=h32)
+    nt = int(n_tree.item())
+    forest_ref = orc.spanning_forest(ko_ref, N, tail=tail, head=head)
+    assert nt == forest_ref.size == N - 1                 # the ring makes the graph connected
+    assert np.array_equal(tree[:nt].cpu().numpy(), forest_ref)
+    y = dev.tree_potentials(tree, nt, N, cu(c), N - 1, tail=t32, head=h32, plus=1)
+    y_ref = orc.tree_potentials(tail[forest_ref], head[forest_ref], c[forest_ref], N, N - 1)
+    np.testing.assert_allclose(y.cpu().numpy(), y_ref, rtol=RTOL, atol=RTOL * np.abs(y_ref).max())
+    vb = np.where(x > u / 2, -2, -1).astype(np.int8)
+    res = dev.price_arcs(cu(c), t32, h32, cu(y_ref), vbasis=cu(vb), K=1000, want_rc=True)
+    rc_ref = orc.reduced_costs_arcs(c, tail, head, y_ref, vb)
+    assert res.rc.cpu().numpy().tobytes() == rc_ref.tobytes()
+    cnt, mn, ids, vals = orc.price_summary(rc_ref, K=1000)
+    assert res.n_violating == cnt and res.min_rc == mn
+    assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
