@@ -48,11 +48,14 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=60000, help="S = D of the dense OT instance")
+    ap.add_argument("--rows", type=int, default=0, help="S if different from --size (profiling a per-rank slab shape)")
     ap.add_argument("--topk", type=int, default=1024)
     ap.add_argument("--variant", type=int, default=-1, help="-1 auto (TMA), 0 TMA, 1 vector loads, 2 scalar loads")
     ap.add_argument("--violators", type=float, default=1e-4, help="target fraction of violating arcs")
     ap.add_argument("--no-tree", action="store_true", help="skip the tree-basis build timings")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: NVLink peer-store exchange of the result blocks (default) or NCCL all-gather")
     ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
     ap.add_argument("--tree-only", type=int, default=0, metavar="S",
                     help="only time the tree-basis build on an S x S instance and exit")
@@ -366,13 +369,15 @@ def main():
         return
 
     S = D = args.size
+    if args.rows:
+        S = args.rows
     K = args.topk
     row0, S_loc = row_partition(S, world, rank)
     P, Q, a = make_points(S, D, device)
     M_loc = make_slab(P, Q, row0, S_loc)
     y_dev = planted_duals(P, Q, a, M_loc, row0, args.violators, world)
     y_host = y_dev.cpu().numpy()
-    sp = ShardedDensePricer(M_loc, S, row0, K, TOL, variant=args.variant)
+    sp = ShardedDensePricer(M_loc, S, row0, K, TOL, variant=args.variant, exchange=args.exchange)
 
     if args.sweep:
         sweep(args, sp, y_dev, S_loc, D, lib, dev)
@@ -434,6 +439,7 @@ def main():
                 "h2d_bytes": 8 * S_loc * D, "note": f"upload time scaled from a {rows_c}-row pinned sample"}
         del h_M
 
+    exchange_mode = sp.exchange
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -477,7 +483,7 @@ def main():
             "config": {"workload": f"dense synthetic OT {S}x{D} ({S * D:.3g} arcs, {8 * S * D / 1e9:.1f} GB fp64 cost) "
                                    f"column-generation pricing pass, row-sharded over {world} GPU(s)",
                        "S": S, "D": D, "topk": K, "tol": TOL, "violating_arcs": count_dev,
-                       "rows_per_gpu": S_loc, "variant": args.variant,
+                       "rows_per_gpu": S_loc, "variant": args.variant, "exchange": exchange_mode,
                        "l2": f"inputs larger than L2 ({8 * S_loc * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sp_h2d(S, D),

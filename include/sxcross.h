@@ -46,6 +46,7 @@ extern "C" {
 #define SX_ERR_NOT_SPANNING    -5   /* sx_tree_potentials: arcs are not a spanning tree */
 #define SX_ERR_UNALIGNED       -6   /* TMA path needs 16-byte aligned base and even ld */
 #define SX_ERR_NO_DEVICE       -7   /* no sm_100 device / driver entry point missing */
+#define SX_ERR_PEER_TIMEOUT    -8   /* sx_exchange_blocks: a peer never raised its flag */
 
 #define SX_ABI_VERSION 1
 
@@ -189,6 +190,21 @@ SX_API size_t sx_topk_merge_workspace_bytes(int64_t G);
 SX_API int    sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t block_stride,
                      int64_t G, int64_t K, const int64_t *headers, double *out_rc, int64_t *out_id,
                      int64_t *out_n, int64_t *out_summary, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- multi-GPU exchange of the result blocks over NVLink peer memory ------------------------
+ * Replaces the NCCL all-gather of the row-sharded pricing pass (no reference counterpart: the
+ * reference is single process).  Every rank owns a symmetric buffer of sx_exchange_buffer_bytes()
+ * bytes, zero-initialised and peer-mapped (e.g. torch symmetric memory); peer_bufs_dev is a DEVICE
+ * array of the G base pointers (entry g = rank g's buffer as mapped in this process).  One call
+ * stores this rank's block (block_len int64, even, 16 B aligned) into slot [epoch & 1][rank] of
+ * every rank's buffer and returns (on the stream) when all G blocks of this epoch have landed in
+ * the local slots [epoch & 1][0..G), contiguous, block_len apart.  `epoch` must start at 1 and
+ * increase by 1 per call on every rank.  status_dev receives SX_ERR_PEER_TIMEOUT if a peer does
+ * not show up within 10 s (it is never cleared by the library).
+ */
+SX_API size_t sx_exchange_buffer_bytes(int64_t block_len, int G);
+SX_API int    sx_exchange_blocks(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev,
+                          int rank, int G, unsigned long long epoch, int32_t *status_dev, void *stream);
 
 /* ---- host-buffer entry point (what a reference-side binding calls with NumPy arrays) ----
  * One pricing pass with HOST buffers: uploads y (and M if M_dev == NULL), prices, selects

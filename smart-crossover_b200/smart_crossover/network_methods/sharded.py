@@ -42,7 +42,7 @@ class ShardedDensePricer:
     row-major, device resident for the life of the problem, like the reference keeps `ot.M`)."""
 
     def __init__(self, M_loc: torch.Tensor, S: int, row0: int, K: int, tol: float = dev.TOL_RC,
-                 group=None, variant: int = -1):
+                 group=None, variant: int = -1, exchange: str = "p2p"):
         self.M = M_loc
         self.S, self.D = int(S), int(M_loc.shape[1])
         self.S_loc, self.row0 = int(M_loc.shape[0]), int(row0)
@@ -62,6 +62,30 @@ class ShardedDensePricer:
         self._m_id = self.d_out[Kp:2 * Kp]
         self._m_n = self.d_out[2 * Kp:2 * Kp + 1]
         self._m_sum = self.d_out[2 * Kp + 1:2 * Kp + 4]
+        # exchange of the result blocks: "p2p" = direct peer stores over NVLink into a symmetric buffer
+        # (sx_exchange_blocks), "nccl" = all_gather_into_tensor.  p2p needs torch symmetric memory.
+        self.exchange = exchange if self.world > 1 else "none"
+        self._epoch = 0
+        if self.exchange == "p2p":
+            try:
+                self._setup_p2p(Kp)
+            except Exception as e:                      # no peer access on this box: say so, use NCCL
+                import warnings
+                warnings.warn(f"NVLink peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+                self.exchange = "nccl"
+
+    def _setup_p2p(self, Kp: int):
+        import torch.distributed._symmetric_memory as symm
+        blk = 2 * Kp + 4
+        n64 = lib.sx_exchange_buffer_bytes(blk, self.world) // 8
+        self._symm = symm.empty(n64, dtype=torch.int64, device=self.M.device)
+        self._symm.zero_()
+        torch.cuda.synchronize()
+        self._hdl = symm.rendezvous(self._symm, group=self.group if self.group is not None else dist.group.WORLD)
+        self._rank = dist.get_rank(self.group)
+        self._xstatus = torch.zeros(1, dtype=torch.int32, device=self.M.device)
+        self._h_xstatus = torch.zeros(1, dtype=torch.int32).pin_memory()
+        dist.barrier(group=self.group)
 
     @property
     def launches(self):
@@ -86,10 +110,20 @@ class ShardedDensePricer:
         Kp = max(self.K, 1)
         if self.world == 1:
             return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0]
-        # one collective: every rank's block (top-K + header) lands in `gathered`, consumed in place
-        dist.all_gather_into_tensor(self.gathered.view(-1), p.block, group=self.group)
-        rc, ids, hdr = block_views(self.gathered, Kp)
-        check(lib.sx_topk_merge(dev._ptr(rc), dev._ptr(ids), self.gathered.stride(0), self.world, Kp, dev._ptr(hdr),
+        # one exchange: every rank's block (top-K + header) lands in `gathered`, consumed in place
+        if self.exchange == "p2p":
+            self._epoch += 1
+            blk = 2 * Kp + 4
+            check(lib.sx_exchange_blocks(dev._ptr(p.block), blk, self._hdl.buffer_ptrs_dev, self._rank, self.world,
+                                         self._epoch, dev._ptr(self._xstatus), dev._stream()), "sx_exchange_blocks")
+            self._merge_launches += 1
+            par = self._epoch & 1
+            gathered = self._symm[par * self.world * blk:(par + 1) * self.world * blk].view(self.world, blk)
+        else:
+            dist.all_gather_into_tensor(self.gathered.view(-1), p.block, group=self.group)
+            gathered = self.gathered
+        rc, ids, hdr = block_views(gathered, Kp)
+        check(lib.sx_topk_merge(dev._ptr(rc), dev._ptr(ids), gathered.stride(0), self.world, Kp, dev._ptr(hdr),
                                 dev._ptr(self._m_rc), dev._ptr(self._m_id), dev._ptr(self._m_n), dev._ptr(self._m_sum),
                                 dev._ptr(self._merge_ws), self._merge_ws.numel(), dev._stream()), "sx_topk_merge")
         self._merge_launches += 2
@@ -109,7 +143,11 @@ class ShardedDensePricer:
             else:
                 # d_out = [rc | ids | n_out, total count, min key, largest per-rank count], written by the merge
                 self.h_out.copy_(self.d_out, non_blocking=True)
+                if self.exchange == "p2p":
+                    self._h_xstatus.copy_(self._xstatus, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
+                if self.exchange == "p2p" and int(self._h_xstatus[0]) != 0:
+                    check(int(self._h_xstatus[0]), "sx_exchange_blocks")
                 h = self.h_out.numpy()
                 n_out = int(h[2 * K]) if self.K > 0 else 0
                 res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
