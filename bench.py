@@ -407,6 +407,7 @@ def main():
     launches = sp.launches - launches0
     kern_ms = float(np.mean([k0[i].elapsed_time(k1[i]) for i in range(steps)]))
     count_dev = int(out[3].item())
+    assert int(out[6].item()) == 0, "selection status not clean: the timed pass would have to be repeated"
     value = S * D * steps / (ms_total * 1e-3)
 
     # ---- end-to-end arm: duals from pinned host memory, result back to the host every step ---------

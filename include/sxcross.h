@@ -48,7 +48,7 @@ extern "C" {
 #define SX_ERR_NO_DEVICE       -7   /* no sm_100 device / driver entry point missing */
 #define SX_ERR_PEER_TIMEOUT    -8   /* sx_exchange_blocks: a peer never raised its flag */
 
-#define SX_ABI_VERSION 1
+#define SX_ABI_VERSION 2
 
 /* Endpoint convention of sx_tree_potentials (which end of an arc carries +1 in A). */
 #define SX_PLUS_IS_HEAD 0   /* OT:  A[S+j,k] = +1, A[i,k] = -1      (formats.py:156-158)     */
@@ -59,8 +59,17 @@ typedef struct sx_price_header {
     unsigned long long n_violating;   /* #arcs with rc < -tol (exact, even past the candidate cap) */
     long long          min_rc_key;    /* order-preserving int64 image of min rc; see sx_key_to_f64 */
     unsigned long long n_priced;      /* arcs priced by this launch (sanity / throughput) */
-    unsigned long long reserved;
+    unsigned long long status;        /* SX_STATUS_* bits; 0 = the selection below is complete */
 } sx_price_header;
+
+#define SX_STATUS_CAND_OVERFLOW  1   /* candidate buffer too small: enlarge it and price again */
+#define SX_STATUS_NEED_SORTED    2   /* too many ties at the K-th reduced cost for the fast selection:
+                                        call sx_topk_select_sorted on the same candidates */
+
+/* Selection state of a pricing pass (opaque device memory, sx_select_state_bytes() bytes, 16 B
+ * aligned): candidate counter, pruning bound and the reduced-cost histogram the bound is derived
+ * from.  Zeroed by sx_price_pass_begin, filled by sx_price_*, consumed by sx_topk_select. */
+typedef struct sx_select_state sx_select_state;
 
 SX_API int         sx_abi_version(void);
 SX_API const char *sx_error_string(int code);
@@ -141,27 +150,33 @@ SX_API int    sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int3
  *   M: rows [row0, row0 + S_loc) of the S x D cost matrix, leading dimension ld (elements);
  *   y_src: the S_loc source potentials of those rows; y_dst: the D sink potentials.
  *   Arc ids reported are global: (row0 + i) * D + j.
- *   header: counts / min (see sx_price_header).  Candidates (rc < -tol) are appended to
- *   cand_rc / cand_id (capacity cand_cap, unordered; may be NULL with cand_cap = 0).
+ *   header: counts / min (see sx_price_header).
  *   rc_out: optional full reduced-cost output (S_loc x D, ld_out), else NULL.
  *   variant: 0 = TMA-staged pipeline (needs 16 B aligned M and even ld; returns
  *   SX_ERR_UNALIGNED otherwise), 1 = vectorised direct loads, 2 = scalar loads (any
  *   alignment), -1 = choose automatically.
  * sx_price_arcs replaces net_manager.py:293-319 for an arc list:
  *   rc_k = c_k - (y[tail_k] - y[head_k]), negated where vbasis_k == -2.
- * sx_price_header_reset must be enqueued before the first sx_price_* call of a pass;
- *   several calls (row slabs, arc-list tail) may then accumulate into one header.
+ * Candidates: violators that can still be among the K most violating arcs are appended to
+ *   cand_rc / cand_id (capacity cand_cap, unordered).  "Can still be" is decided from a running
+ *   histogram of the appended reduced costs in `sel`, so the list stays O(K log(n / K)) long
+ *   however many arcs violate; header->n_violating stays exact.  cand_cap = 0 (cand_* and sel
+ *   NULL) prices for count / min only.
+ * sx_price_pass_begin must be enqueued before the first sx_price_* call of a pass (it clears the
+ *   header and `sel`, and records the K the pass prunes for; sel may be NULL when cand_cap = 0);
+ *   several calls (row slabs, arc-list tail) may then accumulate into one header / candidate list.
  */
-SX_API int    sx_price_header_reset(sx_price_header *header, void *stream);
+SX_API size_t sx_select_state_bytes(void);
+SX_API int    sx_price_pass_begin(sx_price_header *header, sx_select_state *sel, int64_t K, void *stream);
 SX_API int    sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int64_t S_loc, int64_t D,
                          const double *y_src, const double *y_dst, double tol,
-                         sx_price_header *header, double *cand_rc, int64_t *cand_id,
-                         int64_t cand_cap, double *rc_out, int64_t ld_out, int variant,
-                         void *stream);
+                         sx_price_header *header, sx_select_state *sel, double *cand_rc,
+                         int64_t *cand_id, int64_t cand_cap, double *rc_out, int64_t ld_out,
+                         int variant, void *stream);
 SX_API int    sx_price_arcs(const double *c, const int32_t *tail, const int32_t *head,
                      const int8_t *vbasis, const double *y, int64_t E, int64_t id0, double tol,
-                     sx_price_header *header, double *cand_rc, int64_t *cand_id,
-                     int64_t cand_cap, double *rc_out, void *stream);
+                     sx_price_header *header, sx_select_state *sel, double *cand_rc,
+                     int64_t *cand_id, int64_t cand_cap, double *rc_out, void *stream);
 
 /* Tuning knobs of sx_price_dense_ot (bench sweeps): index into the table of TMA pipeline shapes
  * {rows per box, stages, consumer warps, CTAs per SM} of variant 0 (see sx_price.cu), and the
@@ -169,23 +184,30 @@ SX_API int    sx_price_arcs(const double *c, const int32_t *tail, const int32_t 
 SX_API int    sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm);
 
 /* ---- top-k most violating arcs (north_star extension) -------
- * Among the candidates (rc, id) select the K smallest by (rc ascending, id ascending).
- *   n_cand_dev: device pointer to the candidate count (header->n_violating; clamped to
- *   cand_cap inside).  out_rc / out_id have capacity K; out_n (device int64) = min(K, n).
- *   Entries past out_n are filled with (+inf, -1) so fixed-size blocks can be all-gathered.
- *   K <= SX_TOPK_MAX_K uses the warp-shuffle bitonic path and needs no host round trip.
- * sx_topk_merge merges G such blocks (as gathered from G ranks) into one.  Block g has its rc
- *   list at blocks_rc + g * block_stride and its ids at blocks_id + g * block_stride (strides in
- *   8-byte elements, so the all-gathered buffer is consumed in place).  Optionally folds the G
- *   pricing headers {n_violating, min_rc_key} found at headers + g * block_stride into
- *   out_summary = {total n_violating, min key, largest single n_violating}.
+ * Among the candidates (rc, id) left by a pricing pass select the K smallest by (rc ascending,
+ * id ascending).  sel / header are the pass's selection state and header (the candidate count
+ * lives in sel).  out_rc / out_id have capacity K; out_n (device int64) = min(K, #violators).
+ * Entries past out_n are filled with (+inf, -1) so fixed-size blocks can be exchanged.
+ * sx_topk_select: K <= SX_TOPK_MAX_K runs the histogram filter + all-pairs rank (two launches,
+ *   no host round trip); if it cannot finish (more than 8192 candidates tie around the K-th
+ *   value) it raises SX_STATUS_NEED_SORTED in header->status and the caller runs
+ *   sx_topk_select_sorted on the same buffers.  K > SX_TOPK_MAX_K goes to the sorted path directly.
+ * sx_topk_select_sorted: bitonic slice sort + rank merge (K <= SX_TOPK_MAX_K) or two stable radix
+ *   argsorts (larger K; synchronises the stream once to read the candidate count).
+ * sx_topk_merge merges G sorted, padded blocks (as exchanged between G ranks) into one.  Block g
+ *   has its rc list at blocks_rc + g * block_stride and its ids at blocks_id + g * block_stride
+ *   (strides in 8-byte elements, so the gathered buffer is consumed in place).  Optionally folds
+ *   the G pricing headers found at headers + g * block_stride into out_summary =
+ *   {total n_violating, min key, largest single n_violating, OR of the status words}.
  */
 #define SX_TOPK_MAX_K 1024
 SX_API size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K);
-SX_API int    sx_topk_select(const double *cand_rc, const int64_t *cand_id,
-                      const unsigned long long *n_cand_dev, int64_t cand_cap, int64_t K,
-                      double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
-                      void *stream);
+SX_API int    sx_topk_select(const double *cand_rc, const int64_t *cand_id, int64_t cand_cap,
+                      sx_select_state *sel, sx_price_header *header, int64_t K, double *out_rc,
+                      int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes, void *stream);
+SX_API int    sx_topk_select_sorted(const double *cand_rc, const int64_t *cand_id, int64_t cand_cap,
+                      sx_select_state *sel, sx_price_header *header, int64_t K, double *out_rc,
+                      int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes, void *stream);
 SX_API size_t sx_topk_merge_workspace_bytes(int64_t G);
 SX_API int    sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t block_stride,
                      int64_t G, int64_t K, const int64_t *headers, double *out_rc, int64_t *out_id,

@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "sx_common.cuh"
+#include "sx_select.cuh"
 
 namespace sx {
 
@@ -82,46 +83,79 @@ __device__ __forceinline__ bool lt_or(double a, double b, bool acc) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Candidate compaction shared by all pricing kernels.
-// A warp reserves slots for all violators of its tile with ONE atomicAdd on
-// header->n_violating (which is also the exact violator count); once the buffer is full
-// it stops reserving and only counts (flushed at kernel end).
+// Violator accounting shared by all pricing kernels (rare path: a tile with at least one
+// violator).  Violators are COUNTED exactly in a per-warp register (one atomicAdd per warp at
+// kernel end); they are APPENDED to the candidate list only while they can still be among the
+// K most violating arcs, i.e. while their histogram bin is <= SelState::bstar (sx_select.cuh).
 // ---------------------------------------------------------------------------------------
 struct CandSink {
     sx_price_header *hdr;
+    SelState        *sel;   // nullptr <=> cap == 0 (count / min only)
     double          *rc;
     int64_t         *id;
     long long        cap;
 };
 
 struct WarpTally {
-    unsigned long long deferred = 0;   // violators counted but not reserved (lane 0 only)
-    bool               full     = false;
+    unsigned long long count = 0;   // violators seen by this warp (same value in every lane)
 };
 
-// Reserve `n` (warp-uniform) slots; returns the base slot or -1 if nothing can be written.
-__device__ __forceinline__ long long warp_reserve(const CandSink &sink, WarpTally &tally, unsigned n) {
-    if (tally.full || sink.cap == 0) {
-        if (lane_id() == 0) tally.deferred += n;
-        return -1;
+// NE elements per thread, given by val(e) / id(e) with e a compile-time index after unrolling.
+template <int NE, class ValFn, class IdFn>
+__device__ __forceinline__ void emit_violators(const CandSink &sink, WarpTally &tally, double thr, ValFn val,
+                                               IdFn id) {
+    unsigned nviol = 0;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) nviol += __popc(__ballot_sync(0xffffffffu, val(e) < thr));
+    tally.count += nviol;
+    if (sink.cap == 0 || nviol == 0) return;
+    SelState *st = sink.sel;
+    unsigned bs = 0;
+    if (lane_id() == 0) bs = ld_relaxed_u32(&st->bstar);
+    bs = __shfl_sync(0xffffffffu, bs, 0);
+    unsigned qm = 0;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const double v = val(e);
+        if (v < thr && cand_bin(v) <= bs) qm |= 1u << e;
     }
+    const unsigned mine = __popc(qm);
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane_id() >= o) incl += t;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
     unsigned long long base = 0;
-    if (lane_id() == 0) base = atomicAdd(&sink.hdr->n_violating, (unsigned long long)n);
+    if (lane_id() == 0) base = atomicAdd(&st->n_cand, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= (unsigned long long)sink.cap) {
-        tally.full = true;
-        return -1;
+    long long slot = (long long)base + (incl - mine);
+    bool dropped = false;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if (qm & (1u << e)) {
+            const double v = val(e);
+            if (slot < sink.cap) { sink.rc[slot] = v; sink.id[slot] = id(e); } else dropped = true;
+            ++slot;
+            atomicAdd(&st->fine[cand_bin(v)], 1u);
+        }
     }
-    return (long long)base;
-}
-__device__ __forceinline__ void cand_store(const CandSink &sink, long long slot, double rc, long long id) {
-    if (slot < sink.cap) {
-        sink.rc[slot] = rc;
-        sink.id[slot] = id;
+    if (dropped) atomicOr(&sink.hdr->status, kStatusCandOverflow);
+    __threadfence();   // fine before top: the coarse level never runs ahead of the fine one
+#pragma unroll
+    for (int e = 0; e < NE; ++e)
+        if (qm & (1u << e)) atomicAdd(&st->top[cand_bin(val(e)) >> 8], 1u);
+    // every kTightenPeriod candidates the warp that crosses the mark lowers the bound
+    const unsigned long long after = base + total;
+    if (base / kTightenPeriod != after / kTightenPeriod && after >= st->K) {
+        const unsigned b = warp_find_bound(st, st->K, nullptr);
+        if (lane_id() == 0 && b < bs) atomicMin(&st->bstar, b);
     }
 }
 __device__ __forceinline__ void warp_flush(const CandSink &sink, const WarpTally &tally) {
-    if (lane_id() == 0 && tally.deferred) atomicAdd(&sink.hdr->n_violating, tally.deferred);
+    if (lane_id() == 0 && tally.count) atomicAdd(&sink.hdr->n_violating, tally.count);
 }
 
 // Block-level min -> one atomicMin per CTA.
@@ -155,34 +189,11 @@ struct DenseParams {
     long long     n_col_blocks, n_row_tiles;
 };
 
-// Epilogue of one warp's share of a tile: RPT rows x 2 adjacent columns per thread already in
-// registers as reduced costs (+inf where masked).  Counts, reserves and stores the violators.
-template <int RPT>
-__device__ __forceinline__ void emit_violators(const DenseParams &p, WarpTally &tally, const double (&rc0)[RPT],
-                                               const double (&rc1)[RPT], long long gid0, long long row_stride,
-                                               int col_gap = 1) {
-    unsigned nviol = 0;
-#pragma unroll
-    for (int r = 0; r < RPT; ++r)
-        nviol += __popc(__ballot_sync(0xffffffffu, rc0[r] < p.thr)) + __popc(__ballot_sync(0xffffffffu, rc1[r] < p.thr));
-    long long slot = warp_reserve(p.sink, tally, nviol);
-    if (slot < 0) return;
-    const unsigned lt = (1u << lane_id()) - 1u;
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const long long gid = gid0 + r * row_stride;
-        const unsigned b0 = __ballot_sync(0xffffffffu, rc0[r] < p.thr);
-        if (rc0[r] < p.thr) cand_store(p.sink, slot + __popc(b0 & lt), rc0[r], gid);
-        slot += __popc(b0);
-        const unsigned b1 = __ballot_sync(0xffffffffu, rc1[r] < p.thr);
-        if (rc1[r] < p.thr) cand_store(p.sink, slot + __popc(b1 & lt), rc1[r], gid + col_gap);
-        slot += __popc(b1);
-    }
-}
-
-// Lazy epilogue.  The hot loop does ONE compare per reduced cost, against lim = max(running min,
-// -tol): a hit means "new minimum or violator", both rare, and only then are the exact minimum
-// updated and the violators counted and stored (fp64 min costs ~8 SASS instructions on sm_100a).
+// Lazy epilogue of one warp's share of a tile: RPT rows x 2 columns per thread already in registers
+// as reduced costs (+inf where masked).  The hot loop does ONE compare per reduced cost, against
+// lim = max(running min, -tol): a hit means "new minimum or violator", both rare, and only then are
+// the exact minimum updated and the violators counted / appended (fp64 min costs ~8 SASS
+// instructions on sm_100a).
 template <int RPT>
 __device__ __forceinline__ void tile_epilogue(const DenseParams &p, WarpTally &tally, double &tmin, double &lim,
                                               const double (&rc0)[RPT], const double (&rc1)[RPT], bool hit,
@@ -200,7 +211,10 @@ __device__ __forceinline__ void tile_epilogue(const DenseParams &p, WarpTally &t
         tmin = mn;
         lim = tmin > p.thr ? tmin : p.thr;
     }
-    if (__any_sync(0xffffffffu, viol)) emit_violators<RPT>(p, tally, rc0, rc1, gid0, row_stride, col_gap);
+    if (__any_sync(0xffffffffu, viol))
+        emit_violators<2 * RPT>(
+            p.sink, tally, p.thr, [&](int e) { return (e & 1) ? rc1[e >> 1] : rc0[e >> 1]; },
+            [&](int e) { return gid0 + (long long)(e >> 1) * row_stride + ((e & 1) ? col_gap : 0); });
 }
 
 // CWARPS consumer warps: 4 warps span the 256 box columns (2 adjacent columns per thread, so a
@@ -474,30 +488,31 @@ price_arcs_kernel(const double *__restrict__ c, const int32_t *__restrict__ tail
             lim = tmin > thr ? tmin : thr;
         }
         if (!__any_sync(0xffffffffu, viol)) continue;
-        unsigned nviol = 0;
-#pragma unroll
-        for (int q = 0; q < kArcPerThread; ++q) nviol += __popc(__ballot_sync(0xffffffffu, rc[q] < thr));
-        long long slot = warp_reserve(sink, tally, nviol);
-        if (slot >= 0) {
-            const unsigned lt = (1u << lane_id()) - 1u;
-#pragma unroll
-            for (int q = 0; q < kArcPerThread; ++q) {
-                const long long k = ch * chunk + (long long)q * kArcThreads + threadIdx.x;
-                const unsigned b = __ballot_sync(0xffffffffu, rc[q] < thr);
-                if (rc[q] < thr) cand_store(sink, slot + __popc(b & lt), rc[q], id0 + k);
-                slot += __popc(b);
-            }
-        }
+        const long long k0 = id0 + ch * chunk + threadIdx.x;
+        emit_violators<kArcPerThread>(
+            sink, tally, thr, [&](int q) { return rc[q]; },
+            [&](int q) { return k0 + (long long)q * kArcThreads; });
     }
     warp_flush(sink, tally);
     block_min_commit(tmin, sink.hdr, scratch, kArcThreads / 32, warp, (unsigned long long)E);
 }
 
-__global__ void header_reset_kernel(sx_price_header *h) {
-    h->n_violating = 0ull;
-    h->min_rc_key  = 0x7fffffffffffffffll;
-    h->n_priced    = 0ull;
-    h->reserved    = 0ull;
+// Start of a pricing pass: header cleared, selection state (histograms, counters) zeroed.
+__global__ void __launch_bounds__(256) pass_begin_kernel(sx_price_header *h, SelState *st, unsigned K) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        h->n_violating = 0ull;
+        h->min_rc_key  = 0x7fffffffffffffffll;
+        h->n_priced    = 0ull;
+        h->status      = 0ull;
+    }
+    if (st == nullptr) return;
+    uint4 *w = reinterpret_cast<uint4 *>(st);
+    const size_t n16 = sizeof(SelState) / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        if (i == 0) { z.z = kFineBins - 1u; z.w = K; }   // n_cand = 0 | bstar | K
+        w[i] = z;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -570,21 +585,24 @@ extern "C" int sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm) {
     return SX_OK;
 }
 
-extern "C" int sx_price_header_reset(sx_price_header *header, void *stream) {
-    if (!header) return SX_ERR_INVALID;
-    header_reset_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(header);
+extern "C" size_t sx_select_state_bytes(void) { return sizeof(SelState); }
+
+extern "C" int sx_price_pass_begin(sx_price_header *header, sx_select_state *sel, int64_t K, void *stream) {
+    if (!header || K < 0 || K > 0xffffffffll) return SX_ERR_INVALID;
+    if (((uintptr_t)sel & 15) != 0) return SX_ERR_UNALIGNED;
+    pass_begin_kernel<<<sel ? kNumSMs : 1, 256, 0, (cudaStream_t)stream>>>(header, (SelState *)sel, (unsigned)K);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }
 
 extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int64_t S_loc, int64_t D,
                                  const double *y_src, const double *y_dst, double tol,
-                                 sx_price_header *header, double *cand_rc, int64_t *cand_id,
-                                 int64_t cand_cap, double *rc_out, int64_t ld_out, int variant,
-                                 void *stream) {
+                                 sx_price_header *header, sx_select_state *sel, double *cand_rc,
+                                 int64_t *cand_id, int64_t cand_cap, double *rc_out, int64_t ld_out,
+                                 int variant, void *stream) {
     if (!M || !y_src || !y_dst || !header || S_loc < 0 || D <= 0 || ld < D || row0 < 0 || cand_cap < 0)
         return SX_ERR_INVALID;
-    if (cand_cap > 0 && (!cand_rc || !cand_id)) return SX_ERR_INVALID;
+    if (cand_cap > 0 && (!cand_rc || !cand_id || !sel)) return SX_ERR_INVALID;
     if (rc_out && ld_out < D) return SX_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     if (S_loc == 0) return SX_OK;
@@ -595,7 +613,8 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
 
     DenseParams p;
     p.y_src = y_src; p.y_dst = y_dst; p.S_loc = S_loc; p.D = D; p.row0 = row0; p.thr = -tol;
-    p.sink.hdr = header; p.sink.rc = cand_rc; p.sink.id = (int64_t *)cand_id; p.sink.cap = cand_cap;
+    p.sink.hdr = header; p.sink.sel = (SelState *)sel; p.sink.rc = cand_rc; p.sink.id = (int64_t *)cand_id;
+    p.sink.cap = cand_cap;
     p.rc_out = rc_out; p.ld_out = ld_out;
     p.n_col_blocks = (D + kBoxCols - 1) / kBoxCols;
 
@@ -634,13 +653,13 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
 
 extern "C" int sx_price_arcs(const double *c, const int32_t *tail, const int32_t *head,
                              const int8_t *vbasis, const double *y, int64_t E, int64_t id0, double tol,
-                             sx_price_header *header, double *cand_rc, int64_t *cand_id,
-                             int64_t cand_cap, double *rc_out, void *stream) {
+                             sx_price_header *header, sx_select_state *sel, double *cand_rc,
+                             int64_t *cand_id, int64_t cand_cap, double *rc_out, void *stream) {
     if (!c || !tail || !head || !y || !header || E < 0 || cand_cap < 0) return SX_ERR_INVALID;
-    if (cand_cap > 0 && (!cand_rc || !cand_id)) return SX_ERR_INVALID;
+    if (cand_cap > 0 && (!cand_rc || !cand_id || !sel)) return SX_ERR_INVALID;
     if (E == 0) return SX_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    CandSink sink{header, cand_rc, (int64_t *)cand_id, cand_cap};
+    CandSink sink{header, (SelState *)sel, cand_rc, (int64_t *)cand_id, cand_cap};
     const long long chunk = (long long)kArcThreads * kArcPerThread;
     long long n_chunks = (E + chunk - 1) / chunk;
     long long grid = (long long)kNumSMs * 8;

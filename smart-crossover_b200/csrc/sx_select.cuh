@@ -1,0 +1,140 @@
+// sx_select.cuh -- selection state shared by the pricing kernels (sx_price.cu) and the top-k
+// selection (sx_topk.cu).
+//
+// While a pricing pass streams the arcs, the violators that can still be among the K most
+// violating ones are appended to an unordered candidate list, and a two-level histogram over an
+// order-preserving 19-bit image of their reduced cost (sign-stripped exponent + 8 mantissa bits,
+// 0.4 % relative width per bin) is kept beside it.  Every `kTightenPeriod` appended candidates the
+// appending warp scans the histogram for the smallest bin b* whose cumulative count reaches K and
+// lowers `bstar` to it: from then on only violators with bin <= b* are appended (the K-th smallest
+// reduced cost lies in a bin <= b*, and counts only grow, so the bound stays valid).  The list
+// therefore stays O(K log(n/K)) long however many arcs violate, and the final selection
+// (sx_topk.cu) is a filter by the final b* plus an all-pairs rank of the few survivors.
+#pragma once
+#include "sx_common.cuh"
+
+namespace sx {
+
+constexpr int      kFineBits      = 19;
+constexpr unsigned kFineBins      = 1u << kFineBits;          // 524 288 bins, 2 MB
+constexpr unsigned kTopBins       = kFineBins / 256;          // 2 048 coarse bins of 256 fine bins
+constexpr unsigned kTightenPeriod = 4096;                     // candidates between two tightenings
+constexpr int      kSurvCap       = 8192;                     // survivors the all-pairs rank handles
+
+struct SelState {
+    unsigned long long n_cand;       // candidates appended so far (can exceed the buffer capacity)
+    unsigned int       bstar;        // only violators with bin <= bstar are appended
+    unsigned int       K;            // selection size this pass prunes for
+    unsigned int       n_surv;       // survivors of the final filter
+    unsigned int       done;         // CTA completion counter of the rank kernel
+    unsigned int       pad[10];
+    unsigned int       top[kTopBins];
+    unsigned int       fine[kFineBins];
+};
+static_assert(sizeof(SelState) == 64 + 4 * (kTopBins + kFineBins), "SelState layout");
+
+// bits of sx_price_header.status
+constexpr unsigned long long kStatusCandOverflow = 1ull;   // candidate buffer too small: grow and price again
+constexpr unsigned long long kStatusNeedSlowPath = 2ull;   // too many survivors (ties): use sx_topk_select_sorted
+
+// Monotone (non-strict) 19-bit image of a reduced cost: a < b  =>  bin(a) <= bin(b).
+// Negative values (every violator when tol >= 0) use the full resolution; anything >= +0 clamps
+// into the last bin.
+__device__ __forceinline__ unsigned cand_bin(double rc) {
+    const unsigned long long k = f64_to_sort_key(rc) >> (64 - 1 - kFineBits);   // sign + 19 bits
+    return k < (unsigned long long)kFineBins ? (unsigned)k : kFineBins - 1u;
+}
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const unsigned *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// Executed by one full warp.  Returns (to every lane) the smallest fine bin b with
+// cum(<= b) >= need, or kFineBins - 1 if the histogram holds fewer than `need` entries.
+// `top` may lag behind `fine` (fine is incremented first, then a fence, then top), never the
+// other way round, so the returned bound is valid for the true counts.
+static __device__ __noinline__ unsigned warp_find_bound(const SelState *st, unsigned need, unsigned *below_out) {
+    const unsigned lane = threadIdx.x & 31u;
+    // level 1: 2048 coarse bins, 64 per lane
+    constexpr int kPerLane = kTopBins / 32;
+    unsigned local = 0;
+    const unsigned *tp = st->top + lane * kPerLane;
+#pragma unroll 4
+    for (int q = 0; q < kPerLane; q += 4) {
+        const uint4 v = ld_relaxed_v4(tp + q);
+        local += v.x + v.y + v.z + v.w;
+    }
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total < need) {
+        if (below_out) *below_out = total;
+        return kFineBins - 1u;
+    }
+    const unsigned cross = __ballot_sync(0xffffffffu, incl >= need);
+    const int      owner = __ffs(cross) - 1;
+    unsigned c_star = 0, below = 0;
+    if ((int)lane == owner) {
+        unsigned cum = incl - local;
+        int q = 0;
+        for (; q < kPerLane; ++q) {
+            const unsigned v = ld_relaxed_u32(tp + q);
+            if (cum + v >= need) break;
+            cum += v;
+        }
+        if (q == kPerLane) q = kPerLane - 1;   // counts grew between the two reads: stay in range
+        c_star = lane * kPerLane + q;
+        below = cum;
+    }
+    c_star = __shfl_sync(0xffffffffu, c_star, owner);
+    below  = __shfl_sync(0xffffffffu, below, owner);
+    // level 2: the 256 fine bins of coarse bin c_star, 8 per lane
+    const unsigned *fp = st->fine + (size_t)c_star * 256 + lane * 8;
+    const uint4 a = ld_relaxed_v4(fp), b = ld_relaxed_v4(fp + 4);
+    const unsigned f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    unsigned l2 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) l2 += f[q];
+    unsigned incl2 = l2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl2, o);
+        if (lane >= o) incl2 += t;
+    }
+    const unsigned cross2 = __ballot_sync(0xffffffffu, below + incl2 >= need);
+    if (cross2 == 0) {                        // cannot happen (fine >= top); no bound rather than a wrong one
+        if (below_out) *below_out = below;
+        return kFineBins - 1u;
+    }
+    const int owner2 = __ffs(cross2) - 1;
+    unsigned b_star = 0, below2 = 0;
+    if ((int)lane == owner2) {
+        unsigned cum = below + incl2 - l2;
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            if (q == r && cum + f[r] < need) { cum += f[r]; ++q; }
+        }
+        if (q > 7) q = 7;
+        b_star = c_star * 256 + lane * 8 + q;
+        below2 = cum;
+    }
+    b_star = __shfl_sync(0xffffffffu, b_star, owner2);
+    below2 = __shfl_sync(0xffffffffu, below2, owner2);
+    if (below_out) *below_out = below2;
+    return b_star;
+}
+
+}  // namespace sx

@@ -6,17 +6,27 @@
 // (rc, id) is a strict total order, so the result does not depend on the (unordered)
 // compaction, on the slicing below, or on how many GPUs priced the matrix.
 //
-// K <= 1024 (device-driven, no host round trip):
+// Fast path, K <= 1024 (device-driven, two launches, no host round trip):
+//   1. filter: the pricing kernels left a histogram of the candidates' reduced costs
+//      (sx_select.cuh); b* = the smallest bin whose cumulative count reaches K.  Candidates
+//      with bin <= b* survive: the K best plus the rest of bin b* (0.4 % wide);
+//   2. all-pairs rank: every survivor counts the survivors below it; that count is its
+//      position in the output.  O(n_surv^2) compares spread over the whole GPU (1 to 32 lanes
+//      per element), a few microseconds for the typical 1-2 K survivors.
+//   More than 8192 survivors (massive ties around the K-th value) raise
+//   SX_STATUS_NEED_SORTED in the pricing header and the caller runs the sorted path.
+// The same all-pairs rank merges the per-GPU lists after the exchange (sx_topk_merge).
+// Sorted path (sx_topk_select_sorted), K <= 1024:
 //   1. every CTA bitonic-sorts one slice of 4096 candidates -- the 5 innermost stages of each
 //      merge step run on registers with warp shuffles, the wider ones through shared memory --
 //      and keeps the slice's K best as a padded, sorted list;
 //   2. rank merge: an element's global rank is the sum over lists of lower_bound(list, element);
 //      elements above the smallest "K-th of a full list" cannot be in the answer and are skipped.
-// The same rank merge combines the per-GPU lists after the all-gather (sx_topk_merge).
 // K > 1024: two stable radix argsorts (by id, then by rc) over the candidates.
 #include <math.h>
 
 #include "sx_common.cuh"
+#include "sx_select.cuh"
 
 namespace sx {
 
@@ -164,12 +174,12 @@ topk_prep_kernel(const double *__restrict__ lists_rc, const long long *__restric
     for (int i = threadIdx.x; i < K; i += blockDim.x) { out_rc[i] = INFINITY; out_id[i] = -1; }
     if (headers && out_summary && threadIdx.x == 0) {
         // fold the per-rank pricing headers {n_violating, min_rc_key}: total, min, largest single count
-        long long tot = 0, mn = 0x7fffffffffffffffll, mx = 0;
+        long long tot = 0, mn = 0x7fffffffffffffffll, mx = 0, stt = 0;
         for (int l = 0; l < L; ++l) {
             const long long c = headers[(long long)l * LS], k = headers[(long long)l * LS + 1];
-            tot += c; mn = k < mn ? k : mn; mx = c > mx ? c : mx;
+            tot += c; mn = k < mn ? k : mn; mx = c > mx ? c : mx; stt |= headers[(long long)l * LS + 3];
         }
-        out_summary[0] = tot; out_summary[1] = mn; out_summary[2] = mx;
+        out_summary[0] = tot; out_summary[1] = mn; out_summary[2] = mx; out_summary[3] = stt;
     }
     __shared__ Cand s_thr[32];
     __shared__ int  s_warp[32];
@@ -307,6 +317,151 @@ topk_rank_kernel(const double *__restrict__ lists_rc, const long long *__restric
     }
 }
 
+// ---- fast path ----------------------------------------------------------------------------
+constexpr int kApThreads = 256;
+constexpr int kApTile    = 2048;
+
+struct KeyId {
+    unsigned long long key;   // f64_to_sort_key(rc); ~0 for padding
+    long long          id;    // arc id; INT64_MAX for padding
+};
+__device__ __forceinline__ bool keyid_less(const KeyId &a, const KeyId &b) {
+    return a.key < b.key || (a.key == b.key && a.id < b.id);
+}
+
+// Survivors of the final bound: candidates whose bin is <= b*.
+__global__ void __launch_bounds__(256)
+sel_filter_kernel(const double *__restrict__ cand_rc, const long long *__restrict__ cand_id, long long cand_cap,
+                  SelState *st, sx_price_header *hdr, unsigned K, double *__restrict__ surv_rc,
+                  long long *__restrict__ surv_id) {
+    __shared__ unsigned s_b;
+    const unsigned long long n64 = st->n_cand;
+    long long n = (long long)n64;
+    if (n64 > (unsigned long long)cand_cap) {
+        n = cand_cap;
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&hdr->status, kStatusCandOverflow);
+    }
+    if (threadIdx.x < 32) {
+        const unsigned b = warp_find_bound(st, K, nullptr);
+        if (threadIdx.x == 0) s_b = b;
+    }
+    __syncthreads();
+    const unsigned b = s_b;
+    const unsigned lt = (1u << lane_id()) - 1u;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_ceil = (n + 31) / 32 * 32;               // whole warps stay in the loop (ballots)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_ceil; i += stride) {
+        double rc = 0.0;
+        bool keep = false;
+        if (i < n) { rc = cand_rc[i]; keep = cand_bin(rc) <= b; }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0) continue;
+        unsigned base = 0;
+        if (lane_id() == 0) base = atomicAdd(&st->n_surv, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned slot = base + __popc(m & lt);
+        if (keep && slot < (unsigned)kSurvCap) { surv_rc[slot] = rc; surv_id[slot] = cand_id[i]; }
+    }
+}
+
+// All-pairs rank of n elements given by load(e) (padding sorts last).  Every thread of the grid
+// takes part; L = 1..32 lanes share one element and split the comparison range.  emit(e, rank)
+// is called once per real element.  Needs n <= gridDim.x * kApThreads.
+template <class LoadFn, class EmitFn>
+__device__ __forceinline__ void all_pairs_rank(int n, LoadFn load, EmitFn emit) {
+    __shared__ KeyId tile[kApTile];
+    const int T = gridDim.x * kApThreads;
+    int L = 32;
+    while (L > 1 && (long long)n * L > T) L >>= 1;
+    const int gtid = blockIdx.x * kApThreads + threadIdx.x;
+    const int e = gtid / L, sub = gtid % L;
+    if ((blockIdx.x * kApThreads) / L >= n) return;            // CTA-uniform: nothing to rank here
+    KeyId mine{~0ull, 0x7fffffffffffffffll};
+    const bool real = e < n;
+    if (real) mine = load(e);
+    const bool valid = real && mine.key != ~0ull;
+    int cnt = 0;
+    for (int t0 = 0; t0 < n; t0 += kApTile) {
+        const int tn = n - t0 < kApTile ? n - t0 : kApTile;
+        __syncthreads();
+        for (int j = threadIdx.x; j < tn; j += kApThreads) tile[j] = load(t0 + j);
+        __syncthreads();
+        if (valid) {
+#pragma unroll 4
+            for (int j = sub; j < tn; j += L) cnt += keyid_less(tile[j], mine) ? 1 : 0;
+        }
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (valid && sub == 0) emit(e, cnt);
+}
+
+__global__ void __launch_bounds__(kApThreads)
+sel_rank_kernel(const SelState *st, sx_price_header *hdr, const double *__restrict__ surv_rc,
+                const long long *__restrict__ surv_id, int K, double *__restrict__ out_rc,
+                long long *__restrict__ out_id, long long *out_n) {
+    const unsigned n_raw = st->n_surv;
+    const bool too_many = n_raw > (unsigned)kSurvCap;
+    const int n = too_many ? 0 : (int)n_raw;
+    const int n_out = n < K ? n : K;
+    if (blockIdx.x == 0) {
+        for (int i = n_out + threadIdx.x; i < K; i += kApThreads) { out_rc[i] = INFINITY; out_id[i] = -1; }
+        if (threadIdx.x == 0) {
+            *out_n = n_out;
+            if (too_many) atomicOr(&hdr->status, kStatusNeedSlowPath);
+        }
+    }
+    if (n == 0) return;
+    all_pairs_rank(
+        n, [&](int e) { return KeyId{f64_to_sort_key(surv_rc[e]), surv_id[e]}; },
+        [&](int e, int rank) {
+            if (rank < K) { out_rc[rank] = surv_rc[e]; out_id[rank] = surv_id[e]; }
+        });
+}
+
+// Merge of G sorted, padded blocks of K (all-gathered from G ranks): all-pairs rank over G * K.
+__global__ void __launch_bounds__(kApThreads)
+merge_rank_kernel(const double *__restrict__ blocks_rc, const long long *__restrict__ blocks_id, long long LS, int G,
+                  int K, const long long *headers, double *__restrict__ out_rc, long long *__restrict__ out_id,
+                  long long *out_n, long long *out_summary) {
+    const int n = G * K;
+    auto load = [&](int e) {
+        const long long off = (long long)(e / K) * LS + (e % K);
+        const long long id = blocks_id[off];
+        return id < 0 ? KeyId{~0ull, 0x7fffffffffffffffll} : KeyId{f64_to_sort_key(blocks_rc[off]), id};
+    };
+    if (blockIdx.x == 0) {
+        __shared__ int s_cnt[kApThreads / 32];
+        int c = 0;
+        for (int e = threadIdx.x; e < n; e += kApThreads) c += blocks_id[(long long)(e / K) * LS + (e % K)] >= 0;
+        c = warp_sum(c);
+        if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = c;
+        __syncthreads();
+        int n_real = 0;
+        for (int w = 0; w < kApThreads / 32; ++w) n_real += s_cnt[w];
+        const int n_out = n_real < K ? n_real : K;
+        for (int i = n_out + threadIdx.x; i < K; i += kApThreads) { out_rc[i] = INFINITY; out_id[i] = -1; }
+        if (threadIdx.x == 0) {
+            *out_n = n_out;
+            if (headers && out_summary) {
+                // fold the per-rank pricing headers: total count, min key, largest single count, status bits
+                long long tot = 0, mn = 0x7fffffffffffffffll, mx = 0, stt = 0;
+                for (int g = 0; g < G; ++g) {
+                    const long long *h = headers + (long long)g * LS;
+                    tot += h[0]; mn = h[1] < mn ? h[1] : mn; mx = h[0] > mx ? h[0] : mx; stt |= h[3];
+                }
+                out_summary[0] = tot; out_summary[1] = mn; out_summary[2] = mx; out_summary[3] = stt;
+            }
+        }
+        __syncthreads();
+    }
+    all_pairs_rank(n, load, [&](int e, int rank) {
+        if (rank < K) {
+            const long long off = (long long)(e / K) * LS + (e % K);
+            out_rc[rank] = blocks_rc[off]; out_id[rank] = blocks_id[off];
+        }
+    });
+}
+
 // ---- large-K path helpers ---------------------------------------------------------------
 __global__ void tk_gather_kernel(const double *__restrict__ rc, const long long *__restrict__ id,
                                  const uint32_t *__restrict__ perm, long long n, double *rc_out, long long *id_out) {
@@ -341,23 +496,35 @@ using namespace sx;
 
 extern "C" size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K) {
     if (cand_cap < 0 || K < 0) return 0;
+    const size_t fast = 2 * carve_bytes((size_t)kSurvCap, 8);
     if (K <= SX_TOPK_MAX_K) {
         const size_t L = ((size_t)cand_cap + kTkSlice - 1) / kTkSlice + 1;
-        return carve_bytes(L * (size_t)(K > 0 ? K : 1), 8) * 2 + 2 * carve_bytes(L + 2, 4) + 256;
+        return fast + carve_bytes(L * (size_t)(K > 0 ? K : 1), 8) * 2 + 2 * carve_bytes(L + 2, 4) + 256;
     }
-    return 2 * carve_bytes((size_t)cand_cap, 8) + 2 * carve_bytes((size_t)cand_cap, 4) +
+    return fast + 2 * carve_bytes((size_t)cand_cap, 8) + 2 * carve_bytes((size_t)cand_cap, 4) +
            sx_argsort_workspace_bytes(cand_cap) + 256;
 }
 
-extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id,
-                              const unsigned long long *n_cand_dev, int64_t cand_cap, int64_t K,
-                              double *out_rc, int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes,
-                              void *stream) {
-    if (K <= 0 || cand_cap < 0 || !n_cand_dev || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
+static int topk_check_args(const double *cand_rc, const int64_t *cand_id, int64_t cand_cap,
+                           const sx_select_state *sel, const sx_price_header *header, int64_t K,
+                           const double *out_rc, const int64_t *out_id, const int64_t *out_n, const void *ws,
+                           size_t ws_bytes) {
+    if (K <= 0 || cand_cap < 0 || !sel || !header || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
     if (cand_cap > 0 && (!cand_rc || !cand_id)) return SX_ERR_INVALID;
     if (!ws || ws_bytes < sx_topk_workspace_bytes(cand_cap, K)) return SX_ERR_WORKSPACE;
+    return SX_OK;
+}
+
+extern "C" int sx_topk_select_sorted(const double *cand_rc, const int64_t *cand_id, int64_t cand_cap,
+                                     sx_select_state *sel, sx_price_header *header, int64_t K, double *out_rc,
+                                     int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes, void *stream) {
+    int arg = topk_check_args(cand_rc, cand_id, cand_cap, sel, header, K, out_rc, out_id, out_n, ws, ws_bytes);
+    if (arg != SX_OK) return arg;
     cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long *n_cand_dev = &((const SelState *)sel)->n_cand;
     Carver cv(ws);
+    cv.take<double>(kSurvCap);
+    cv.take<long long>(kSurvCap);
     if (K <= SX_TOPK_MAX_K) {
         const int L = (int)((cand_cap + kTkSlice - 1) / kTkSlice);
         if (L == 0) {
@@ -405,6 +572,30 @@ extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id,
     return SX_OK;
 }
 
+extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id, int64_t cand_cap,
+                              sx_select_state *sel, sx_price_header *header, int64_t K, double *out_rc,
+                              int64_t *out_id, int64_t *out_n, void *ws, size_t ws_bytes, void *stream) {
+    if (K > SX_TOPK_MAX_K)
+        return sx_topk_select_sorted(cand_rc, cand_id, cand_cap, sel, header, K, out_rc, out_id, out_n, ws, ws_bytes,
+                                     stream);
+    int arg = topk_check_args(cand_rc, cand_id, cand_cap, sel, header, K, out_rc, out_id, out_n, ws, ws_bytes);
+    if (arg != SX_OK) return arg;
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(ws);
+    double *surv_rc = cv.take<double>(kSurvCap);
+    long long *surv_id = cv.take<long long>(kSurvCap);
+    long long grid = (cand_cap + 256 * 8 - 1) / (256 * 8);
+    if (grid > kNumSMs * 2) grid = kNumSMs * 2;
+    if (grid < 1) grid = 1;
+    sel_filter_kernel<<<(int)grid, 256, 0, st>>>(cand_rc, (const long long *)cand_id, cand_cap, (SelState *)sel, header,
+                                                 (unsigned)K, surv_rc, surv_id);
+    SX_LAUNCH_CHECK();
+    sel_rank_kernel<<<kNumSMs, kApThreads, 0, st>>>((const SelState *)sel, header, surv_rc, surv_id, (int)K, out_rc,
+                                                    (long long *)out_id, (long long *)out_n);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}
+
 extern "C" size_t sx_topk_merge_workspace_bytes(int64_t G) {
     if (G < 0) return 0;
     return 2 * carve_bytes((size_t)G + 2, 4) + 256;
@@ -418,6 +609,14 @@ extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, 
     if (G > (1 << 20) || K > (1ll << 30)) return SX_ERR_TOO_LARGE;
     if (!ws || ws_bytes < sx_topk_merge_workspace_bytes(G)) return SX_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    if (G * K <= 2 * kSurvCap) {
+        merge_rank_kernel<<<kNumSMs, kApThreads, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G,
+                                                          (int)K, (const long long *)headers, out_rc,
+                                                          (long long *)out_id, (long long *)out_n,
+                                                          (long long *)out_summary);
+        SX_LAUNCH_CHECK();
+        return SX_OK;
+    }
     Carver cv(ws);
     int *plen = cv.take<int>(G + 2), *poff = cv.take<int>(G + 2);
     topk_prep_kernel<<<1, 1024, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G, (int)K, nullptr,

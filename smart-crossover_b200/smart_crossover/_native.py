@@ -15,7 +15,9 @@ SX_ERR_UNALIGNED = -6
 SX_PLUS_IS_HEAD = 0
 SX_PLUS_IS_TAIL = 1
 SX_TOPK_MAX_K = 1024
-SX_ABI_VERSION = 1
+SX_STATUS_CAND_OVERFLOW = 1
+SX_STATUS_NEED_SORTED = 2
+SX_ABI_VERSION = 2
 
 
 class SxError(RuntimeError):
@@ -29,7 +31,7 @@ class SxError(RuntimeError):
 
 class PriceHeader(ctypes.Structure):
     _fields_ = [("n_violating", ctypes.c_ulonglong), ("min_rc_key", ctypes.c_longlong),
-                ("n_priced", ctypes.c_ulonglong), ("reserved", ctypes.c_ulonglong)]
+                ("n_priced", ctypes.c_ulonglong), ("status", ctypes.c_ulonglong)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -65,12 +67,14 @@ SIGNATURES = {
     "sx_kruskal": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "sx_tree_potentials_workspace_bytes": (_sz, [_i64]),
     "sx_tree_potentials": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _p, _i64, _int, _i64, _p, _p, _p, _sz, _p]),
-    "sx_price_header_reset": (_int, [_p, _p]),
-    "sx_price_dense_ot": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _dbl, _p, _p, _p, _i64, _p, _i64, _int, _p]),
-    "sx_price_arcs": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _dbl, _p, _p, _p, _i64, _p, _p]),
+    "sx_select_state_bytes": (_sz, []),
+    "sx_price_pass_begin": (_int, [_p, _p, _i64, _p]),
+    "sx_price_dense_ot": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _dbl, _p, _p, _p, _p, _i64, _p, _i64, _int, _p]),
+    "sx_price_arcs": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _dbl, _p, _p, _p, _p, _i64, _p, _p]),
     "sx_price_set_tuning": (_int, [_int, _int]),
     "sx_topk_workspace_bytes": (_sz, [_i64, _i64]),
-    "sx_topk_select": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "sx_topk_select": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "sx_topk_select_sorted": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "sx_topk_merge_workspace_bytes": (_sz, [_i64]),
     "sx_topk_merge": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sx_exchange_buffer_bytes": (_sz, [_i64, _int]),

@@ -136,9 +136,11 @@ class PriceResult:
 class Pricer:
     """Reusable buffers for repeated pricing passes over one problem (one CG loop).
 
-    The top-K rc list, the id list and the pricing header live in ONE int64 tensor
-    `block = [K rc bits | K ids | header (4)]`, so a rank's whole contribution to the multi-GPU
-    all-gather is a single contiguous buffer that needs no packing kernels."""
+    The top-K rc list, the id list, the pricing header and the output count live in ONE int64
+    tensor `block = [K rc bits | K ids | header (4) | n_out | pad]`, so a rank's whole contribution
+    to the multi-GPU exchange -- and the per-pass read-back -- is a single contiguous buffer."""
+
+    BLOCK_TAIL = 6      # header (4) + n_out + pad (block length stays even: 16-byte peer stores)
 
     def __init__(self, device, K: int, cand_cap: int | None = None):
         _require_cuda()
@@ -147,17 +149,17 @@ class Pricer:
         if cand_cap is None:
             cand_cap = max(64 * self.K, 1 << 20) if self.K > 0 else 0
         self.cap = int(cand_cap)
+        self.sel = torch.zeros(lib.sx_select_state_bytes(), dtype=torch.uint8, device=device) if self.K > 0 else None
         self._alloc()
         Kp = max(self.K, 1)
         self.Kp = Kp
-        self.block = torch.zeros(2 * Kp + 4, dtype=torch.int64, device=device)
+        self.block = torch.zeros(2 * Kp + self.BLOCK_TAIL, dtype=torch.int64, device=device)
         self.out_rc = self.block[:Kp].view(torch.float64)
         self.out_id = self.block[Kp:2 * Kp]
         self.header = self.block[2 * Kp:2 * Kp + 4]
-        self.out_n = torch.zeros(1, dtype=torch.int64, device=device)
+        self.out_n = self.block[2 * Kp + 4:2 * Kp + 5]
         # pinned staging for the per-pass host round trip
-        self.h_block = torch.zeros(2 * Kp + 4, dtype=torch.int64).pin_memory()
-        self.h_n = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.h_block = torch.zeros(2 * Kp + self.BLOCK_TAIL, dtype=torch.int64).pin_memory()
         self.launches = 0
 
     def _alloc(self):
@@ -166,48 +168,65 @@ class Pricer:
         self.ws = _ws(lib.sx_topk_workspace_bytes(self.cap, max(self.K, 1)), self.device)
 
     def reset(self):
-        check(lib.sx_price_header_reset(_ptr(self.header), _stream()), "sx_price_header_reset")
+        check(lib.sx_price_pass_begin(_ptr(self.header), _ptr(self.sel), self.K, _stream()), "sx_price_pass_begin")
         self.launches += 1
 
     def price_dense(self, M, ld, row0, S_loc, D, y_src, y_dst, tol=TOL_RC, rc_out=None, variant=-1):
         check(lib.sx_price_dense_ot(_ptr(M), ld, row0, S_loc, D, _ptr(y_src), _ptr(y_dst), float(tol),
-                                    _ptr(self.header), _ptr(self.cand_rc), _ptr(self.cand_id), self.cap,
-                                    _ptr(rc_out), D if rc_out is not None else 0, variant, _stream()),
+                                    _ptr(self.header), _ptr(self.sel), _ptr(self.cand_rc), _ptr(self.cand_id),
+                                    self.cap if self.K > 0 else 0, _ptr(rc_out), D if rc_out is not None else 0,
+                                    variant, _stream()),
               "sx_price_dense_ot")
         self.launches += 1
 
     def price_arcs(self, c, tail, head, vbasis, y, id0=0, tol=TOL_RC, rc_out=None):
         check(lib.sx_price_arcs(_ptr(c), _ptr(tail), _ptr(head), _ptr(vbasis), _ptr(y), c.numel(), id0,
-                                float(tol), _ptr(self.header), _ptr(self.cand_rc), _ptr(self.cand_id),
-                                self.cap, _ptr(rc_out), _stream()), "sx_price_arcs")
+                                float(tol), _ptr(self.header), _ptr(self.sel), _ptr(self.cand_rc),
+                                _ptr(self.cand_id), self.cap if self.K > 0 else 0, _ptr(rc_out), _stream()),
+              "sx_price_arcs")
         self.launches += 1
 
-    def select(self):
-        """Enqueue the top-K selection over the compacted candidates (device only)."""
+    def select(self, sorted_path: bool = False):
+        """Enqueue the top-K selection over the candidates (device only).  `sorted_path` forces the
+        slice-sort selection, which the fast one asks for through SX_STATUS_NEED_SORTED."""
         if self.K > 0:
-            check(lib.sx_topk_select(_ptr(self.cand_rc), _ptr(self.cand_id), _ptr(self.header), self.cap,
-                                     self.K, _ptr(self.out_rc), _ptr(self.out_id), _ptr(self.out_n),
-                                     _ptr(self.ws), self.ws.numel(), _stream()), "sx_topk_select")
-            self.launches += 3 if self.K <= _native.SX_TOPK_MAX_K else 6
+            fn = lib.sx_topk_select_sorted if sorted_path else lib.sx_topk_select
+            check(fn(_ptr(self.cand_rc), _ptr(self.cand_id), self.cap, _ptr(self.sel), _ptr(self.header),
+                     self.K, _ptr(self.out_rc), _ptr(self.out_id), _ptr(self.out_n),
+                     _ptr(self.ws), self.ws.numel(), _stream()), "sx_topk_select")
+            if self.K > _native.SX_TOPK_MAX_K:
+                self.launches += 6
+            else:
+                self.launches += 3 if sorted_path else 2
 
     def fetch(self) -> PriceResult:
-        """Device -> pinned host copy of the block (top-K + header); one synchronisation."""
-        self.h_block.copy_(self.block, non_blocking=True)
-        if self.K > 0:
-            self.h_n.copy_(self.out_n, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        h = self.h_block.numpy()
-        Kp = self.Kp
+        """Device -> pinned host copy of the block (top-K + header + count); one synchronisation.
+        Runs the sorted selection and reads again if the fast one asked for it."""
+        while True:
+            self.h_block.copy_(self.block, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            h = self.h_block.numpy()
+            Kp = self.Kp
+            self.status = int(h[2 * Kp + 3])
+            if self.K > 0 and (self.status & _native.SX_STATUS_NEED_SORTED) \
+                    and not (self.status & _native.SX_STATUS_CAND_OVERFLOW):
+                self.header[3:4].zero_()
+                self.select(sorted_path=True)
+                continue
+            break
         nviol = int(h[2 * Kp]) & 0xFFFFFFFFFFFFFFFF
         min_rc = float(lib.sx_key_to_f64(int(h[2 * Kp + 1])))
-        k = int(self.h_n[0].item()) if self.K > 0 else 0
+        k = int(h[2 * Kp + 4]) if self.K > 0 else 0
         return PriceResult(nviol, min_rc, h[Kp:Kp + k].copy(), h[:k].view(np.float64).copy())
 
-    def overflowed(self, res: PriceResult) -> bool:
-        return self.K > 0 and res.n_violating > self.cap
+    def overflowed(self, res: PriceResult | None = None) -> bool:
+        return self.K > 0 and bool(self.status & _native.SX_STATUS_CAND_OVERFLOW)
 
-    def grow(self, n_violating: int):
-        self.cap = int(n_violating)
+    def grow(self, n_violating: int = 0):
+        """Enlarge the candidate buffer after SX_STATUS_CAND_OVERFLOW (x4, at most every violator)."""
+        self.cap = max(4 * self.cap, 1024)
+        if n_violating:
+            self.cap = min(self.cap, max(int(n_violating), 1024))
         self._alloc()
 
 
@@ -252,8 +271,8 @@ def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor, headers: torch.
     """Merge G sorted, padded top-K lists into one (rc, id, n[, summary]) on the device.
 
     blocks_rc / blocks_id are (G, K) views that may be strided (e.g. columns of the all-gathered
-    (G, 2K+4) buffer); `headers` (G, >=2) with the same row stride folds the per-rank
-    {n_violating, min key} into summary = {total, min key, largest single count}."""
+    (G, 2K+4) buffer); `headers` (G, 4) with the same row stride folds the per-rank
+    pricing headers into summary = {total, min key, largest single count, OR of status words}."""
     G, K = blocks_rc.shape
     stride = blocks_rc.stride(0)
     assert blocks_id.stride(0) == stride and blocks_rc.stride(1) == 1 and blocks_id.stride(1) == 1
@@ -261,7 +280,7 @@ def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor, headers: torch.
     out_rc = torch.empty(K, dtype=torch.float64, device=dev_)
     out_id = torch.empty(K, dtype=torch.int64, device=dev_)
     out_n = torch.zeros(1, dtype=torch.int64, device=dev_)
-    summary = torch.zeros(3, dtype=torch.int64, device=dev_) if headers is not None else None
+    summary = torch.zeros(4, dtype=torch.int64, device=dev_) if headers is not None else None
     if headers is not None:
         assert headers.stride(0) == stride
     ws = _ws(lib.sx_topk_merge_workspace_bytes(G), dev_)

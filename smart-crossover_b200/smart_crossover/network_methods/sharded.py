@@ -8,8 +8,9 @@ as one contiguous slab in its HBM; a pricing pass is
     y (S + D fp64, <= 1 MB) on every rank
       -> sx_price_dense_ot over the slab   (count, min, violator compaction)
       -> sx_topk_select                    (local K best, padded block)
-      -> all_gather of one packed block per rank: K rc + K ids + (count, min key) = 16 K + 16 B
-      -> sx_topk_merge over the G blocks   (rank merge; result independent of G)
+      -> exchange of one packed block per rank: K rc + K ids + header = 16 K + 48 B
+         (NVLink peer stores, sx_exchange_blocks; or an NCCL all-gather)
+      -> sx_topk_merge over the G blocks   (all-pairs rank; result independent of G)
 
 With world size 1 the collective and the merge are skipped.  The reference has no
 counterpart (single process, `net_manager.py:485-497` prices every arc on one core).
@@ -21,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 from .. import device as dev
+from .. import _native
 from .._native import check, lib
 
 
@@ -32,8 +34,8 @@ def row_partition(S: int, world: int, rank: int):
 
 
 def block_views(gathered: torch.Tensor, K: int):
-    """Views into the all-gathered (G, 2K+4) int64 buffer: (G, K) rc, (G, K) ids, (G, 4) headers.
-    Each rank's row is its `Pricer.block` = [K rc bits | K ids | n_violating, min key, n_priced, -]."""
+    """Views into the gathered (G, 2K+6) int64 buffer: (G, K) rc, (G, K) ids, (G, 4) headers.
+    Each rank's row is its `Pricer.block` = [K rc bits | K ids | n_violating, min key, n_priced, status | n_out, -]."""
     return gathered[:, :K].view(torch.float64), gathered[:, K:2 * K], gathered[:, 2 * K:2 * K + 4]
 
 
@@ -54,14 +56,16 @@ class ShardedDensePricer:
         self.y_dev = torch.empty(self.S + self.D, dtype=torch.float64, device=M_loc.device)
         self.h_y = torch.empty(self.S + self.D, dtype=torch.float64).pin_memory()
         Kp = max(self.K, 1)
-        self.gathered = torch.empty(self.world, 2 * Kp + 4, dtype=torch.int64, device=M_loc.device)
-        self.h_out = torch.empty(2 * Kp + 4, dtype=torch.int64).pin_memory()
-        self.d_out = torch.empty(2 * Kp + 4, dtype=torch.int64, device=M_loc.device)
+        self.blk = 2 * Kp + dev.Pricer.BLOCK_TAIL
+        self.gathered = torch.empty(self.world, self.blk, dtype=torch.int64, device=M_loc.device)
+        # merged result: [K rc | K ids | n_out | total count, min key, largest per-rank count, status]
+        self.h_out = torch.empty(2 * Kp + 6, dtype=torch.int64).pin_memory()
+        self.d_out = torch.zeros(2 * Kp + 6, dtype=torch.int64, device=M_loc.device)
         self._merge_ws = dev._ws(lib.sx_topk_merge_workspace_bytes(self.world), M_loc.device)
         self._m_rc = self.d_out[:Kp].view(torch.float64)
         self._m_id = self.d_out[Kp:2 * Kp]
         self._m_n = self.d_out[2 * Kp:2 * Kp + 1]
-        self._m_sum = self.d_out[2 * Kp + 1:2 * Kp + 4]
+        self._m_sum = self.d_out[2 * Kp + 1:2 * Kp + 5]
         # exchange of the result blocks: "p2p" = direct peer stores over NVLink into a symmetric buffer
         # (sx_exchange_blocks), "nccl" = all_gather_into_tensor.  p2p needs torch symmetric memory.
         self.exchange = exchange if self.world > 1 else "none"
@@ -76,7 +80,7 @@ class ShardedDensePricer:
 
     def _setup_p2p(self, Kp: int):
         import torch.distributed._symmetric_memory as symm
-        blk = 2 * Kp + 4
+        blk = self.blk
         n64 = lib.sx_exchange_buffer_bytes(blk, self.world) // 8
         self._symm = symm.empty(n64, dtype=torch.int64, device=self.M.device)
         self._symm.zero_()
@@ -93,10 +97,12 @@ class ShardedDensePricer:
         return self.pricer.launches + self._merge_launches
 
     # -- device-only step: everything stays on the GPU(s) --------------------------------------
-    def enqueue(self, y_dev: torch.Tensor, kernel_events=None):
+    def enqueue(self, y_dev: torch.Tensor, kernel_events=None, sorted_path: bool = False):
         """Enqueue one pricing pass; returns device tensors
-        (rc[K], id[K], n_out, count, min key, largest per-rank count).  `kernel_events` = (start, end)
-        CUDA events recorded around the pricing kernel launch (bench.py's roofline measurement)."""
+        (rc[K], id[K], n_out, count, min key, largest per-rank count, status).  A non-zero status
+        (SX_STATUS_*) means the pass must be repeated (`price` does that).  `kernel_events` =
+        (start, end) CUDA events recorded around the pricing kernel launch (bench.py's roofline
+        measurement)."""
         p = self.pricer
         p.reset()
         if kernel_events is not None:
@@ -106,14 +112,14 @@ class ShardedDensePricer:
                       self.tol, None, self.variant)
         if kernel_events is not None:
             kernel_events[1].record()
-        p.select()
+        p.select(sorted_path=sorted_path)
         Kp = max(self.K, 1)
         if self.world == 1:
-            return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0]
+            return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0], p.header[3]
         # one exchange: every rank's block (top-K + header) lands in `gathered`, consumed in place
         if self.exchange == "p2p":
             self._epoch += 1
-            blk = 2 * Kp + 4
+            blk = self.blk
             check(lib.sx_exchange_blocks(dev._ptr(p.block), blk, self._hdl.buffer_ptrs_dev, self._rank, self.world,
                                          self._epoch, dev._ptr(self._xstatus), dev._stream()), "sx_exchange_blocks")
             self._merge_launches += 1
@@ -126,8 +132,8 @@ class ShardedDensePricer:
         check(lib.sx_topk_merge(dev._ptr(rc), dev._ptr(ids), gathered.stride(0), self.world, Kp, dev._ptr(hdr),
                                 dev._ptr(self._m_rc), dev._ptr(self._m_id), dev._ptr(self._m_n), dev._ptr(self._m_sum),
                                 dev._ptr(self._merge_ws), self._merge_ws.numel(), dev._stream()), "sx_topk_merge")
-        self._merge_launches += 2
-        return self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2]
+        self._merge_launches += 1
+        return self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2], self._m_sum[3]
 
     # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
     def price(self, y_host: np.ndarray) -> dev.PriceResult:
@@ -135,13 +141,13 @@ class ShardedDensePricer:
         self.h_y.numpy()[:] = y_host
         self.y_dev.copy_(self.h_y, non_blocking=True)
         K = max(self.K, 1)
+        sorted_path = False
         while True:
-            self.enqueue(self.y_dev)
+            self.enqueue(self.y_dev, sorted_path=sorted_path)
             if self.world == 1:
-                res = self.pricer.fetch()                  # block + out_n, two small D2H copies, one sync
-                cmax = res.n_violating
+                res = self.pricer.fetch()                  # one D2H copy of the block, one sync
+                status, cmax = self.pricer.status, res.n_violating
             else:
-                # d_out = [rc | ids | n_out, total count, min key, largest per-rank count], written by the merge
                 self.h_out.copy_(self.d_out, non_blocking=True)
                 if self.exchange == "p2p":
                     self._h_xstatus.copy_(self._xstatus, non_blocking=True)
@@ -152,12 +158,15 @@ class ShardedDensePricer:
                 n_out = int(h[2 * K]) if self.K > 0 else 0
                 res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
                                       h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
-                cmax = int(h[2 * K + 3])
-            # If some rank saw more violators than its candidate buffer holds, every rank (they all
-            # read the same gathered counts) grows to that size and the pass is priced again.
-            if self.K == 0 or cmax <= self.pricer.cap:
+                cmax, status = int(h[2 * K + 3]), int(h[2 * K + 4])
+            # Every rank reads the same folded status, so all ranks repeat the pass together: with a larger
+            # candidate buffer after an overflow, with the sorted selection after SX_STATUS_NEED_SORTED.
+            if self.K == 0 or status == 0:
                 return res
-            self.pricer.grow(cmax)
+            if status & _native.SX_STATUS_CAND_OVERFLOW:
+                self.pricer.grow(cmax)
+            else:
+                sorted_path = True
 
     @property
     def h2d_bytes(self):
@@ -165,4 +174,4 @@ class ShardedDensePricer:
 
     @property
     def d2h_bytes(self):
-        return 8 * (2 * max(self.K, 1) + 4)
+        return 8 * (2 * max(self.K, 1) + 6)

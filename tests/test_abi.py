@@ -22,7 +22,8 @@ def _ensure_built():
 def test_header_declares_the_expected_entry_points():
     names = _declared()
     for must in ("sx_score_ot", "sx_score_mcf", "sx_argsort_f64", "sx_kruskal_order", "sx_kruskal",
-                 "sx_tree_potentials", "sx_price_dense_ot", "sx_price_arcs", "sx_topk_select",
+                 "sx_tree_potentials", "sx_price_pass_begin", "sx_price_dense_ot", "sx_price_arcs", "sx_topk_select",
+                 "sx_topk_select_sorted", "sx_exchange_blocks",
                  "sx_topk_merge", "sx_price_dense_ot_h"):
         assert must in names
     assert len(names) >= 24
@@ -34,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), f"{name} declared in sxcross.h but not exported"
     lib.sx_abi_version.restype = ctypes.c_int
-    assert lib.sx_abi_version() == 1
+    assert lib.sx_abi_version() == 2
     lib.sx_error_string.restype = ctypes.c_char_p
     assert b"spanning" in lib.sx_error_string(-5)
 
@@ -56,5 +57,7 @@ def test_workspace_queries_and_argument_validation_without_gpu():
     assert lib.sx_topk_workspace_bytes(1 << 20, 1024) > 0
     assert lib.sx_score_ot(None, None, None, 3, 3, None, None) == -1
     assert lib.sx_argsort_f64(None, 10, None, None, None, 0, None) == -1
-    assert lib.sx_price_dense_ot(None, 4, 0, 4, 4, None, None, 1e-6, None, None, None, 0, None, 0, -1, None) == -1
+    assert lib.sx_price_dense_ot(None, 4, 0, 4, 4, None, None, 1e-6, None, None, None, None, 0, None, 0, -1, None) == -1
+    assert lib.sx_select_state_bytes() >= 2 * 1024 * 1024
+    assert lib.sx_price_pass_begin(None, None, 16, None) == -1
     assert lib.sx_key_to_f64(0x7fffffffffffffff) != lib.sx_key_to_f64(0x7fffffffffffffff)  # NaN image of the reset value

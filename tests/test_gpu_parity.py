@@ -220,8 +220,64 @@ def test_price_tied_reduced_costs_and_overflow(dev):
         cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
         pr = dev.Pricer(torch.device("cuda"), K, cand_cap=100)
         res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
-        assert cnt > 100 and pr.cap >= cnt
+        assert cnt > 100 and pr.cap > 100                  # grew after SX_STATUS_CAND_OVERFLOW
         assert res.n_violating == cnt and np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+
+
+@pytest.mark.parametrize("frac,K", [(0.5, 64), (0.5, 1024), (0.9, 1), (0.02, 1024), (0.3, 4000)])
+def test_price_many_violators_are_pruned(dev, frac, K):
+    """A far-from-optimal y (10 % - 90 % of all arcs violate): the count stays exact, the candidate
+    list stays short (running histogram bound) and the top-K is still exact."""
+    S, D = 1500, 2048
+    rng = np.random.default_rng(int(frac * 100) + K)
+    M = rng.random((S, D))
+    y = np.concatenate([np.zeros(S), np.full(D, 1.0 - frac)])      # rc = M - (1 - frac): `frac` of the arcs < 0
+    y[:S] += rng.normal(0, 0.01, S)
+    rc_ref = orc.reduced_costs_ot(M, y)
+    cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
+    pr = dev.Pricer(torch.device("cuda"), K)
+    res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
+    assert res.n_violating == cnt and res.min_rc == mn and cnt > 0.9 * frac * S * D
+    assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+    n_cand = int(pr.sel[:8].view(torch.int64).item())
+    assert n_cand < min(cnt, 40 * max(K, 4096)), f"pruning kept {n_cand} of {cnt} violators"
+    assert pr.status == 0 and pr.cap == max(64 * K, 1 << 20)    # no overflow, no fallback
+
+
+def test_price_all_equal_reduced_costs_takes_the_sorted_path(dev):
+    """Every arc has the same reduced cost: no bound can prune, more than 8192 survivors tie at the
+    K-th value, SX_STATUS_NEED_SORTED routes the selection to the slice-sort path; ids win ties."""
+    S, D, K = 300, 200, 100
+    M = np.full((S, D), 2.0)
+    y = np.concatenate([np.zeros(S), np.full(D, 3.0)])            # rc = -1 everywhere
+    pr = dev.Pricer(torch.device("cuda"), K)
+    res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
+    assert res.n_violating == S * D and res.min_rc == -1.0
+    assert np.array_equal(res.topk_id, np.arange(K)) and np.all(res.topk_rc == -1.0)
+    # the fast path alone must have raised the flag (and nothing else)
+    pr.reset()
+    pr.price_dense(cu(M), D, 0, S, D, cu(y[:S]), cu(y[S:]))
+    pr.select()
+    torch.cuda.synchronize()
+    from smart_crossover._native import SX_STATUS_NEED_SORTED
+    assert int(pr.header[3].item()) == SX_STATUS_NEED_SORTED
+
+
+def test_price_bins_are_monotone_over_magnitudes(dev):
+    """Violations spread over 12 orders of magnitude, both signs of the exponent, with K landing
+    inside a dense cluster: exercises the two-level histogram scan."""
+    S, D = 512, 1024
+    rng = np.random.default_rng(11)
+    mag = 10.0 ** rng.uniform(-5.5, 6.5, size=(S, D))
+    M = np.where(rng.random((S, D)) < 0.2, -mag, mag)
+    M.ravel()[rng.choice(S * D, 3000, replace=False)] = -3.0e6        # a cluster of exact ties around rank 200..3200
+    y = np.zeros(S + D)
+    rc_ref = orc.reduced_costs_ot(M, y)
+    for K in (1, 37, 1024):
+        cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
+        res = dev.price_dense_ot(cu(M), cu(y), K=K)
+        assert res.n_violating == cnt and res.min_rc == mn
+        assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
 
 
 def test_price_row_slabs_and_merge(dev):

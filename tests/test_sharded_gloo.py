@@ -42,15 +42,15 @@ def _worker(rank, world, port, S, D, K, ret):
         rc = orc.reduced_costs_ot(M[row0:row0 + S_loc], np.concatenate([y[row0:row0 + S_loc], y[S:]]))
         cnt, mn, ids, vals = orc.price_summary(rc, K)
         ids = ids + row0 * D                                    # global arc ids
-        # the rank's block, laid out as device.Pricer.block: [K rc bits | K ids | header (4)]
-        block = torch.zeros(2 * K + 4, dtype=torch.int64)
+        # the rank's block, laid out as device.Pricer.block: [K rc bits | K ids | header (4) | n_out, pad]
+        block = torch.zeros(2 * K + 6, dtype=torch.int64)
         block[:K] = torch.full((K,), float("inf"), dtype=torch.float64).view(torch.int64)
         block[K:2 * K] = -1
         block[:ids.size] = torch.from_numpy(vals.copy()).view(torch.int64)
         block[K:K + ids.size] = torch.from_numpy(ids)
         block[2 * K] = cnt
         block[2 * K + 1] = int(np.float64(mn).view(np.int64))
-        gathered = torch.empty(world, 2 * K + 4, dtype=torch.int64)
+        gathered = torch.empty(world, 2 * K + 6, dtype=torch.int64)
         dist.all_gather_into_tensor(gathered.view(-1), block)
         g_rc, g_id, hdr = block_views(gathered, K)
         count, cmax = hdr[:, 0].sum(), hdr[:, 0].max()
