@@ -157,11 +157,14 @@ def make_slab(P, Q, row0, S_loc, out=None, block=1000):
 
 
 def planted_duals(P, Q, a, M_loc, row0, frac, world, sample_rows=1500):
-    """y = (a, b + delta): b_j = min_i (M_ij + a_i) makes every reduced cost >= 0 and tight once per
-    column; delta >= 0 is bisected so that about `frac` of the arcs end up with rc < -tol."""
+    """Planted duals plus noise: y0 = (a, b) with b_j = min_i (M_ij + a_i) makes
+    every reduced cost >= 0 and tight once per column; y = y0 + sigma * N(0, 1) on every node, with
+    sigma bisected on a row sample so that about `frac` of the arcs end up with rc < -tol.  The same
+    seeded noise on every rank."""
     import torch
     import torch.distributed as dist
     S_loc, D = M_loc.shape
+    S = P.shape[0]
     b = torch.full((D,), float("inf"), dtype=torch.float64, device=M_loc.device)
     for r in range(0, S_loc, 1000):
         e = min(S_loc, r + 1000)
@@ -170,14 +173,17 @@ def planted_duals(P, Q, a, M_loc, row0, frac, world, sample_rows=1500):
         dist.all_reduce(b, op=dist.ReduceOp.MIN)
     if frac <= 0:
         return torch.cat([a, b - 1e-3])
-    R = min(sample_rows, P.shape[0])
+    g = torch.Generator(device=M_loc.device).manual_seed(20260105)
+    noise = torch.randn(S + D, generator=g, device=M_loc.device, dtype=torch.float64)
+    R = min(sample_rows, S)
     rc0 = cost_rows(P, Q, 0, R) - (b[None, :] - a[:R, None])       # same rows on every rank
+    dn = noise[S:][None, :] - noise[:R, None]                      # rc = rc0 - sigma * dn
     lo, hi = 0.0, 1.0
     for _ in range(40):
         mid = 0.5 * (lo + hi)
-        f = float((rc0 < mid - TOL).sum().item()) / rc0.numel()
+        f = float((rc0 - mid * dn < -TOL).sum().item()) / rc0.numel()
         lo, hi = (mid, hi) if f < frac else (lo, mid)
-    return torch.cat([a, b + hi])
+    return torch.cat([a, b]) + hi * noise
 
 
 # ------------------------------------------------------------------------------------------------
@@ -505,7 +511,8 @@ def sweep(args, sp, y_dev, S_loc, D, lib, dev):
     """Pricing-kernel variants and tunings, kernel-only GB/s (CUDA events, 20 reps after 3 warm-ups)."""
     import torch
     res = []
-    shapes = ["16x6 8w", "16x6 16w", "32x3 8w", "32x3 16w", "16x7 16w", "8x12 16w", "16x3 8w x2cta", "8x6 8w x2cta"]
+    shapes = ["16x6 8w", "16x6 16w", "32x3 8w", "32x3 16w", "16x7 16w", "8x12 16w", "16x3 8w x2cta", "8x6 8w x2cta",
+              "24x4 16w", "20x5 16w", "12x9 16w", "12x4 8w x2cta", "8x7 8w x2cta", "8x4 8w x3cta"]
     confs = [(f"tma {nm}", 0, (i, 0)) for i, nm in enumerate(shapes)]
     confs += [("vec", 1, (-1, 4)), ("vec", 1, (-1, 8)), ("vec", 1, (-1, 16)), ("scalar", 2, (-1, 8)),
               ("scalar", 2, (-1, 16))]

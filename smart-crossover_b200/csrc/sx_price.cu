@@ -40,6 +40,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive that cannot be issued before `dep` is known.  A consumer releases a stage once its data
+// is in registers; "the loads were issued" is not enough (an LDS queued behind global atomics can
+// still be in flight when the arrive lets the producer's TMA overwrite the stage), so the release
+// carries a register dependency on a value computed from every loaded element.
+// `dep_times_zero` = dep * (a zero only known at run time): folded into the barrier address.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t *bar, uint32_t dep_times_zero) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + dep_times_zero) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -187,6 +195,7 @@ struct DenseParams {
     double       *rc_out;  // optional
     long long     ld_out;
     long long     n_col_blocks, n_row_tiles;
+    uint32_t      zero;    // 0, but only the host knows: see mbar_arrive_after
 };
 
 // Lazy epilogue of one warp's share of a tile: RPT rows x 2 columns per thread already in registers
@@ -295,9 +304,14 @@ price_dense_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DensePara
             double2 m[RPT];
 #pragma unroll
             for (int r = 0; r < RPT; ++r) m[r] = tile[(size_t)r * (kBoxCols / 2)];
-            // all shared reads of this stage are in registers: release the slot
-            __syncwarp();
-            if (lane_id() == 0) mbar_arrive(&empty_bar[s]);
+            // Release the slot once the data has ARRIVED in registers: the vote below cannot issue before
+            // every lane's shared loads have completed (it consumes one word of each), and the arrive's
+            // address depends on the vote.
+            uint32_t landed = 0;
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) landed ^= (uint32_t)__double2loint(m[r].x);
+            const bool rel = __any_sync(0xffffffffu, landed == 0x5a5a5a5au);
+            if (lane_id() == 0) mbar_arrive_after(&empty_bar[s], (uint32_t)rel * p.zero);
 
             double rc0[RPT], rc1[RPT];
             bool   hit = false;
@@ -540,7 +554,8 @@ static EncodeTiledFn get_encode_fn() {
 struct TmaShape { int rows, stages, cwarps, ctas_per_sm; };
 static const TmaShape kTmaShapes[] = {
     {16, 6, 8, 1}, {16, 6, 16, 1}, {32, 3, 8, 1}, {32, 3, 16, 1}, {16, 7, 16, 1}, {8, 12, 16, 1},
-    {16, 3, 8, 2}, {8, 6, 8, 2},
+    {16, 3, 8, 2}, {8, 6, 8, 2}, {24, 4, 16, 1}, {20, 5, 16, 1}, {12, 9, 16, 1},
+    {12, 4, 8, 2}, {8, 7, 8, 2}, {8, 4, 8, 3},
 };
 constexpr int kNumTmaShapes = sizeof(kTmaShapes) / sizeof(kTmaShapes[0]);
 static int g_tma_shape = 3, g_ctas_per_sm_direct = 16;
@@ -570,6 +585,12 @@ static int dispatch_tma(int shape, const CUtensorMap &map, const DenseParams &p,
         case 5: return launch_tma<8, 12, 16, 1, WRITE_RC>(map, p, st);
         case 6: return launch_tma<16, 3, 8, 2, WRITE_RC>(map, p, st);
         case 7: return launch_tma<8, 6, 8, 2, WRITE_RC>(map, p, st);
+        case 8: return launch_tma<24, 4, 16, 1, WRITE_RC>(map, p, st);
+        case 9: return launch_tma<20, 5, 16, 1, WRITE_RC>(map, p, st);
+        case 10: return launch_tma<12, 9, 16, 1, WRITE_RC>(map, p, st);
+        case 11: return launch_tma<12, 4, 8, 2, WRITE_RC>(map, p, st);
+        case 12: return launch_tma<8, 7, 8, 2, WRITE_RC>(map, p, st);
+        case 13: return launch_tma<8, 4, 8, 3, WRITE_RC>(map, p, st);
         default: return launch_tma<32, 3, 16, 1, WRITE_RC>(map, p, st);
     }
 }
@@ -615,7 +636,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
     p.y_src = y_src; p.y_dst = y_dst; p.S_loc = S_loc; p.D = D; p.row0 = row0; p.thr = -tol;
     p.sink.hdr = header; p.sink.sel = (SelState *)sel; p.sink.rc = cand_rc; p.sink.id = (int64_t *)cand_id;
     p.sink.cap = cand_cap;
-    p.rc_out = rc_out; p.ld_out = ld_out;
+    p.rc_out = rc_out; p.ld_out = ld_out; p.zero = 0;
     p.n_col_blocks = (D + kBoxCols - 1) / kBoxCols;
 
     int rc = SX_OK;

@@ -21,17 +21,27 @@ constexpr unsigned kTopBins       = kFineBins / 256;          // 2 048 coarse bi
 constexpr unsigned kTightenPeriod = 4096;                     // candidates between two tightenings
 constexpr int      kSurvCap       = 8192;                     // survivors the all-pairs rank handles
 
+constexpr int kMaxLevels = 16;                                // radix refinement levels of the selection
+constexpr int kRefBins   = 2048;                              // 11-bit digits
+
 struct SelState {
     unsigned long long n_cand;       // candidates appended so far (can exceed the buffer capacity)
     unsigned int       bstar;        // only violators with bin <= bstar are appended
     unsigned int       K;            // selection size this pass prunes for
-    unsigned int       n_surv;       // survivors of the final filter
-    unsigned int       done;         // CTA completion counter of the rank kernel
-    unsigned int       pad[10];
+    // ---- scratch of the selection kernel (sx_topk.cu), zero at the start of a pass ----
+    unsigned int       n_sure;       // elements known to be among the K best
+    unsigned int       pad0[3];
+    unsigned int       n_list[kMaxLevels + 4];                // boundary-list length per level
+    unsigned long long inv_kmin[kMaxLevels + 2];              // ~min key of the level's boundary list
+    unsigned long long kmax[kMaxLevels + 2];
+    unsigned long long inv_imin[kMaxLevels + 2];              // ~min id
+    unsigned long long imax[kMaxLevels + 2];
+    unsigned int       hist2[kMaxLevels][kRefBins];
+    // ---- histogram of the appended reduced costs (sx_price.cu) ----
     unsigned int       top[kTopBins];
     unsigned int       fine[kFineBins];
 };
-static_assert(sizeof(SelState) == 64 + 4 * (kTopBins + kFineBins), "SelState layout");
+static_assert(sizeof(SelState) % 16 == 0, "SelState is cleared with 16-byte stores");
 
 // bits of sx_price_header.status
 constexpr unsigned long long kStatusCandOverflow = 1ull;   // candidate buffer too small: grow and price again
@@ -57,26 +67,45 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const unsigned *p) {
     return v;
 }
 
+// Position of rank `need` in N per-lane counts v[] whose warp-wide inclusive scan crosses `need` in
+// this lane: q = first index with before + v[0..q] >= need, before is advanced to the sum below q.
+// Static indexing only (v stays in registers).
+template <int N>
+__device__ __forceinline__ int find_in_lane(const unsigned (&v)[N], unsigned need, unsigned &before) {
+    int q = -1;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        if (q < 0) {
+            if (before + v[r] >= need) q = r; else before += v[r];
+        }
+    }
+    return q < 0 ? N - 1 : q;
+}
+
 // Executed by one full warp.  Returns (to every lane) the smallest fine bin b with
-// cum(<= b) >= need, or kFineBins - 1 if the histogram holds fewer than `need` entries.
-// `top` may lag behind `fine` (fine is incremented first, then a fence, then top), never the
-// other way round, so the returned bound is valid for the true counts.
+// cum(<= b) >= need, or kFineBins - 1 if the histogram holds fewer than `need` entries;
+// *below_out = number of entries in bins < b.  One snapshot of each level is read (all loads in
+// flight together).  `top` may lag behind `fine` (fine is incremented first, then a fence, then
+// top), never the other way round, so a bound derived from `top` is valid for the true counts.
 static __device__ __noinline__ unsigned warp_find_bound(const SelState *st, unsigned need, unsigned *below_out) {
     const unsigned lane = threadIdx.x & 31u;
     // level 1: 2048 coarse bins, 64 per lane
     constexpr int kPerLane = kTopBins / 32;
-    unsigned local = 0;
+    unsigned t[kPerLane];
     const unsigned *tp = st->top + lane * kPerLane;
-#pragma unroll 4
+#pragma unroll
     for (int q = 0; q < kPerLane; q += 4) {
         const uint4 v = ld_relaxed_v4(tp + q);
-        local += v.x + v.y + v.z + v.w;
+        t[q] = v.x; t[q + 1] = v.y; t[q + 2] = v.z; t[q + 3] = v.w;
     }
+    unsigned local = 0;
+#pragma unroll
+    for (int q = 0; q < kPerLane; ++q) local += t[q];
     unsigned incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
     }
     const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
     if (total < need) {
@@ -87,16 +116,8 @@ static __device__ __noinline__ unsigned warp_find_bound(const SelState *st, unsi
     const int      owner = __ffs(cross) - 1;
     unsigned c_star = 0, below = 0;
     if ((int)lane == owner) {
-        unsigned cum = incl - local;
-        int q = 0;
-        for (; q < kPerLane; ++q) {
-            const unsigned v = ld_relaxed_u32(tp + q);
-            if (cum + v >= need) break;
-            cum += v;
-        }
-        if (q == kPerLane) q = kPerLane - 1;   // counts grew between the two reads: stay in range
-        c_star = lane * kPerLane + q;
-        below = cum;
+        below = incl - local;
+        c_star = lane * kPerLane + find_in_lane(t, need, below);
     }
     c_star = __shfl_sync(0xffffffffu, c_star, owner);
     below  = __shfl_sync(0xffffffffu, below, owner);
@@ -110,8 +131,8 @@ static __device__ __noinline__ unsigned warp_find_bound(const SelState *st, unsi
     unsigned incl2 = l2;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl2, o);
-        if (lane >= o) incl2 += t;
+        const unsigned u = __shfl_up_sync(0xffffffffu, incl2, o);
+        if (lane >= o) incl2 += u;
     }
     const unsigned cross2 = __ballot_sync(0xffffffffu, below + incl2 >= need);
     if (cross2 == 0) {                        // cannot happen (fine >= top); no bound rather than a wrong one
@@ -121,15 +142,8 @@ static __device__ __noinline__ unsigned warp_find_bound(const SelState *st, unsi
     const int owner2 = __ffs(cross2) - 1;
     unsigned b_star = 0, below2 = 0;
     if ((int)lane == owner2) {
-        unsigned cum = below + incl2 - l2;
-        int q = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            if (q == r && cum + f[r] < need) { cum += f[r]; ++q; }
-        }
-        if (q > 7) q = 7;
-        b_star = c_star * 256 + lane * 8 + q;
-        below2 = cum;
+        below2 = below + incl2 - l2;
+        b_star = c_star * 256 + lane * 8 + find_in_lane(f, need, below2);
     }
     b_star = __shfl_sync(0xffffffffu, b_star, owner2);
     below2 = __shfl_sync(0xffffffffu, below2, owner2);

@@ -25,8 +25,12 @@
 // K > 1024: two stable radix argsorts (by id, then by rc) over the candidates.
 #include <math.h>
 
+#include <cooperative_groups.h>
+
 #include "sx_common.cuh"
 #include "sx_select.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sx {
 
@@ -320,48 +324,19 @@ topk_rank_kernel(const double *__restrict__ lists_rc, const long long *__restric
 // ---- fast path ----------------------------------------------------------------------------
 constexpr int kApThreads = 256;
 constexpr int kApTile    = 2048;
+constexpr int kRankCap   = 4096;   // refine until sure + boundary fit this; the rank itself takes up to kSurvCap
 
 struct KeyId {
     unsigned long long key;   // f64_to_sort_key(rc); ~0 for padding
     long long          id;    // arc id; INT64_MAX for padding
 };
+// L2 load (lists are rewritten by other SMs between grid-wide barriers of one kernel)
+__device__ __forceinline__ KeyId ld_keyid(const KeyId *p) {
+    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
+    return KeyId{v.x, (long long)v.y};
+}
 __device__ __forceinline__ bool keyid_less(const KeyId &a, const KeyId &b) {
     return a.key < b.key || (a.key == b.key && a.id < b.id);
-}
-
-// Survivors of the final bound: candidates whose bin is <= b*.
-__global__ void __launch_bounds__(256)
-sel_filter_kernel(const double *__restrict__ cand_rc, const long long *__restrict__ cand_id, long long cand_cap,
-                  SelState *st, sx_price_header *hdr, unsigned K, double *__restrict__ surv_rc,
-                  long long *__restrict__ surv_id) {
-    __shared__ unsigned s_b;
-    const unsigned long long n64 = st->n_cand;
-    long long n = (long long)n64;
-    if (n64 > (unsigned long long)cand_cap) {
-        n = cand_cap;
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&hdr->status, kStatusCandOverflow);
-    }
-    if (threadIdx.x < 32) {
-        const unsigned b = warp_find_bound(st, K, nullptr);
-        if (threadIdx.x == 0) s_b = b;
-    }
-    __syncthreads();
-    const unsigned b = s_b;
-    const unsigned lt = (1u << lane_id()) - 1u;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long n_ceil = (n + 31) / 32 * 32;               // whole warps stay in the loop (ballots)
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_ceil; i += stride) {
-        double rc = 0.0;
-        bool keep = false;
-        if (i < n) { rc = cand_rc[i]; keep = cand_bin(rc) <= b; }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m == 0) continue;
-        unsigned base = 0;
-        if (lane_id() == 0) base = atomicAdd(&st->n_surv, (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned slot = base + __popc(m & lt);
-        if (keep && slot < (unsigned)kSurvCap) { surv_rc[slot] = rc; surv_id[slot] = cand_id[i]; }
-    }
 }
 
 // All-pairs rank of n elements given by load(e) (padding sorts last).  Every thread of the grid
@@ -395,26 +370,218 @@ __device__ __forceinline__ void all_pairs_rank(int n, LoadFn load, EmitFn emit) 
     if (valid && sub == 0) emit(e, cnt);
 }
 
+template <class T> __device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+// One partition step of the selection, executed by the whole grid: every element e of this CTA's
+// strided share is classified by cls(e) -> 0 (sure), 1 (new boundary list) or 2 (dropped) and
+// moved to the end of `sure` / into `bnd`.  Counts are aggregated per CTA (one atomicAdd per list
+// and CTA, one set of range atomics per CTA): the classification runs twice, first to count, then
+// to scatter.  Also tracks the (key, id) range of the new boundary list for the next level.
+template <class LoadFn, class ClsFn>
+__device__ __forceinline__ void partition_step(long long n, LoadFn load, ClsFn cls, KeyId *sure, unsigned *n_sure,
+                                               KeyId *bnd, unsigned *n_bnd, long long bnd_cap, SelState *st,
+                                               int next_level, unsigned *s_scan /* 2 * 8 + 2 words */,
+                                               unsigned long long *s_range /* 8 * 4 */) {
+    const long long gtid = (long long)blockIdx.x * kApThreads + threadIdx.x;
+    const long long gsz = (long long)gridDim.x * kApThreads;
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    unsigned c0 = 0, c1 = 0;
+    unsigned long long a = 0, b = 0, c = 0, d = 0;      // ~min key, max key, ~min id, max id
+    for (long long i = gtid; i < n; i += gsz) {
+        const KeyId v = load(i);
+        const int k = cls(v);
+        c0 += k == 0;
+        if (k == 1) {
+            ++c1;
+            const unsigned long long id = (unsigned long long)v.id;
+            a = ~v.key > a ? ~v.key : a; b = v.key > b ? v.key : b;
+            c = ~id > c ? ~id : c;       d = id > d ? id : d;
+        }
+    }
+    // block-exclusive scan of (c0, c1)
+    unsigned i0 = c0, i1 = c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += t0; i1 += t1; }
+    }
+    a = warp_max(a); b = warp_max(b); c = warp_max(c); d = warp_max(d);
+    __syncthreads();
+    if (lane == 31) { s_scan[warp] = i0; s_scan[8 + warp] = i1; }
+    if (lane == 0) { s_range[warp * 4] = a; s_range[warp * 4 + 1] = b; s_range[warp * 4 + 2] = c; s_range[warp * 4 + 3] = d; }
+    __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < 36) {        // one range atomic per CTA and quantity
+        const int q = threadIdx.x - 32;
+        unsigned long long m = 0;
+        for (int w = 0; w < kApThreads / 32; ++w) m = s_range[w * 4 + q] > m ? s_range[w * 4 + q] : m;
+        unsigned long long *dst = q == 0 ? st->inv_kmin : (q == 1 ? st->kmax : (q == 2 ? st->inv_imin : st->imax));
+        if (m) atomicMax(&dst[next_level], m);
+    }
+    if (threadIdx.x == 0) {
+        unsigned t0 = 0, t1 = 0;
+        for (int w = 0; w < kApThreads / 32; ++w) {
+            const unsigned x0 = s_scan[w], x1 = s_scan[8 + w];
+            s_scan[w] = t0; s_scan[8 + w] = t1;
+            t0 += x0; t1 += x1;
+        }
+        s_scan[16] = t0 ? atomicAdd(n_sure, t0) : 0u;
+        s_scan[17] = t1 ? atomicAdd(n_bnd, t1) : 0u;
+    }
+    __syncthreads();
+    unsigned p0 = s_scan[16] + s_scan[warp] + i0 - c0;
+    unsigned p1 = s_scan[17] + s_scan[8 + warp] + i1 - c1;
+    for (long long i = gtid; i < n; i += gsz) {
+        const KeyId v = load(i);
+        const int k = cls(v);
+        if (k == 0) { if (p0 < (unsigned)kSurvCap) sure[p0] = v; ++p0; }
+        else if (k == 1) { if ((long long)p1 < bnd_cap) bnd[p1] = v; ++p1; }
+    }
+}
+
+// The whole selection in ONE cooperative launch (K <= 1024):
+//   level 0   candidates are split by the pricing histogram's final bound b*: bin < b* are "sure"
+//             (there are fewer than K of them), bin == b* form the boundary list, the rest is dropped;
+//   refine    while sure + boundary > kSurvCap: an 11-bit digit of (key, id) taken at the highest bit
+//             in which the boundary list's minimum and maximum differ is histogrammed, the digit d*
+//             that holds the remaining rank is found, digits < d* become sure, == d* the new boundary
+//             list.  Near-ties resolve in one level, exact ties fall through to the id;
+//   rank      all-pairs rank of sure + boundary (<= 8192 elements) gives every output position.
 __global__ void __launch_bounds__(kApThreads)
-sel_rank_kernel(const SelState *st, sx_price_header *hdr, const double *__restrict__ surv_rc,
-                const long long *__restrict__ surv_id, int K, double *__restrict__ out_rc,
-                long long *__restrict__ out_id, long long *out_n) {
-    const unsigned n_raw = st->n_surv;
-    const bool too_many = n_raw > (unsigned)kSurvCap;
-    const int n = too_many ? 0 : (int)n_raw;
-    const int n_out = n < K ? n : K;
+topk_select_kernel(const double *__restrict__ cand_rc, const long long *__restrict__ cand_id, long long cand_cap,
+                   SelState *st, sx_price_header *hdr, int K, KeyId *sure, KeyId *listA, KeyId *listB,
+                   double *__restrict__ out_rc, long long *__restrict__ out_id, long long *out_n) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned s_hist[kRefBins];
+    __shared__ unsigned s_b[2];
+    __shared__ unsigned s_scan[18];
+    __shared__ unsigned long long s_range[32];
+    const unsigned long long n64 = st->n_cand;
+    long long n = (long long)n64;
+    if (n64 > (unsigned long long)cand_cap) {
+        n = cand_cap;
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&hdr->status, kStatusCandOverflow);
+    }
+    const long long gtid = (long long)blockIdx.x * kApThreads + threadIdx.x;
+    const long long gsz = (long long)gridDim.x * kApThreads;
+
+    // ---- level 0: split by the pricing histogram ----
+    if (threadIdx.x < 32) {
+        unsigned below = 0;
+        const unsigned b = warp_find_bound(st, (unsigned)K, &below);
+        if (threadIdx.x == 0) { s_b[0] = b; s_b[1] = below; }
+    }
+    __syncthreads();
+    const unsigned b1 = s_b[0];
+    long long need = (long long)K - (long long)s_b[1];          // rank still to find inside the boundary list
+    partition_step(
+        n, [&](long long i) { return KeyId{f64_to_sort_key(cand_rc[i]), cand_id[i]}; },
+        [&](const KeyId &v) {
+            const unsigned long long kb = v.key >> (64 - 1 - kFineBits);                 // = cand_bin(rc)
+            const unsigned bin = kb < (unsigned long long)kFineBins ? (unsigned)kb : kFineBins - 1u;
+            return bin < b1 ? 0 : (bin == b1 ? 1 : 2);
+        },
+        sure, &st->n_sure, listA, &st->n_list[0], cand_cap, st, 0, s_scan, s_range);
+    grid.sync();
+
+    // ---- refinement levels ----
+    int level = 0;
+    bool failed = false;
+    for (;; ++level) {
+        const unsigned n_sure = ld_relaxed_u32(&st->n_sure), n_a = ld_relaxed_u32(&st->n_list[level]);
+        if (n_sure + n_a <= (unsigned)kRankCap) break;
+        if (level == kMaxLevels) { failed = n_sure + n_a > (unsigned)kSurvCap; break; }
+        const unsigned long long kmin = ~__ldcg(&st->inv_kmin[level]), kmax = __ldcg(&st->kmax[level]);
+        const unsigned long long imin = ~__ldcg(&st->inv_imin[level]), imax = __ldcg(&st->imax[level]);
+        const bool by_key = kmin != kmax;
+        const unsigned long long diff = by_key ? (kmin ^ kmax) : (imin ^ imax);
+        if (diff == 0) { failed = n_sure + n_a > (unsigned)kSurvCap; break; }   // duplicates of one (key, id)
+        const int p = 63 - __clzll((long long)diff);
+        const int sh = p > 10 ? p - 10 : 0;
+        auto digit = [&](const KeyId &v) {
+            return (unsigned)(((by_key ? v.key : (unsigned long long)v.id) >> sh) & (kRefBins - 1));
+        };
+        for (int i = threadIdx.x; i < kRefBins; i += kApThreads) s_hist[i] = 0;
+        __syncthreads();
+        {   // digit histogram; lanes holding the same digit add once (near-ties share one digit)
+            const long long na_ceil = ((long long)n_a + 31) / 32 * 32;
+            for (long long i = gtid; i < na_ceil; i += gsz) {
+                const unsigned dg = i < n_a ? digit(ld_keyid(listA + i)) : 0xffffffffu;
+                const unsigned peers = __match_any_sync(0xffffffffu, dg);
+                if (dg != 0xffffffffu && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&s_hist[dg], (unsigned)__popc(peers));
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kRefBins; i += kApThreads)
+            if (s_hist[i]) atomicAdd(&st->hist2[level][i], s_hist[i]);
+        grid.sync();
+        // digit holding rank `need`: 2048 bins, 64 per lane of warp 0
+        if (threadIdx.x < 32) {
+            const unsigned *h = st->hist2[level] + threadIdx.x * 64;
+            unsigned hv[64];
+#pragma unroll
+            for (int q = 0; q < 64; q += 4) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(h + q));
+                hv[q] = v.x; hv[q + 1] = v.y; hv[q + 2] = v.z; hv[q + 3] = v.w;
+            }
+            unsigned local = 0;
+#pragma unroll
+            for (int q = 0; q < 64; ++q) local += hv[q];
+            unsigned incl = local;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (threadIdx.x >= o) incl += t;
+            }
+            const unsigned cross = __ballot_sync(0xffffffffu, (long long)incl >= need);
+            const int owner = cross ? __ffs(cross) - 1 : 31;
+            if ((int)threadIdx.x == owner) {
+                unsigned cum = incl - local;
+                const int q = find_in_lane(hv, (unsigned)need, cum);
+                s_b[0] = threadIdx.x * 64 + q;
+                s_b[1] = cum;
+            }
+        }
+        __syncthreads();
+        const unsigned dstar = s_b[0];
+        need -= (long long)s_b[1];
+        partition_step(
+            (long long)n_a, [&](long long i) { return ld_keyid(listA + i); },
+            [&](const KeyId &v) {
+                const unsigned dg = digit(v);
+                return dg < dstar ? 0 : (dg == dstar ? 1 : 2);
+            },
+            sure, &st->n_sure, listB, &st->n_list[level + 1], cand_cap, st, level + 1, s_scan, s_range);
+        grid.sync();
+        KeyId *t = listA; listA = listB; listB = t;
+    }
+
+    // ---- all-pairs rank of sure ++ boundary ----
+    const int n_sure = failed ? 0 : (int)ld_relaxed_u32(&st->n_sure);
+    const int n_s = failed ? 0 : n_sure + (int)ld_relaxed_u32(&st->n_list[level]);
+    const int n_out = n_s < K ? n_s : K;
     if (blockIdx.x == 0) {
         for (int i = n_out + threadIdx.x; i < K; i += kApThreads) { out_rc[i] = INFINITY; out_id[i] = -1; }
         if (threadIdx.x == 0) {
             *out_n = n_out;
-            if (too_many) atomicOr(&hdr->status, kStatusNeedSlowPath);
+            if (failed) atomicOr(&hdr->status, kStatusNeedSlowPath);
         }
     }
-    if (n == 0) return;
+    if (n_s == 0) return;
     all_pairs_rank(
-        n, [&](int e) { return KeyId{f64_to_sort_key(surv_rc[e]), surv_id[e]}; },
+        n_s, [&](int e) { return ld_keyid(e < n_sure ? sure + e : listA + (e - n_sure)); },
         [&](int e, int rank) {
-            if (rank < K) { out_rc[rank] = surv_rc[e]; out_id[rank] = surv_id[e]; }
+            if (rank < K) {
+                const KeyId v = ld_keyid(e < n_sure ? sure + e : listA + (e - n_sure));
+                out_rc[rank] = sort_key_to_f64(v.key);
+                out_id[rank] = v.id;
+            }
         });
 }
 
@@ -496,7 +663,7 @@ using namespace sx;
 
 extern "C" size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K) {
     if (cand_cap < 0 || K < 0) return 0;
-    const size_t fast = 2 * carve_bytes((size_t)kSurvCap, 8);
+    const size_t fast = carve_bytes((size_t)kSurvCap, 16) + 2 * carve_bytes((size_t)(cand_cap > 0 ? cand_cap : 1), 16);
     if (K <= SX_TOPK_MAX_K) {
         const size_t L = ((size_t)cand_cap + kTkSlice - 1) / kTkSlice + 1;
         return fast + carve_bytes(L * (size_t)(K > 0 ? K : 1), 8) * 2 + 2 * carve_bytes(L + 2, 4) + 256;
@@ -523,8 +690,9 @@ extern "C" int sx_topk_select_sorted(const double *cand_rc, const int64_t *cand_
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long *n_cand_dev = &((const SelState *)sel)->n_cand;
     Carver cv(ws);
-    cv.take<double>(kSurvCap);
-    cv.take<long long>(kSurvCap);
+    cv.take<KeyId>(kSurvCap);
+    cv.take<KeyId>(cand_cap > 0 ? cand_cap : 1);
+    cv.take<KeyId>(cand_cap > 0 ? cand_cap : 1);
     if (K <= SX_TOPK_MAX_K) {
         const int L = (int)((cand_cap + kTkSlice - 1) / kTkSlice);
         if (L == 0) {
@@ -582,17 +750,16 @@ extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id, int
     if (arg != SX_OK) return arg;
     cudaStream_t st = (cudaStream_t)stream;
     Carver cv(ws);
-    double *surv_rc = cv.take<double>(kSurvCap);
-    long long *surv_id = cv.take<long long>(kSurvCap);
-    long long grid = (cand_cap + 256 * 8 - 1) / (256 * 8);
-    if (grid > kNumSMs * 2) grid = kNumSMs * 2;
-    if (grid < 1) grid = 1;
-    sel_filter_kernel<<<(int)grid, 256, 0, st>>>(cand_rc, (const long long *)cand_id, cand_cap, (SelState *)sel, header,
-                                                 (unsigned)K, surv_rc, surv_id);
-    SX_LAUNCH_CHECK();
-    sel_rank_kernel<<<kNumSMs, kApThreads, 0, st>>>((const SelState *)sel, header, surv_rc, surv_id, (int)K, out_rc,
-                                                    (long long *)out_id, (long long *)out_n);
-    SX_LAUNCH_CHECK();
+    KeyId *sure = cv.take<KeyId>(kSurvCap);
+    KeyId *listA = cv.take<KeyId>(cand_cap > 0 ? cand_cap : 1);
+    KeyId *listB = cv.take<KeyId>(cand_cap > 0 ? cand_cap : 1);
+    const long long *cid = (const long long *)cand_id;
+    SelState *sst = (SelState *)sel;
+    int Ki = (int)K;
+    long long *oid = (long long *)out_id, *on = (long long *)out_n;
+    void *args[] = {(void *)&cand_rc, (void *)&cid, (void *)&cand_cap, (void *)&sst, (void *)&header, (void *)&Ki,
+                    (void *)&sure, (void *)&listA, (void *)&listB, (void *)&out_rc, (void *)&oid, (void *)&on};
+    SX_CUDA(cudaLaunchCooperativeKernel((void *)topk_select_kernel, dim3(kNumSMs), dim3(kApThreads), args, 0, st));
     return SX_OK;
 }
 

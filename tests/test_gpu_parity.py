@@ -228,10 +228,10 @@ def test_price_tied_reduced_costs_and_overflow(dev):
 def test_price_many_violators_are_pruned(dev, frac, K):
     """A far-from-optimal y (10 % - 90 % of all arcs violate): the count stays exact, the candidate
     list stays short (running histogram bound) and the top-K is still exact."""
-    S, D = 1500, 2048
+    S, D = 6000, 4096
     rng = np.random.default_rng(int(frac * 100) + K)
     M = rng.random((S, D))
-    y = np.concatenate([np.zeros(S), np.full(D, 1.0 - frac)])      # rc = M - (1 - frac): `frac` of the arcs < 0
+    y = np.concatenate([np.zeros(S), np.full(D, frac)])            # rc = M - frac: `frac` of the arcs < 0
     y[:S] += rng.normal(0, 0.01, S)
     rc_ref = orc.reduced_costs_ot(M, y)
     cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
@@ -240,13 +240,13 @@ def test_price_many_violators_are_pruned(dev, frac, K):
     assert res.n_violating == cnt and res.min_rc == mn and cnt > 0.9 * frac * S * D
     assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
     n_cand = int(pr.sel[:8].view(torch.int64).item())
-    assert n_cand < min(cnt, 40 * max(K, 4096)), f"pruning kept {n_cand} of {cnt} violators"
-    assert pr.status == 0 and pr.cap == max(64 * K, 1 << 20)    # no overflow, no fallback
+    assert n_cand < cnt // 4, f"pruning kept {n_cand} of {cnt} violators"
+    assert pr.status == 0
 
 
-def test_price_all_equal_reduced_costs_takes_the_sorted_path(dev):
-    """Every arc has the same reduced cost: no bound can prune, more than 8192 survivors tie at the
-    K-th value, SX_STATUS_NEED_SORTED routes the selection to the slice-sort path; ids win ties."""
+def test_price_all_equal_reduced_costs(dev):
+    """Every arc has the same reduced cost: no bound can prune and 60 000 candidates tie at the K-th
+    value; the selection refines on the arc id (ids win ties).  The sorted path gives the same."""
     S, D, K = 300, 200, 100
     M = np.full((S, D), 2.0)
     y = np.concatenate([np.zeros(S), np.full(D, 3.0)])            # rc = -1 everywhere
@@ -254,13 +254,30 @@ def test_price_all_equal_reduced_costs_takes_the_sorted_path(dev):
     res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
     assert res.n_violating == S * D and res.min_rc == -1.0
     assert np.array_equal(res.topk_id, np.arange(K)) and np.all(res.topk_rc == -1.0)
-    # the fast path alone must have raised the flag (and nothing else)
+    assert pr.status == 0
     pr.reset()
     pr.price_dense(cu(M), D, 0, S, D, cu(y[:S]), cu(y[S:]))
-    pr.select()
-    torch.cuda.synchronize()
-    from smart_crossover._native import SX_STATUS_NEED_SORTED
-    assert int(pr.header[3].item()) == SX_STATUS_NEED_SORTED
+    pr.select(sorted_path=True)
+    alt = pr.fetch()
+    assert np.array_equal(alt.topk_id, np.arange(K)) and alt.n_violating == S * D
+
+
+def test_price_near_ties_at_the_kth_value(dev):
+    """One tight arc per column shifted by the same delta (bench.py's planted duals): D reduced costs
+    that differ only in their last bits sit at the top, far more than 8192 of them."""
+    S, D, K = 700, 20000, 1024
+    rng = np.random.default_rng(3)
+    M = rng.random((S, D)) + 0.5
+    a = rng.random(S)
+    b = (M + a[:, None]).min(axis=0)
+    y = np.concatenate([a, b + 0.01])
+    rc_ref = orc.reduced_costs_ot(M, y)
+    cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
+    assert cnt >= D
+    pr = dev.Pricer(torch.device("cuda"), K)
+    res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
+    assert pr.status == 0 and res.n_violating == cnt and res.min_rc == mn
+    assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
 
 
 def test_price_bins_are_monotone_over_magnitudes(dev):
@@ -278,6 +295,36 @@ def test_price_bins_are_monotone_over_magnitudes(dev):
         res = dev.price_dense_ot(cu(M), cu(y), K=K)
         assert res.n_violating == cnt and res.min_rc == mn
         assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+
+
+def test_price_tma_stage_release_under_atomic_pressure(dev):
+    """Every arc violates and all reduced costs fall into one histogram bin, so nothing is pruned and
+    every warp-tile appends ~500 candidates (global atomics + stores saturate the load/store queue).
+    The TMA pipeline must still hand out intact tiles: a stage may only be released once its data has
+    ARRIVED in registers (regression: releasing after the shared loads were merely issued let the
+    producer overwrite tiles still being read)."""
+    S, D, K = 2000, 4096, 1024
+    rng = np.random.default_rng(21)
+    M = 1.0 + 1e-6 * rng.random((S, D))
+    y = np.concatenate([np.zeros(S), np.full(D, 2.0)])              # rc in [-1, -1 + 1e-6]
+    rc_ref = orc.reduced_costs_ot(M, y)
+    cnt, mn, ids, vals = orc.price_summary(rc_ref, K=K)
+    assert cnt == S * D
+    pr = dev.Pricer(torch.device("cuda"), K, cand_cap=S * D)
+    for _ in range(3):
+        rc = torch.empty(S * D, dtype=torch.float64, device="cuda")
+        pr.reset()
+        pr.price_dense(cu(M), D, 0, S, D, cu(y[:S]), cu(y[S:]), rc_out=rc, variant=0)
+        pr.select()
+        res = pr.fetch()
+        assert rc.cpu().numpy().tobytes() == rc_ref.tobytes()
+        assert res.n_violating == cnt and res.min_rc == mn
+        assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+        pr.reset()
+        pr.price_dense(cu(M), D, 0, S, D, cu(y[:S]), cu(y[S:]), variant=0)      # same without the rc output
+        pr.select()
+        res = pr.fetch()
+        assert res.n_violating == cnt and np.array_equal(res.topk_id, ids)
 
 
 def test_price_row_slabs_and_merge(dev):
