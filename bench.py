@@ -447,6 +447,7 @@ def main():
         del h_M
 
     exchange_mode = sp.exchange
+    e2e_h2d, e2e_d2h, e2e_graph = sp.h2d_bytes, sp.d2h_bytes, sp._graph is not None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -493,18 +494,16 @@ def main():
                        "rows_per_gpu": S_loc, "variant": args.variant, "exchange": exchange_mode,
                        "l2": f"inputs larger than L2 ({8 * S_loc * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sp_h2d(S, D),
-                    "d2h_bytes_per_step": 8 * (2 * max(K, 1) + 5), "ms_per_step": e2e_ms / steps,
-                    "inputs": "duals y (S+D fp64) from pinned host memory every step; cost matrix resident "
-                              "(uploaded once per problem, see e2e_cold)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
+                    "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms / steps,
+                    "cuda_graph": e2e_graph,
+                    "inputs": "host vector of duals y every step (copied to pinned memory, this rank's S_loc + D "
+                              "entries uploaded), result block read back; cost matrix resident (uploaded once "
+                              "per problem, see e2e_cold)"},
             "e2e_cold": cold, "gpu_launches": launches, "clocks": clocks, "tree_build": tree}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def sp_h2d(S, D):
-    return 8 * (S + D)
 
 
 def sweep(args, sp, y_dev, S_loc, D, lib, dev):

@@ -199,6 +199,10 @@ SX_API int    sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm);
  *   (strides in 8-byte elements, so the gathered buffer is consumed in place).  Optionally folds
  *   the G pricing headers found at headers + g * block_stride into out_summary =
  *   {total n_violating, min key, largest single n_violating, OR of the status words}.
+ *   parity_ctr (device, may be NULL): when the blocks sit in a double-buffered exchange buffer
+ *   (sx_exchange_blocks), the epoch counter of that buffer; the kernel then reads the half
+ *   (*parity_ctr & 1), i.e. blocks_* / headers + (*parity_ctr & 1) * parity_stride, so that the
+ *   launch carries no per-step argument (CUDA graphs).  Needs G * K <= 16384.
  */
 #define SX_TOPK_MAX_K 1024
 SX_API size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K);
@@ -211,22 +215,26 @@ SX_API int    sx_topk_select_sorted(const double *cand_rc, const int64_t *cand_i
 SX_API size_t sx_topk_merge_workspace_bytes(int64_t G);
 SX_API int    sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t block_stride,
                      int64_t G, int64_t K, const int64_t *headers, double *out_rc, int64_t *out_id,
-                     int64_t *out_n, int64_t *out_summary, void *ws, size_t ws_bytes, void *stream);
+                     int64_t *out_n, int64_t *out_summary, const unsigned long long *parity_ctr,
+                     int64_t parity_stride, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- multi-GPU exchange of the result blocks over NVLink peer memory ------------------------
  * Replaces the NCCL all-gather of the row-sharded pricing pass (no reference counterpart: the
  * reference is single process).  Every rank owns a symmetric buffer of sx_exchange_buffer_bytes()
  * bytes, zero-initialised and peer-mapped (e.g. torch symmetric memory); peer_bufs_dev is a DEVICE
- * array of the G base pointers (entry g = rank g's buffer as mapped in this process).  One call
- * stores this rank's block (block_len int64, even, 16 B aligned) into slot [epoch & 1][rank] of
- * every rank's buffer and returns (on the stream) when all G blocks of this epoch have landed in
- * the local slots [epoch & 1][0..G), contiguous, block_len apart.  `epoch` must start at 1 and
- * increase by 1 per call on every rank.  status_dev receives SX_ERR_PEER_TIMEOUT if a peer does
- * not show up within 10 s (it is never cleared by the library).
+ * array of the G base pointers (entry g = rank g's buffer as mapped in this process).  The buffer
+ * holds [2][G][block_len] slots, [2][G] flags and, at sx_exchange_epoch_offset(), the epoch counter
+ * (starts at 0; call n of every rank is epoch n).  One call stores this rank's block (block_len
+ * int64, even, 16 B aligned) into slot [epoch & 1][rank] of every rank's buffer and returns (on the
+ * stream) when all G blocks of this epoch have landed in the local slots [epoch & 1][0..G),
+ * contiguous, block_len apart, and the local epoch counter has advanced to `epoch`.  No per-call
+ * argument changes between calls, so the launch can be captured in a CUDA graph.  status_dev
+ * receives SX_ERR_PEER_TIMEOUT if a peer does not show up within 10 s (never cleared by the library).
  */
 SX_API size_t sx_exchange_buffer_bytes(int64_t block_len, int G);
+SX_API size_t sx_exchange_epoch_offset(int64_t block_len, int G);
 SX_API int    sx_exchange_blocks(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev,
-                          int rank, int G, unsigned long long epoch, int32_t *status_dev, void *stream);
+                          int rank, int G, int32_t *status_dev, void *stream);
 
 /* ---- host-buffer entry point (what a reference-side binding calls with NumPy arrays) ----
  * One pricing pass with HOST buffers: uploads y (and M if M_dev == NULL), prices, selects

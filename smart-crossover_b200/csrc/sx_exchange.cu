@@ -2,11 +2,13 @@
 // NVLink / NVSwitch (sm_100a), replacing the NCCL all-gather of the multi-GPU pricing pass.
 //
 // Every rank owns a symmetric, peer-mapped buffer  [2][G][block_len] int64 slots + [2][G] u64 flags
-// (double-buffered by the parity of a monotonically increasing epoch).  One launch of G CTAs:
-// CTA p stores this rank's block into slot [parity][rank] of rank p's buffer with 128-bit stores,
-// fences at system scope, raises flag [parity][rank] on rank p to `epoch`, and then waits until
-// rank p has raised flag [parity][p] in the LOCAL buffer.  When the kernel ends, the local slots
-// [parity][0..G) hold all G blocks and the merge kernels (sx_topk_merge) consume them in place.
+// + {epoch, done} counters (double-buffered by the parity of a monotonically increasing epoch that
+// lives in the buffer itself, so the launch has no per-step argument and can sit in a CUDA graph).
+// One launch of G CTAs: CTA p stores this rank's block into slot [parity][rank] of rank p's buffer
+// with 128-bit stores, fences at system scope, raises flag [parity][rank] on rank p to `epoch`, and
+// then waits until rank p has raised flag [parity][p] in the LOCAL buffer.  When the kernel ends,
+// the local slots [parity][0..G) hold all G blocks, the local epoch counter has advanced, and the
+// merge kernel (sx_topk_merge with parity_ctr = the epoch counter) consumes them in place.
 // 16 KB per rank is pure latency: this costs one kernel (~5 us + NVLink round trip) instead of a
 // collective launch.  Ranks run on different GPUs, so the wait never depends on a kernel queued
 // behind it on the same device; a bounded spin turns a lost peer into an error code, not a hang.
@@ -35,10 +37,14 @@ constexpr int kXcThreads = 256;
 
 __global__ void __launch_bounds__(kXcThreads)
 exchange_blocks_kernel(const long long *__restrict__ block, long long block_len, char *const *peer_bufs,
-                       int rank, int G, unsigned long long epoch, unsigned long long timeout_ns, int *status) {
+                       int rank, int G, unsigned long long timeout_ns, int *status) {
     const int p = blockIdx.x;                      // peer served by this CTA
-    const int parity = (int)(epoch & 1ull);
     const size_t slots_bytes = (size_t)2 * G * block_len * sizeof(long long);
+    char *local = peer_bufs[rank];
+    unsigned long long *ctr = reinterpret_cast<unsigned long long *>(local + slots_bytes) + (size_t)2 * G;
+    // every CTA reads the counter before any CTA can have finished (it advances only after all G are done)
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(ctr) + 1ull;
+    const int parity = (int)(epoch & 1ull);
     char *remote = peer_bufs[p];
     long long *dst = reinterpret_cast<long long *>(remote) + ((size_t)parity * G + rank) * block_len;
     // block_len is even and every base is 16-byte aligned: 128-bit stores
@@ -52,11 +58,17 @@ exchange_blocks_kernel(const long long *__restrict__ block, long long block_len,
             reinterpret_cast<unsigned long long *>(remote + slots_bytes) + (size_t)parity * G + rank;
         st_release_sys(remote_flag, epoch);
         const unsigned long long *local_flag =
-            reinterpret_cast<const unsigned long long *>(peer_bufs[rank] + slots_bytes) + (size_t)parity * G + p;
+            reinterpret_cast<const unsigned long long *>(local + slots_bytes) + (size_t)parity * G + p;
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(local_flag) < epoch) {
             if (global_timer_ns() - t0 > timeout_ns) { atomicExch(status, SX_ERR_PEER_TIMEOUT); break; }
             __nanosleep(100);
+        }
+        // the last CTA to finish advances the epoch for the next launch
+        __threadfence();
+        if (atomicAdd(ctr + 1, 1ull) == (unsigned long long)(G - 1)) {
+            ctr[1] = 0ull;
+            *reinterpret_cast<volatile unsigned long long *>(ctr) = epoch;
         }
     }
 }
@@ -67,17 +79,22 @@ using namespace sx;
 
 extern "C" size_t sx_exchange_buffer_bytes(int64_t block_len, int G) {
     if (block_len < 0 || G < 1) return 0;
+    return (size_t)2 * G * block_len * 8 + (size_t)2 * G * 8 + 16;
+}
+
+extern "C" size_t sx_exchange_epoch_offset(int64_t block_len, int G) {
+    if (block_len < 0 || G < 1) return 0;
     return (size_t)2 * G * block_len * 8 + (size_t)2 * G * 8;
 }
 
 extern "C" int sx_exchange_blocks(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev, int rank,
-                                  int G, unsigned long long epoch, int32_t *status_dev, void *stream) {
+                                  int G, int32_t *status_dev, void *stream) {
     if (!block || !peer_bufs_dev || !status_dev || block_len <= 0 || (block_len & 1) || G < 1 || rank < 0 ||
-        rank >= G || epoch == 0)
+        rank >= G)
         return SX_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(block) & 15) != 0) return SX_ERR_UNALIGNED;
     exchange_blocks_kernel<<<G, kXcThreads, 0, (cudaStream_t)stream>>>(
-        (const long long *)block, block_len, (char *const *)peer_bufs_dev, rank, G, epoch,
+        (const long long *)block, block_len, (char *const *)peer_bufs_dev, rank, G,
         /*timeout_ns=*/10ull * 1000 * 1000 * 1000, status_dev);
     SX_LAUNCH_CHECK();
     return SX_OK;

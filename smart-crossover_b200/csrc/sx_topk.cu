@@ -587,9 +587,15 @@ topk_select_kernel(const double *__restrict__ cand_rc, const long long *__restri
 
 // Merge of G sorted, padded blocks of K (all-gathered from G ranks): all-pairs rank over G * K.
 __global__ void __launch_bounds__(kApThreads)
-merge_rank_kernel(const double *__restrict__ blocks_rc, const long long *__restrict__ blocks_id, long long LS, int G,
+merge_rank_kernel(const double *blocks_rc, const long long *blocks_id, long long LS, int G,
                   int K, const long long *headers, double *__restrict__ out_rc, long long *__restrict__ out_id,
-                  long long *out_n, long long *out_summary) {
+                  long long *out_n, long long *out_summary, const unsigned long long *parity_ctr,
+                  long long parity_stride) {
+    if (parity_ctr) {   // double-buffered exchange: the blocks of this epoch are in half (epoch & 1)
+        const long long off = (long long)(*parity_ctr & 1ull) * parity_stride;
+        blocks_rc += off; blocks_id += off;
+        if (headers) headers += off;
+    }
     const int n = G * K;
     auto load = [&](int e) {
         const long long off = (long long)(e / K) * LS + (e % K);
@@ -770,8 +776,10 @@ extern "C" size_t sx_topk_merge_workspace_bytes(int64_t G) {
 
 extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, int64_t block_stride, int64_t G,
                              int64_t K, const int64_t *headers, double *out_rc, int64_t *out_id, int64_t *out_n,
-                             int64_t *out_summary, void *ws, size_t ws_bytes, void *stream) {
+                             int64_t *out_summary, const unsigned long long *parity_ctr, int64_t parity_stride,
+                             void *ws, size_t ws_bytes, void *stream) {
     if (G <= 0 || K <= 0 || !blocks_rc || !blocks_id || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
+    if (parity_ctr && G * K > 2 * kSurvCap) return SX_ERR_TOO_LARGE;
     if (block_stride < K || ((headers == nullptr) != (out_summary == nullptr))) return SX_ERR_INVALID;
     if (G > (1 << 20) || K > (1ll << 30)) return SX_ERR_TOO_LARGE;
     if (!ws || ws_bytes < sx_topk_merge_workspace_bytes(G)) return SX_ERR_WORKSPACE;
@@ -780,7 +788,7 @@ extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, 
         merge_rank_kernel<<<kNumSMs, kApThreads, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G,
                                                           (int)K, (const long long *)headers, out_rc,
                                                           (long long *)out_id, (long long *)out_n,
-                                                          (long long *)out_summary);
+                                                          (long long *)out_summary, parity_ctr, parity_stride);
         SX_LAUNCH_CHECK();
         return SX_OK;
     }

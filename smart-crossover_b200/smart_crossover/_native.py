@@ -76,9 +76,10 @@ SIGNATURES = {
     "sx_topk_select": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "sx_topk_select_sorted": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "sx_topk_merge_workspace_bytes": (_sz, [_i64]),
-    "sx_topk_merge": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "sx_topk_merge": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _sz, _p]),
     "sx_exchange_buffer_bytes": (_sz, [_i64, _int]),
-    "sx_exchange_blocks": (_int, [_p, _i64, _p, _int, _int, ctypes.c_ulonglong, _p, _p]),
+    "sx_exchange_epoch_offset": (_sz, [_i64, _int]),
+    "sx_exchange_blocks": (_int, [_p, _i64, _p, _int, _int, _p, _p]),
     "sx_price_dense_ot_h": (_int, [_p, _p, _i64, _i64, _p, _dbl, _i64, _p, _p, _p, _p, _p]),
 }
 

@@ -285,7 +285,7 @@ def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor, headers: torch.
         assert headers.stride(0) == stride
     ws = _ws(lib.sx_topk_merge_workspace_bytes(G), dev_)
     check(lib.sx_topk_merge(_ptr(blocks_rc), _ptr(blocks_id), stride, G, K, _ptr(headers), _ptr(out_rc),
-                            _ptr(out_id), _ptr(out_n), _ptr(summary), _ptr(ws), ws.numel(), _stream()),
+                            _ptr(out_id), _ptr(out_n), _ptr(summary), None, 0, _ptr(ws), ws.numel(), _stream()),
           "sx_topk_merge")
     if headers is not None:
         return out_rc, out_id, out_n, summary

@@ -44,7 +44,7 @@ class ShardedDensePricer:
     row-major, device resident for the life of the problem, like the reference keeps `ot.M`)."""
 
     def __init__(self, M_loc: torch.Tensor, S: int, row0: int, K: int, tol: float = dev.TOL_RC,
-                 group=None, variant: int = -1, exchange: str = "p2p"):
+                 group=None, variant: int = -1, exchange: str = "p2p", use_graph: bool = True):
         self.M = M_loc
         self.S, self.D = int(S), int(M_loc.shape[1])
         self.S_loc, self.row0 = int(M_loc.shape[0]), int(row0)
@@ -53,6 +53,9 @@ class ShardedDensePricer:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.pricer = dev.Pricer(M_loc.device, self.K)
         self._merge_launches = 0
+        self.use_graph = bool(use_graph)
+        self._graph, self._capture_tried, self._graph_launches, self._replayed_launches = None, False, 0, 0
+        self._capture_overcount = 0
         self.y_dev = torch.empty(self.S + self.D, dtype=torch.float64, device=M_loc.device)
         self.h_y = torch.empty(self.S + self.D, dtype=torch.float64).pin_memory()
         Kp = max(self.K, 1)
@@ -69,7 +72,6 @@ class ShardedDensePricer:
         # exchange of the result blocks: "p2p" = direct peer stores over NVLink into a symmetric buffer
         # (sx_exchange_blocks), "nccl" = all_gather_into_tensor.  p2p needs torch symmetric memory.
         self.exchange = exchange if self.world > 1 else "none"
-        self._epoch = 0
         if self.exchange == "p2p":
             try:
                 self._setup_p2p(Kp)
@@ -87,6 +89,8 @@ class ShardedDensePricer:
         torch.cuda.synchronize()
         self._hdl = symm.rendezvous(self._symm, group=self.group if self.group is not None else dist.group.WORLD)
         self._rank = dist.get_rank(self.group)
+        off = lib.sx_exchange_epoch_offset(blk, self.world) // 8
+        self._epoch_ctr = self._symm[off:off + 1]
         self._xstatus = torch.zeros(1, dtype=torch.int32, device=self.M.device)
         self._h_xstatus = torch.zeros(1, dtype=torch.int32).pin_memory()
         dist.barrier(group=self.group)
@@ -94,7 +98,7 @@ class ShardedDensePricer:
     @property
     def launches(self):
         """Kernels of libsxcross enqueued by this object."""
-        return self.pricer.launches + self._merge_launches
+        return self.pricer.launches + self._merge_launches + self._replayed_launches - self._capture_overcount
 
     # -- device-only step: everything stays on the GPU(s) --------------------------------------
     def enqueue(self, y_dev: torch.Tensor, kernel_events=None, sorted_path: bool = False):
@@ -118,59 +122,109 @@ class ShardedDensePricer:
             return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0], p.header[3]
         # one exchange: every rank's block (top-K + header) lands in `gathered`, consumed in place
         if self.exchange == "p2p":
-            self._epoch += 1
-            blk = self.blk
-            check(lib.sx_exchange_blocks(dev._ptr(p.block), blk, self._hdl.buffer_ptrs_dev, self._rank, self.world,
-                                         self._epoch, dev._ptr(self._xstatus), dev._stream()), "sx_exchange_blocks")
+            check(lib.sx_exchange_blocks(dev._ptr(p.block), self.blk, self._hdl.buffer_ptrs_dev, self._rank,
+                                         self.world, dev._ptr(self._xstatus), dev._stream()), "sx_exchange_blocks")
             self._merge_launches += 1
-            par = self._epoch & 1
-            gathered = self._symm[par * self.world * blk:(par + 1) * self.world * blk].view(self.world, blk)
+            # both halves of the double buffer are passed; the merge kernel picks (epoch & 1) on the device
+            gathered = self._symm[:self.world * self.blk].view(self.world, self.blk)
+            parity_ctr, parity_stride = dev._ptr(self._epoch_ctr), self.world * self.blk
         else:
             dist.all_gather_into_tensor(self.gathered.view(-1), p.block, group=self.group)
             gathered = self.gathered
+            parity_ctr, parity_stride = None, 0
         rc, ids, hdr = block_views(gathered, Kp)
         check(lib.sx_topk_merge(dev._ptr(rc), dev._ptr(ids), gathered.stride(0), self.world, Kp, dev._ptr(hdr),
                                 dev._ptr(self._m_rc), dev._ptr(self._m_id), dev._ptr(self._m_n), dev._ptr(self._m_sum),
+                                parity_ctr, parity_stride,
                                 dev._ptr(self._merge_ws), self._merge_ws.numel(), dev._stream()), "sx_topk_merge")
         self._merge_launches += 1
         return self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2], self._m_sum[3]
 
     # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
-    def price(self, y_host: np.ndarray) -> dev.PriceResult:
-        """Upload y from pinned host memory, price, read the result back (one sync)."""
-        self.h_y.numpy()[:] = y_host
-        self.y_dev.copy_(self.h_y, non_blocking=True)
+    def _step(self, sorted_path: bool = False):
+        """H2D of the duals this rank needs (its rows + every sink), one pass, D2H of the result."""
+        r0, r1 = self.row0, self.row0 + self.S_loc
+        self.y_dev[r0:r1].copy_(self.h_y[r0:r1], non_blocking=True)
+        self.y_dev[self.S:].copy_(self.h_y[self.S:], non_blocking=True)
+        self.enqueue(self.y_dev, sorted_path=sorted_path)
+        if self.world == 1:
+            self.pricer.h_block.copy_(self.pricer.block, non_blocking=True)
+        else:
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            if self.exchange == "p2p":
+                self._h_xstatus.copy_(self._xstatus, non_blocking=True)
+
+    def _capture(self):
+        """Record one step (copies + kernels) in a CUDA graph: one launch call per pass instead of ~8.
+        NCCL exchange stays eager."""
+        self._graph = None
+        if not self.use_graph or self.exchange == "nccl":
+            return
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._step()                                   # warm-up outside the capture (lazy module loads)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)                 # every rank did the same number of exchanges
+        launches = self.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step()
+        self._graph_launches = self.launches - launches
+        self._capture_overcount += self._graph_launches       # recorded, not executed
+        self._graph = g
+
+    def _read_result(self):
         K = max(self.K, 1)
+        if self.world == 1:
+            h = self.pricer.h_block.numpy()
+            n_out = int(h[2 * K + 4]) if self.K > 0 else 0
+            count, status = int(h[2 * K]) & 0xFFFFFFFFFFFFFFFF, int(h[2 * K + 3])
+            res = dev.PriceResult(count, float(lib.sx_key_to_f64(int(h[2 * K + 1]))),
+                                  h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
+            return res, status, count
+        if self.exchange == "p2p" and int(self._h_xstatus[0]) != 0:
+            check(int(self._h_xstatus[0]), "sx_exchange_blocks")
+        h = self.h_out.numpy()
+        n_out = int(h[2 * K]) if self.K > 0 else 0
+        res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
+                              h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
+        return res, int(h[2 * K + 4]), int(h[2 * K + 3])
+
+    def price(self, y_host: np.ndarray) -> dev.PriceResult:
+        """One pass from a host vector of duals: copy into pinned memory, replay the captured step
+        (H2D, pricing, selection, exchange + merge, D2H), one synchronisation, read the result."""
+        self.h_y.numpy()[:] = y_host
+        if self._graph is None and self.use_graph and not self._capture_tried:
+            self._capture_tried = True
+            self._capture()
         sorted_path = False
+        first = True
         while True:
-            self.enqueue(self.y_dev, sorted_path=sorted_path)
-            if self.world == 1:
-                res = self.pricer.fetch()                  # one D2H copy of the block, one sync
-                status, cmax = self.pricer.status, res.n_violating
+            if first and self._graph is not None:
+                self._graph.replay()
+                self._replayed_launches += self._graph_launches
             else:
-                self.h_out.copy_(self.d_out, non_blocking=True)
-                if self.exchange == "p2p":
-                    self._h_xstatus.copy_(self._xstatus, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                if self.exchange == "p2p" and int(self._h_xstatus[0]) != 0:
-                    check(int(self._h_xstatus[0]), "sx_exchange_blocks")
-                h = self.h_out.numpy()
-                n_out = int(h[2 * K]) if self.K > 0 else 0
-                res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
-                                      h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
-                cmax, status = int(h[2 * K + 3]), int(h[2 * K + 4])
+                self._step(sorted_path=sorted_path)
+            first = False
+            torch.cuda.current_stream().synchronize()
+            res, status, cmax = self._read_result()
             # Every rank reads the same folded status, so all ranks repeat the pass together: with a larger
             # candidate buffer after an overflow, with the sorted selection after SX_STATUS_NEED_SORTED.
             if self.K == 0 or status == 0:
                 return res
             if status & _native.SX_STATUS_CAND_OVERFLOW:
                 self.pricer.grow(cmax)
+                self._graph, self._capture_tried = None, False      # buffers moved: record again next time
             else:
                 sorted_path = True
 
     @property
     def h2d_bytes(self):
-        return 8 * (self.S + self.D)
+        return 8 * (self.S_loc + self.D)
 
     @property
     def d2h_bytes(self):
