@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: NVLink peer-store exchange of the result blocks (default) or NCCL all-gather")
     ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
+    ap.add_argument("--sweep-ab", default="", metavar="I,J,..",
+                    help="with --sweep: interleaved A/B timing of these TMA shape indices only")
     ap.add_argument("--tree-only", type=int, default=0, metavar="S",
                     help="only time the tree-basis build on an S x S instance and exit")
     return ap.parse_args()
@@ -262,7 +264,31 @@ def time_tree_build(S, D, device, reps=3):
     x = ((s[:, None] * d[None, :]) / (t * t * t * t)).reshape(-1)
     x *= 1.0 + 1e-3 * torch.rand(x.shape, generator=g, device=device, dtype=torch.float64)
     del t
+    N = S + D
+    nt = N - 1
+    # (A) tree-basis build as tree_BI.tree_basis_identify runs it: scores -> head of the Kruskal order
+    #     (sx_kruskal_prefix, 16 N arcs) -> union-find -> potentials
     best = None
+    for _ in range(reps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        F = dev.score_ot(x, s, d)
+        ev[1].record()
+        head = dev.kruskal_prefix(F, 16 * N)
+        ev[2].record()
+        tree, n_tree = dev.kruskal(head, N, S=S, D=D)
+        ev[3].record()
+        y = dev.tree_potentials(tree, nt, N, M, N - 1, S=S, D=D)
+        ev[4].record()
+        torch.cuda.synchronize()
+        parts = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        assert head is not None and int(n_tree.item()) == nt
+        if best is None or sum(parts) < sum(best):
+            best = parts
+        tree_a = tree.clone()
+        del F, head, tree, y
+    # (B) the full sorted queue of get_sorted_flows (every arc ranked) and the tree from that order
+    full = None
     for _ in range(reps + 1):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record()
@@ -272,20 +298,22 @@ def time_tree_build(S, D, device, reps=3):
         ev[2].record()
         korder = dev.kruskal_order(skey, order)
         ev[3].record()
-        tree, n_tree = dev.kruskal(korder, S + D, S=S, D=D)
+        tree, n_tree = dev.kruskal(korder, N, S=S, D=D)
         ev[4].record()
-        nt = S + D - 1
-        y = dev.tree_potentials(tree, nt, S + D, M, S + D - 1, S=S, D=D)
+        y = dev.tree_potentials(tree, nt, N, M, N - 1, S=S, D=D)
         ev[5].record()
         torch.cuda.synchronize()
         parts = [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
-        assert int(n_tree.item()) == nt
-        if best is None or sum(parts) < sum(best):
-            best = parts
+        assert int(n_tree.item()) == nt and bool((tree == tree_a).all())      # same tree either way
+        if full is None or sum(parts) < sum(full):
+            full = parts
         del F, order, skey, korder, tree, y
-    names = ["score", "argsort", "kruskal_order", "kruskal", "potentials"]
+    names = ["score", "kruskal_prefix", "kruskal", "potentials"]
+    names_full = ["score", "argsort", "kruskal_order", "kruskal", "potentials"]
     return {"workload": f"OT {S}x{D} ({S * D} arcs)", "ms": round(sum(best), 4),
-            "breakdown_ms": {n: round(v, 4) for n, v in zip(names, best)}}
+            "breakdown_ms": {n: round(v, 4) for n, v in zip(names, best)},
+            "with_full_argsort_ms": round(sum(full), 4),
+            "with_full_argsort_breakdown_ms": {n: round(v, 4) for n, v in zip(names_full, full)}}
 
 
 def time_mcf_path(N, E, device, reps=3):
@@ -509,6 +537,27 @@ def main():
 def sweep(args, sp, y_dev, S_loc, D, lib, dev):
     """Pricing-kernel variants and tunings, kernel-only GB/s (CUDA events, 20 reps after 3 warm-ups)."""
     import torch
+    if args.sweep_ab:
+        idx = [int(t) for t in args.sweep_ab.split(",")]
+        ms = {i: [] for i in idx}
+        sp.variant = 0
+        for rnd in range(8):
+            for i in idx:
+                lib.sx_price_set_tuning(i, 0)
+                for _ in range(2):
+                    sp.enqueue(y_dev)
+                k0 = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+                k1 = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+                for r in range(10):
+                    sp.enqueue(y_dev, kernel_events=(k0[r], k1[r]))
+                torch.cuda.synchronize()
+                ms[i] += [k0[r].elapsed_time(k1[r]) for r in range(10)]
+        for i in idx:
+            print(json.dumps({"tma_shape": i, "kernel_ms_median": round(float(np.median(ms[i])), 4),
+                              "kernel_ms_min": round(float(min(ms[i])), 4),
+                              "GBs_median": round(8.0 * S_loc * D / (np.median(ms[i]) * 1e-3) / 1e9, 1)}), flush=True)
+        lib.sx_price_set_tuning(6, 16)
+        return
     res = []
     shapes = ["16x6 8w", "16x6 16w", "32x3 8w", "32x3 16w", "16x7 16w", "8x12 16w", "16x3 8w x2cta", "8x6 8w x2cta",
               "24x4 16w", "20x5 16w", "12x9 16w", "12x4 8w x2cta", "8x7 8w x2cta", "8x4 8w x3cta"]
@@ -531,7 +580,7 @@ def sweep(args, sp, y_dev, S_loc, D, lib, dev):
         res.append({"variant": name, "tuning": tune, "kernel_ms_median": round(float(np.median(ms)), 4),
                     "kernel_ms_min": round(float(min(ms)), 4), "GBs": round(gbs, 1)})
         print(json.dumps(res[-1]), flush=True)
-    lib.sx_price_set_tuning(3, 16)
+    lib.sx_price_set_tuning(6, 16)
 
 
 if __name__ == "__main__":

@@ -115,6 +115,23 @@ SX_API size_t sx_kruskal_order_workspace_bytes(int64_t n);
 SX_API int    sx_kruskal_order(const double *sorted_key, const uint32_t *order_asc, int64_t n,
                         uint32_t *korder_out, void *ws, size_t ws_bytes, void *stream);
 
+/* ---- K1d: head of the Kruskal order without a full sort ---------------------------------
+ * `max_weight_spanning_tree` (tree_BI.py:32-59) passes all n weights to SciPy's Kruskal, which
+ * argsorts them all although the tree is complete after the first few N arcs.  sx_kruskal_prefix
+ * returns only the head of that order: every arc whose weight is >= the T-th largest one (to 24
+ * bits of its order-preserving image), in Kruskal order (descending weight, ties by ascending
+ * arc id), i.e. exactly the first *n_prefix_h entries of what sx_argsort_f64 + sx_kruskal_order
+ * would produce.  Three streaming passes over the weights (24 B per arc) instead of ~256 B per arc.
+ *   korder_out: capacity T_cap >= T.  *n_prefix_h (HOST) = number of arcs written, or -1 when more
+ *   than T_cap arcs tie at the threshold (use the full argsort then).  Synchronises the stream once.
+ * The caller runs sx_kruskal on the prefix and falls back to the full order if the forest is not
+ * complete within it.
+ */
+SX_API size_t sx_kruskal_prefix_workspace_bytes(int64_t T_cap);
+SX_API int    sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int64_t T_cap,
+                         uint32_t *korder_out, int64_t *n_prefix_h, void *ws, size_t ws_bytes,
+                         void *stream);
+
 /* ---- K2: spanning-tree basis identification -------------------------------------------
  * Replaces `sp.csgraph.minimum_spanning_tree(-w)` + flatnonzero, tree_BI.py:32-59.
  * Visits arcs in `korder`; keeps an arc when its end nodes are in different components

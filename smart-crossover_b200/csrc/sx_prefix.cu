@@ -1,0 +1,231 @@
+// sx_prefix.cu -- K1d: the head of the Kruskal order without sorting every arc (sm_100a).
+//
+// `max_weight_spanning_tree` (reference tree_BI.py:32-59) hands ALL n weights to SciPy, whose
+// Kruskal argsorts them all although the tree is complete after the first few N arcs of the order
+// (last tree arc at sorted rank ~8 N of n = N^2 / 4).  This file produces only
+// the first T' >= T arcs of that order -- descending weight, ties by ascending arc id -- which is
+// all sx_kruskal needs as long as it finishes inside the prefix (the caller checks and falls back
+// to the full argsort otherwise; the tree is identical either way because the prefix of a strict
+// total order is unique).
+//
+//   1. histogram of the top 12 bits (sign + exponent) of every weight's order-preserving image,
+//      then of the next 12 bits inside the bin where the T-th largest weight lies: two streaming
+//      passes, 8 B per arc each;
+//   2. filter: every arc whose 24-bit prefix is >= the T-th largest one is appended to a candidate
+//      list (unordered): one more pass, 8 B per arc;
+//   3. the few candidates are sorted by id, then stably by weight (radix argsort, sx_sort.cu), and
+//      the tie runs are flipped into the Kruskal order (sx_kruskal_order).
+// HBM-bound: 24 B per arc instead of the ~256 B per arc of the full 8-pass argsort.
+#include "sx_common.cuh"
+
+namespace sx {
+
+constexpr int kPfThreads = 512;
+constexpr int kPfBins    = 4096;
+constexpr int kPfSub     = 2;      // sub-histograms per CTA (lanes spread over them): fewer same-address conflicts
+
+struct PrefixCtl {
+    unsigned long long n_sel;      // candidates appended by the filter
+    unsigned long long above;      // arcs in bins strictly above the threshold bin (level 0, then level 0 + 1)
+    unsigned int       b1, b2;     // threshold bin of level 0 / level 1
+    unsigned int       pad[10];
+    unsigned int       hist[2][kPfBins];
+};
+
+// LEVEL 0: digit = bits 63..52 of the image.  LEVEL 1: bits 51..40, only for keys whose level-0 digit is b1.
+template <int LEVEL>
+__global__ void __launch_bounds__(kPfThreads)
+pf_hist_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl) {
+    __shared__ unsigned sh[kPfSub][kPfBins];
+    for (int i = threadIdx.x; i < kPfSub * kPfBins; i += kPfThreads) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned b1 = LEVEL == 1 ? ctl->b1 : 0u;
+    unsigned *mine = sh[threadIdx.x & (kPfSub - 1)];
+    // run-length cache: consecutive equal digits cost one shared atomic
+    unsigned run_d = 0xffffffffu, run_c = 0;
+    auto add = [&](double v) {
+        const unsigned long long k = f64_to_sort_key(v);
+        unsigned d;
+        if (LEVEL == 0) d = (unsigned)(k >> 52);
+        else {
+            if ((unsigned)(k >> 52) != b1) return;
+            d = (unsigned)(k >> 40) & (kPfBins - 1);
+        }
+        if (d == run_d) { ++run_c; return; }
+        if (run_c) atomicAdd(&mine[run_d], run_c);
+        run_d = d; run_c = 1;
+    };
+    const long long n2 = n / 2;
+    const double2 *w2 = reinterpret_cast<const double2 *>(w);
+    const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+    const long long stride = (long long)gridDim.x * kPfThreads;
+    if (aligned) {
+        for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < n2; i += stride) {
+            const double2 v = __ldcs(w2 + i);
+            add(v.x); add(v.y);
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) add(w[n - 1]);
+    } else {
+        for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < n; i += stride) add(__ldcs(w + i));
+    }
+    if (run_c) atomicAdd(&mine[run_d], run_c);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kPfBins; i += kPfThreads) {
+        unsigned c = 0;
+#pragma unroll
+        for (int s = 0; s < kPfSub; ++s) c += sh[s][i];
+        if (c) atomicAdd(&ctl->hist[LEVEL][i], c);
+    }
+}
+
+// One CTA: the largest bin b with count(bins >= b) >= need, scanning the 4096 bins from the top.
+template <int LEVEL>
+__global__ void __launch_bounds__(1024) pf_bound_kernel(PrefixCtl *ctl, unsigned long long T) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned s_found;
+    const unsigned long long need = LEVEL == 0 ? T : (T > ctl->above ? T - ctl->above : 1ull);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // reversed bin index r = 4095 - bin; thread t owns r = 4 t .. 4 t + 3
+    unsigned c[4];
+    unsigned long long local = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = ctl->hist[LEVEL][kPfBins - 1 - (4 * threadIdx.x + q)]; local += c[q]; }
+    unsigned long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    if (threadIdx.x == 0) s_found = 0xffffffffu;
+    __syncthreads();
+    unsigned long long before = 0;
+    for (int w2 = 0; w2 < warp; ++w2) before += s_warp[w2];
+    incl += before;
+    unsigned long long cum = incl - local;      // count in bins strictly above this thread's first bin
+    // the unique thread where the running count crosses `need`
+    if (cum < need && incl >= need) {
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (q == r && cum + c[r] < need) { cum += c[r]; ++q; }
+        if (q > 3) q = 3;
+        s_found = kPfBins - 1 - (4 * threadIdx.x + q);
+        if (LEVEL == 0) { ctl->b1 = s_found; ctl->above = cum; }
+        else { ctl->b2 = s_found; ctl->above += cum; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_found == 0xffffffffu) {   // fewer than `need` arcs in total: take everything
+        if (LEVEL == 0) { ctl->b1 = 0; ctl->above = 0; } else ctl->b2 = 0;
+    }
+}
+
+// Append every arc whose 24-bit prefix is >= (b1, b2).
+__global__ void __launch_bounds__(kPfThreads)
+pf_filter_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, double *__restrict__ cand_w,
+                 unsigned long long *__restrict__ cand_id, long long cap) {
+    const unsigned thr = (ctl->b1 << 12) | ctl->b2;
+    const unsigned lt = (1u << lane_id()) - 1u;
+    const long long stride = (long long)gridDim.x * kPfThreads;
+    const long long n_ceil = (n + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < n_ceil; i += stride) {
+        double v = 0.0;
+        bool keep = false;
+        if (i < n) { v = __ldcs(w + i); keep = (unsigned)(f64_to_sort_key(v) >> 40) >= thr; }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0) continue;
+        unsigned long long base = 0;
+        if (lane_id() == 0) base = atomicAdd(&ctl->n_sel, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const long long slot = (long long)base + __popc(m & lt);
+        if (keep && slot < cap) { cand_w[slot] = v; cand_id[slot] = (unsigned long long)i; }
+    }
+}
+
+__global__ void pf_gather_kernel(const double *__restrict__ w, const unsigned long long *__restrict__ id,
+                                 const uint32_t *__restrict__ perm, long long n, double *w_out, uint32_t *id_out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t s = perm[i];
+        w_out[i] = w[s];
+        id_out[i] = (uint32_t)id[s];
+    }
+}
+__global__ void pf_gather_ids_kernel(const uint32_t *__restrict__ id, const uint32_t *__restrict__ perm, long long n,
+                                     uint32_t *id_out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        id_out[i] = id[perm[i]];
+}
+
+static int pf_grid(long long n, int per_thread) {
+    long long g = (n + (long long)kPfThreads * per_thread - 1) / ((long long)kPfThreads * per_thread);
+    if (g > kNumSMs * 4) g = kNumSMs * 4;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace sx
+
+using namespace sx;
+
+extern "C" size_t sx_kruskal_prefix_workspace_bytes(int64_t T_cap) {
+    if (T_cap < 0) return 0;
+    const size_t c = (size_t)T_cap;
+    return carve_bytes(1, sizeof(PrefixCtl)) + 3 * carve_bytes(c, 8) + 4 * carve_bytes(c, 4) + carve_bytes(c, 8) +
+           sx_argsort_workspace_bytes(T_cap) + sx_kruskal_order_workspace_bytes(T_cap) + 256;
+}
+
+extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int64_t T_cap, uint32_t *korder_out,
+                                 int64_t *n_prefix_h, void *ws, size_t ws_bytes, void *stream) {
+    if (!weight || n <= 0 || T <= 0 || T_cap < T || !korder_out || !n_prefix_h) return SX_ERR_INVALID;
+    if (n >= (1ll << 32)) return SX_ERR_TOO_LARGE;
+    if (!ws || ws_bytes < sx_kruskal_prefix_workspace_bytes(T_cap)) return SX_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    Carver cv(ws);
+    PrefixCtl *ctl = cv.take<PrefixCtl>(1);
+    double *cand_w = cv.take<double>(T_cap);
+    unsigned long long *cand_id = cv.take<unsigned long long>(T_cap);
+    double *w1 = cv.take<double>(T_cap);
+    uint32_t *id1 = cv.take<uint32_t>(T_cap);
+    uint32_t *perm = cv.take<uint32_t>(T_cap);
+    uint32_t *perm2 = cv.take<uint32_t>(T_cap);
+    uint32_t *order_asc = cv.take<uint32_t>(T_cap);
+    double *sorted_w = cv.take<double>(T_cap);
+    void *sort_ws = cv.base + cv.off;
+    const size_t sort_ws_bytes = sx_argsort_workspace_bytes(T_cap);
+    void *ko_ws = (char *)sort_ws + align_up(sort_ws_bytes, 256);
+    const size_t ko_ws_bytes = sx_kruskal_order_workspace_bytes(T_cap);
+
+    SX_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PrefixCtl), st));
+    const int grid = pf_grid(n, 16);
+    pf_hist_kernel<0><<<grid, kPfThreads, 0, st>>>(weight, n, ctl);
+    SX_LAUNCH_CHECK();
+    pf_bound_kernel<0><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
+    SX_LAUNCH_CHECK();
+    pf_hist_kernel<1><<<grid, kPfThreads, 0, st>>>(weight, n, ctl);
+    SX_LAUNCH_CHECK();
+    pf_bound_kernel<1><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
+    SX_LAUNCH_CHECK();
+    pf_filter_kernel<<<grid, kPfThreads, 0, st>>>(weight, n, ctl, cand_w, cand_id, T_cap);
+    SX_LAUNCH_CHECK();
+    unsigned long long n_sel = 0;
+    SX_CUDA(cudaMemcpyAsync(&n_sel, &ctl->n_sel, sizeof(n_sel), cudaMemcpyDeviceToHost, st));
+    SX_CUDA(cudaStreamSynchronize(st));
+    if (n_sel > (unsigned long long)T_cap) {   // too many ties at the threshold for this capacity
+        *n_prefix_h = -1;
+        return SX_OK;
+    }
+    const long long m = (long long)n_sel;
+    *n_prefix_h = m;
+    if (m == 0) return SX_OK;
+    // (weight, id) is a strict total order: sort by id, then stably by weight
+    int rc = sx_argsort_u64(cand_id, m, 32, perm, nullptr, sort_ws, sort_ws_bytes, st);
+    if (rc != SX_OK) return rc;
+    const int g2 = pf_grid(m, 1);
+    pf_gather_kernel<<<g2, kPfThreads, 0, st>>>(cand_w, cand_id, perm, m, w1, id1);
+    SX_LAUNCH_CHECK();
+    rc = sx_argsort_f64(w1, m, perm2, sorted_w, sort_ws, sort_ws_bytes, st);
+    if (rc != SX_OK) return rc;
+    pf_gather_ids_kernel<<<g2, kPfThreads, 0, st>>>(id1, perm2, m, order_asc);
+    SX_LAUNCH_CHECK();
+    return sx_kruskal_order(sorted_w, order_asc, m, korder_out, ko_ws, ko_ws_bytes, st);
+}

@@ -558,7 +558,7 @@ static const TmaShape kTmaShapes[] = {
     {12, 4, 8, 2}, {8, 7, 8, 2}, {8, 4, 8, 3},
 };
 constexpr int kNumTmaShapes = sizeof(kTmaShapes) / sizeof(kTmaShapes[0]);
-static int g_tma_shape = 3, g_ctas_per_sm_direct = 16;
+static int g_tma_shape = 6, g_ctas_per_sm_direct = 16;   // 16 rows x 3 stages, 8 consumer warps, 2 CTAs per SM
 
 template <int ROWS, int STAGES, int CWARPS, int MINB, bool WRITE_RC>
 static int launch_tma(const CUtensorMap &map, const DenseParams &p, cudaStream_t st) {

@@ -63,6 +63,8 @@ SIGNATURES = {
     "sx_queue_from_order": (_int, [_p, _i64, _p, _p]),
     "sx_kruskal_order_workspace_bytes": (_sz, [_i64]),
     "sx_kruskal_order": (_int, [_p, _p, _i64, _p, _p, _sz, _p]),
+    "sx_kruskal_prefix_workspace_bytes": (_sz, [_i64]),
+    "sx_kruskal_prefix": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "sx_kruskal_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_kruskal": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "sx_tree_potentials_workspace_bytes": (_sz, [_i64]),

@@ -92,6 +92,23 @@ def kruskal_order(sorted_key: torch.Tensor, order: torch.Tensor) -> torch.Tensor
     return out
 
 
+def kruskal_prefix(weights: torch.Tensor, T: int, T_cap: int | None = None):
+    """Head of the Kruskal order (descending weight, ties by ascending id): every arc at least as heavy
+    as the T-th heaviest.  Returns an int32 tensor (uint32 bit patterns) or None when more than T_cap
+    arcs tie at the threshold (the caller then sorts everything).  One stream synchronisation."""
+    n = weights.numel()
+    T = int(min(T, n))
+    T_cap = int(T_cap or max(2 * T, T + 65536))
+    out = torch.empty(T_cap, dtype=torch.int32, device=weights.device)
+    ws = _ws(lib.sx_kruskal_prefix_workspace_bytes(T_cap), weights.device)
+    n_prefix = ctypes.c_int64(0)
+    check(lib.sx_kruskal_prefix(_ptr(weights), n, T, T_cap, _ptr(out), ctypes.byref(n_prefix), _ptr(ws), ws.numel(),
+                                _stream()), "sx_kruskal_prefix")
+    if n_prefix.value < 0:
+        return None
+    return out[:n_prefix.value]
+
+
 # ---- K2 ------------------------------------------------------------------------------------
 def kruskal(korder: torch.Tensor, N: int, S: int = 0, D: int = 0, tail=None, head=None):
     """Spanning forest over `korder`; returns (tree arc ids ascending [device, capacity N-1], n_tree [device])."""

@@ -32,16 +32,35 @@ def tree_basis_identify(ot_manager: OTManager, flow_weights: np.ndarray) -> Tupl
     return Basis(vbasis, cbasis), push_iter
 
 
+PREFIX_FACTOR = 16      # the Kruskal order's head handed to the union-find first: 16 N arcs
+
+
 def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlows = None):
-    """(tree arc ids on the device, their number) for the complete bipartite graph of `ot`."""
+    """(tree arc ids on the device, their number) for the complete bipartite graph of `ot`.
+
+    Large instances first try the head of the Kruskal order only (`sx_kruskal_prefix`: the 16 N
+    heaviest arcs, three streaming passes instead of a full argsort); the spanning tree is almost
+    always complete inside it (last tree arc at rank ~8 N).  If not, or when the
+    full sort already exists (`get_sorted_flows` ran on these weights), the full order is used.  Both
+    give the same tree: a prefix of a strict total order is unique."""
     dev = _dev()
     S, D = np.asarray(ot.M).shape
+    N, n = S + D, S * D
     flow_weights = np.asarray(flow_weights, dtype=np.float64)
-    if _sorted is None or not _sorted.matches(flow_weights):
-        _sorted = _SortedFlows(_cuda(flow_weights), flow_weights)
-    if np.isnan(_sorted.scores_np).any():
+    have_sort = _sorted is not None and _sorted.matches(flow_weights)
+    if np.isnan(flow_weights).any():
         raise ValueError("flow weights contain NaN (a zero marginal?): the spanning tree is undefined")
-    tree_t, n_t = dev.kruskal(_sorted.kruskal_order(), S + D, S=S, D=D)
+    if not have_sort and n > 4 * PREFIX_FACTOR * N:
+        w_t = _cuda(flow_weights.ravel())
+        head = dev.kruskal_prefix(w_t, PREFIX_FACTOR * N)
+        if head is not None:
+            tree_t, n_t = dev.kruskal(head, N, S=S, D=D)
+            if int(n_t.item()) == N - 1:
+                return tree_t, N - 1
+        _sorted = _SortedFlows(w_t, flow_weights)
+    elif not have_sort:
+        _sorted = _SortedFlows(_cuda(flow_weights), flow_weights)
+    tree_t, n_t = dev.kruskal(_sorted.kruskal_order(), N, S=S, D=D)
     return tree_t, int(n_t.item())
 
 

@@ -167,6 +167,58 @@ def test_tree_potentials_rejects_non_spanning(dev):
         dev.tree_potentials(cu(tree[:5]), 5, S + D, cu(M), S + D - 1, S=S, D=D)
 
 
+@pytest.mark.parametrize("S,D,T,kind", [(300, 400, 5000, "interior"), (64, 5000, 20000, "interior"),
+                                        (500, 500, 16000, "ties"), (257, 129, 1, "interior"),
+                                        (200, 300, 60000, "interior"), (128, 128, 3000, "zeros")])
+def test_kruskal_prefix_is_the_head_of_the_full_order(dev, S, D, T, kind):
+    """sx_kruskal_prefix == the first entries of argsort + kruskal_order, for generic weights, for
+    product weights with massive ties and with exact zeros."""
+    s, d, M = cases.ot_points(S, D, 900 + S)
+    if kind == "ties":
+        x = np.outer(s, d).ravel()                                   # every score ties along rows / columns
+    else:
+        x = cases.interior_flow(s, d, M, 900 + S, 0.33)
+        if kind == "zeros":
+            x[np.random.default_rng(1).random(x.size) < 0.7] = 0.0
+    F = orc.ot_flow_scores(x, s, d)
+    order, skey, queue, korder = sort_pipeline(dev, cu(F))
+    full = korder.cpu().numpy().view(np.uint32)
+    head = dev.kruskal_prefix(cu(F), T, T_cap=S * D)
+    assert head is not None
+    head = head.cpu().numpy().view(np.uint32)
+    assert min(T, S * D) <= head.size <= S * D
+    assert np.array_equal(head, full[:head.size])
+    # everything left out is strictly lighter than the lightest arc kept (to 24 bits of the key)
+    if head.size < S * D:
+        assert F[full[head.size]] < F[head[-1]]
+    # capacity too small for the ties at the threshold: the caller is told to sort everything
+    if kind == "ties":
+        assert dev.kruskal_prefix(cu(F), 10, T_cap=12) is None
+
+
+def test_tree_from_prefix_equals_tree_from_full_sort(dev):
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods import tree_BI
+    from smart_crossover.network_methods.net_manager import OTManager
+    S, D = 400, 700
+    s, d, M = cases.ot_points(S, D, 31)
+    x = cases.interior_flow(s, d, M, 31, 0.33)
+    F = orc.ot_flow_scores(x, s, d)
+    ot = OptTransport(s, d, M)
+    tree_ref = orc.max_weight_spanning_tree(F, S, D)
+    assert S * D > 4 * tree_BI.PREFIX_FACTOR * (S + D)              # takes the prefix path
+    assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F), tree_ref)
+    mgr = OTManager(ot)
+    q, F2 = mgr.get_sorted_flows(x)                                   # full sort exists: reused
+    assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F2, _sorted=mgr._sorted), tree_ref)
+    old = tree_BI.PREFIX_FACTOR
+    try:
+        tree_BI.PREFIX_FACTOR = 1                                     # head too short: falls back, same tree
+        assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F), tree_ref)
+    finally:
+        tree_BI.PREFIX_FACTOR = old
+
+
 # ---- K4 ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", OT_FULL)
 @pytest.mark.parametrize("variant", [-1, 0, 1, 2])
