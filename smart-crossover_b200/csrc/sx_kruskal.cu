@@ -182,7 +182,7 @@ extern "C" int sx_kruskal(const uint32_t *korder, int64_t n, const int32_t *tail
                           void *ws, size_t ws_bytes, void *stream) {
     if (n < 0 || N < 0 || !tree_out || !n_tree_out) return SX_ERR_INVALID;
     if ((tail == nullptr) != (head == nullptr)) return SX_ERR_INVALID;
-    if (!tail && (S <= 0 || D <= 0 || S + D != N || S * D != n)) return SX_ERR_INVALID;
+    if (!tail && (S <= 0 || D <= 0 || S + D != N || n > S * D)) return SX_ERR_INVALID;   // n < S * D: a prefix of the order
     if (N >= (1ll << 31) || n >= (1ll << 32)) return SX_ERR_TOO_LARGE;
     if (n > 0 && !korder) return SX_ERR_INVALID;
     if (!ws || ws_bytes < sx_kruskal_workspace_bytes(N, n)) return SX_ERR_WORKSPACE;
@@ -221,8 +221,9 @@ extern "C" int sx_kruskal(const uint32_t *korder, int64_t n, const int32_t *tail
     SX_LAUNCH_CHECK();
     if (tcap > 0) {
         // ascending arc ids (np.flatnonzero order, tree_BI.py:56-57); sentinels sort last
+        const long long id_bound = tail ? (1ll << 32) - 1 : S * D;      // korder may be a prefix: ids are not < n
         int bits = 1;
-        while (bits < 63 && (1ll << bits) <= n) ++bits;
+        while (bits < 63 && (1ll << bits) <= id_bound) ++bits;
         // the low `bits` bits of the sentinel are all ones (>= n > any arc id), so it still sorts last
         int rc = sx_argsort_u64((const unsigned long long *)raw_tree, tcap, bits, perm,
                                 (unsigned long long *)tree_out, sort_ws, sort_ws_bytes, st);
