@@ -161,6 +161,18 @@ SX_API int    sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int3
                           double *y_out, int32_t *status_out, void *ws, size_t ws_bytes,
                           void *stream);
 
+/* sx_tree_flows: primal flows of the tree basis, the solution of B x = b[:-1] with B = A[:-1, tree]
+ * that the reference gets from SuperLU (tree_BI.py:74-76; the dropped row is the root's).  The flow
+ * on tree arc t is +/- the sum of b over the subtree below it, taken as a difference of tour-order
+ * prefix sums carried in double-double (each flow is accurate to an ulp of the exact subtree sum).
+ *   b: N supplies (A x = b); flow_out[t] belongs to tree[t]; same workspace size and status as
+ *   sx_tree_potentials.
+ */
+SX_API int    sx_tree_flows(const int64_t *tree, int64_t n_tree, const int32_t *tail, const int32_t *head,
+                     int64_t S, int64_t D, int64_t N, const double *b, int plus_convention,
+                     int64_t root, double *flow_out, int32_t *status_out, void *ws, size_t ws_bytes,
+                     void *stream);
+
 /* ---- K4: pricing ----------------------------------------------------------------------
  * sx_price_dense_ot replaces `c - A.T @ y` + `np.all(rc >= -tol)` over the dense OT cost
  * matrix, net_manager.py:474-497:  rc_ij = fl(M_ij - fl(y_dst[j] - y_src[i])).

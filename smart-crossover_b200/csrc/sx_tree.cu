@@ -13,6 +13,12 @@
 //   5. of each pair of half-edges the one met first goes down the tree, and the prefix sum at
 //      it is the potential of the node it enters.
 // Latency / L2-gather bound (2T <= 2.4e5 elements at C5).
+//
+// The same tour gives the tree's primal flows (sx_tree_flows; reference tree_BI.py:74-76 solves
+// B x = b[:-1] with SuperLU): the flow on a tree arc is +/- the sum of the supplies b over the
+// subtree hanging below it, i.e. a difference of two prefix sums of b taken in tour order.  The
+// prefix sums are carried in double-double (error-free TwoSum), so each flow is the correctly
+// rounded-to-1-ulp subtree sum no matter how large the running total is.
 #include "sx_common.cuh"
 
 namespace sx {
@@ -43,11 +49,11 @@ __global__ void tree_halfedges_kernel(const long long *__restrict__ tree, long l
         if (tail == nullptr) {
             const long long i = e / D, j = e - i * D;
             plus = (int)(S + j); minus = (int)i;
-            c = cost[i * ld + j];
+            c = cost ? cost[i * ld + j] : 0.0;
         } else {
             plus = plus_is_tail ? tail[e] : head[e];
             minus = plus_is_tail ? head[e] : tail[e];
-            c = cost[e];
+            c = cost ? cost[e] : 0.0;
         }
         a.origin[2 * t] = (unsigned long long)minus; a.dest[2 * t] = plus;      a.sum[0][2 * t] = c;
         a.origin[2 * t + 1] = (unsigned long long)plus; a.dest[2 * t + 1] = minus; a.sum[0][2 * t + 1] = -c;
@@ -114,6 +120,77 @@ __global__ void tree_finalize_kernel(long long T, long long root, const double *
 
 __global__ void tree_status_kernel(int32_t *status, int32_t v) { *status = v; }
 
+// ---- primal flows ------------------------------------------------------------------------
+struct dd { double hi, lo; };
+__device__ __forceinline__ dd dd_add(dd a, double b) {           // error-free a + b (Knuth TwoSum), renormalised
+    const double s = a.hi + b;
+    const double bb = s - a.hi;
+    const double e = (a.hi - (s - bb)) + (b - bb);
+    const double lo = a.lo + e;
+    const double hi = s + lo;
+    return dd{hi, lo - (hi - s)};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) { return dd_add(dd_add(a, b.hi), b.lo); }
+
+// w[pos] = supply of the node entered at tour position pos (down half-edges), 0 for up half-edges.
+__global__ void flow_scatter_kernel(long long T, const int *__restrict__ rank, const int *__restrict__ pred,
+                                    const int *__restrict__ dest, const double *__restrict__ b, double *__restrict__ w,
+                                    int32_t *status) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long ha = 2 * t, hb = 2 * t + 1;
+        if (pred[ha] != -1 || pred[hb] != -1) { *status = SX_ERR_NOT_SPANNING; continue; }
+        const bool a_down = rank[ha] < rank[hb];
+        const long long down = a_down ? ha : hb, up = a_down ? hb : ha;
+        w[rank[down] - 1] = b[dest[down]];
+        w[rank[up] - 1] = 0.0;
+    }
+}
+
+// One CTA: inclusive double-double prefix sum of w[0..H) -> (phi, plo).
+__global__ void __launch_bounds__(1024) flow_scan_kernel(long long H, const double *__restrict__ w,
+                                                         double *__restrict__ phi, double *__restrict__ plo) {
+    __shared__ double s_hi[1024], s_lo[1024];
+    const long long chunk = (H + 1023) / 1024;
+    const long long lo = (long long)threadIdx.x * chunk, hi = lo + chunk < H ? lo + chunk : H;
+    dd acc{0.0, 0.0};
+    for (long long i = lo; i < hi; ++i) acc = dd_add(acc, w[i]);
+    s_hi[threadIdx.x] = acc.hi; s_lo[threadIdx.x] = acc.lo;
+    __syncthreads();
+    if (threadIdx.x == 0) {                                     // 1024 chunk totals: serial exclusive scan
+        dd run{0.0, 0.0};
+        for (int i = 0; i < 1024; ++i) {
+            const dd v{s_hi[i], s_lo[i]};
+            s_hi[i] = run.hi; s_lo[i] = run.lo;
+            run = dd_add(run, v);
+        }
+    }
+    __syncthreads();
+    acc = dd{s_hi[threadIdx.x], s_lo[threadIdx.x]};
+    for (long long i = lo; i < hi; ++i) {
+        acc = dd_add(acc, w[i]);
+        phi[i] = acc.hi; plo[i] = acc.lo;
+    }
+}
+
+// flow(t) = +/- (P[rank(up) - 1] - P[rank(down) - 2]): supplies of the subtree below arc t.
+__global__ void flow_finalize_kernel(long long T, const int *__restrict__ rank, const int *__restrict__ dest,
+                                     const double *__restrict__ phi, const double *__restrict__ plo,
+                                     double *__restrict__ flow) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long ha = 2 * t, hb = 2 * t + 1;            // ha: minus -> plus, hb: plus -> minus
+        const bool a_down = rank[ha] < rank[hb];
+        const long long down = a_down ? ha : hb, up = a_down ? hb : ha;
+        const long long r1 = rank[down] - 1, r2 = rank[up] - 1;  // tour positions, r1 < r2
+        dd top{phi[r2], plo[r2]};
+        if (r1 > 0) top = dd_add(top, dd{-phi[r1 - 1], -plo[r1 - 1]});
+        const double subtree = top.hi + top.lo;
+        // the arc's column has +1 at `plus`, -1 at `minus`; conservation over the subtree gives the sign
+        flow[t] = a_down ? subtree : -subtree;
+    }
+}
+
 static int tr_grid(long long n) {
     long long g = (n + kTrThreads - 1) / kTrThreads;
     if (g > kNumSMs * 8) g = kNumSMs * 8;
@@ -132,31 +209,14 @@ extern "C" size_t sx_tree_potentials_workspace_bytes(int64_t N) {
            2 * carve_bytes(H, 8) + 4 * carve_bytes(H, 4) + sx_argsort_workspace_bytes((int64_t)H) + 512;
 }
 
-extern "C" int sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int32_t *tail, const int32_t *head,
-                                  int64_t S, int64_t D, int64_t N, const double *cost, int64_t ld,
-                                  int plus_convention, int64_t root, double *y_out, int32_t *status_out,
-                                  void *ws, size_t ws_bytes, void *stream) {
-    if (!y_out || !status_out || N <= 0 || root < 0 || root >= N || n_tree < 0) return SX_ERR_INVALID;
-    if ((tail == nullptr) != (head == nullptr)) return SX_ERR_INVALID;
-    if (!tail && (S <= 0 || D <= 0 || S + D != N || ld < D)) return SX_ERR_INVALID;
-    if (N >= (1ll << 30)) return SX_ERR_TOO_LARGE;
-    if (!ws || ws_bytes < sx_tree_potentials_workspace_bytes(N)) return SX_ERR_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (n_tree != N - 1) {   // cannot be a spanning tree
-        tree_status_kernel<<<1, 1, 0, st>>>(status_out, SX_ERR_NOT_SPANNING);
-        SX_LAUNCH_CHECK();
-        return SX_OK;
-    }
-    tree_status_kernel<<<1, 1, 0, st>>>(status_out, 0);
-    SX_LAUNCH_CHECK();
-    if (N == 1) {
-        SX_CUDA(cudaMemsetAsync(y_out, 0, sizeof(double), st));
-        return SX_OK;
-    }
-    if (!tree || !cost) return SX_ERR_INVALID;
+// Shared by potentials and flows: half-edges, Euler tour cut at the root, pointer jumping.
+// On return a.sum[cur] / a.rank[cur] / a.pred[cur] hold the inclusive prefix of the half-edge
+// weights, the 1-based tour position, and -1 for every half-edge reached from the root.
+static int tree_tour(const int64_t *tree, int64_t n_tree, const int32_t *tail, const int32_t *head, int64_t S,
+                     int64_t D, int64_t N, const double *cost, int64_t ld, int plus_convention, int64_t root,
+                     int32_t *status_out, void *ws, size_t ws_bytes, cudaStream_t st, TreeArrays &a, int &cur) {
     const long long T = n_tree, H = 2 * T;
     Carver cv(ws);
-    TreeArrays a;
     a.origin = cv.take<unsigned long long>(H);
     a.sorted_origin = cv.take<unsigned long long>(H);
     a.ho = cv.take<uint32_t>(H);
@@ -185,14 +245,87 @@ extern "C" int sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int
     SX_LAUNCH_CHECK();
     int rounds = 1;
     while ((1ll << rounds) < H) ++rounds;
-    int cur = 0;
+    cur = 0;
     for (int r = 0; r < rounds; ++r, cur ^= 1) {
         tree_jump_kernel<<<tr_grid(H), kTrThreads, 0, st>>>(H, a.sum[cur], a.rank[cur], a.pred[cur],
                                                             a.sum[cur ^ 1], a.rank[cur ^ 1], a.pred[cur ^ 1]);
         SX_LAUNCH_CHECK();
     }
-    tree_finalize_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, root, a.sum[cur], a.rank[cur], a.pred[cur], a.dest,
-                                                            y_out, status_out);
+    return SX_OK;
+}
+
+static int tree_check_args(const void *out, const int32_t *status_out, const int32_t *tail, const int32_t *head,
+                           int64_t S, int64_t D, int64_t N, int64_t ld, int64_t root, int64_t n_tree, const void *ws,
+                           size_t ws_bytes) {
+    if (!out || !status_out || N <= 0 || root < 0 || root >= N || n_tree < 0) return SX_ERR_INVALID;
+    if ((tail == nullptr) != (head == nullptr)) return SX_ERR_INVALID;
+    if (!tail && (S <= 0 || D <= 0 || S + D != N || ld < D)) return SX_ERR_INVALID;
+    if (N >= (1ll << 30)) return SX_ERR_TOO_LARGE;
+    if (!ws || ws_bytes < sx_tree_potentials_workspace_bytes(N)) return SX_ERR_WORKSPACE;
+    return SX_OK;
+}
+
+extern "C" int sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int32_t *tail, const int32_t *head,
+                                  int64_t S, int64_t D, int64_t N, const double *cost, int64_t ld,
+                                  int plus_convention, int64_t root, double *y_out, int32_t *status_out,
+                                  void *ws, size_t ws_bytes, void *stream) {
+    int arg = tree_check_args(y_out, status_out, tail, head, S, D, N, ld, root, n_tree, ws, ws_bytes);
+    if (arg != SX_OK) return arg;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tree != N - 1) {   // cannot be a spanning tree
+        tree_status_kernel<<<1, 1, 0, st>>>(status_out, SX_ERR_NOT_SPANNING);
+        SX_LAUNCH_CHECK();
+        return SX_OK;
+    }
+    tree_status_kernel<<<1, 1, 0, st>>>(status_out, 0);
+    SX_LAUNCH_CHECK();
+    if (N == 1) {
+        SX_CUDA(cudaMemsetAsync(y_out, 0, sizeof(double), st));
+        return SX_OK;
+    }
+    if (!tree || !cost) return SX_ERR_INVALID;
+    TreeArrays a;
+    int cur = 0;
+    int rc = tree_tour(tree, n_tree, tail, head, S, D, N, cost, ld, plus_convention, root, status_out, ws, ws_bytes, st,
+                       a, cur);
+    if (rc != SX_OK) return rc;
+    tree_finalize_kernel<<<tr_grid(n_tree), kTrThreads, 0, st>>>(n_tree, root, a.sum[cur], a.rank[cur], a.pred[cur],
+                                                                 a.dest, y_out, status_out);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}
+
+extern "C" int sx_tree_flows(const int64_t *tree, int64_t n_tree, const int32_t *tail, const int32_t *head,
+                             int64_t S, int64_t D, int64_t N, const double *b, int plus_convention, int64_t root,
+                             double *flow_out, int32_t *status_out, void *ws, size_t ws_bytes, void *stream) {
+    int arg = tree_check_args(flow_out, status_out, tail, head, S, D, N, D, root, n_tree, ws, ws_bytes);
+    if (arg != SX_OK) return arg;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tree != N - 1) {
+        tree_status_kernel<<<1, 1, 0, st>>>(status_out, SX_ERR_NOT_SPANNING);
+        SX_LAUNCH_CHECK();
+        return SX_OK;
+    }
+    tree_status_kernel<<<1, 1, 0, st>>>(status_out, 0);
+    SX_LAUNCH_CHECK();
+    if (N == 1) return SX_OK;
+    if (!tree || !b) return SX_ERR_INVALID;
+    TreeArrays a;
+    int cur = 0;
+    // the tour does not depend on the half-edge weights: b stands in for the cost array (one value per
+    // arc is read for OT through cost[i * ld + j] with ld = D, which b does not have) -> use a zero-cost view
+    int rc = tree_tour(tree, n_tree, tail, head, S, D, N, nullptr, D, plus_convention, root, status_out, ws, ws_bytes,
+                       st, a, cur);
+    if (rc != SX_OK) return rc;
+    const long long T = n_tree, H = 2 * T;
+    // scratch: the buffers of the finished ranking that are no longer needed
+    double *w = a.sum[cur ^ 1];
+    double *phi = reinterpret_cast<double *>(a.origin), *plo = reinterpret_cast<double *>(a.sorted_origin);
+    flow_scatter_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, a.rank[cur], a.pred[cur], a.dest, b, w, status_out);
+    SX_LAUNCH_CHECK();
+    flow_scan_kernel<<<1, 1024, 0, st>>>(H, w, phi, plo);
+    SX_LAUNCH_CHECK();
+    flow_finalize_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, a.rank[cur], a.dest, phi, plo, flow_out);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }

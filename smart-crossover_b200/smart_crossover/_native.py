@@ -70,6 +70,7 @@ SIGNATURES = {
     "sx_tree_potentials_workspace_bytes": (_sz, [_i64]),
     "sx_tree_potentials": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _p, _i64, _int, _i64, _p, _p, _p, _sz, _p]),
     "sx_select_state_bytes": (_sz, []),
+    "sx_tree_flows": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _p, _int, _i64, _p, _p, _p, _sz, _p]),
     "sx_price_pass_begin": (_int, [_p, _p, _i64, _p]),
     "sx_price_dense_ot": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _dbl, _p, _p, _p, _p, _i64, _p, _i64, _int, _p]),
     "sx_price_arcs": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _dbl, _p, _p, _p, _p, _i64, _p, _p]),

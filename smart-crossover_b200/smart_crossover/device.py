@@ -136,6 +136,18 @@ def tree_potentials(tree: torch.Tensor, n_tree: int, N: int, cost: torch.Tensor,
     return y
 
 
+def tree_flows(tree: torch.Tensor, n_tree: int, N: int, b: torch.Tensor, root: int, S: int = 0, D: int = 0,
+               tail=None, head=None, plus=_native.SX_PLUS_IS_HEAD) -> torch.Tensor:
+    """Primal flows x_T of the tree basis, B x_T = b[:-1] (reference tree_BI.py:74-76), one per tree arc."""
+    flow = torch.zeros(max(n_tree, 1), dtype=torch.float64, device=b.device)
+    status = torch.zeros(1, dtype=torch.int32, device=b.device)
+    ws = _ws(lib.sx_tree_potentials_workspace_bytes(N), b.device)
+    check(lib.sx_tree_flows(_ptr(tree), n_tree, _ptr(tail), _ptr(head), S, D, N, _ptr(b), plus, root,
+                            _ptr(flow), _ptr(status), _ptr(ws), ws.numel(), _stream()), "sx_tree_flows")
+    check(int(status.item()), "sx_tree_flows")
+    return flow[:n_tree]
+
+
 # ---- K4 ------------------------------------------------------------------------------------
 @dataclass
 class PriceResult:

@@ -4,18 +4,17 @@
                                chunked Kruskal with a lock-free union-find (sx_kruskal)
   tree_potentials           -> device: Euler tour + list ranking (sx_tree_potentials); new, the
                                reference reads duals from the LP solver instead
-  push_tree_to_bfs          -> host: the tree primal solve uses the same (N-1) x (N-1) sparse system
-                               as the reference (`B x = b[:-1]`, tree_BI.py:74-76) but builds B from the
-                               tree arcs directly, and the sequential push loop (tree_BI.py:81-110)
-                               walks the O(N + pushes) non-zeros instead of a dense S x D scratch.
+  push_tree_to_bfs          -> device: the tree primal flows (`B x = b[:-1]`, tree_BI.py:74-76, SuperLU in
+                               the reference) are subtree sums of b on the same Euler tour
+                               (sx_tree_flows, double-double prefix sums);
+                               host: the sequential push loop (tree_BI.py:81-110) walks the O(N + pushes)
+                               non-zeros instead of a dense S x D scratch.
 """
 from __future__ import annotations
 
 from typing import Tuple
 
 import numpy as np
-import scipy.sparse as sp
-import scipy.sparse.linalg
 
 from smart_crossover.formats import OptTransport
 from smart_crossover.network_methods.net_manager import OTManager, _SortedFlows, _cuda, _dev
@@ -83,22 +82,25 @@ def tree_potentials(ot: OptTransport, tree: np.ndarray) -> np.ndarray:
     return y.cpu().numpy()
 
 
-def push_tree_to_bfs(ot_manager: OTManager, tree: np.ndarray) -> Tuple[np.ndarray, int]:
+def tree_flows(ot: OptTransport, tree: np.ndarray) -> np.ndarray:
+    """Primal flows of the tree basis, one per tree arc: B x = b[:-1] with B = A[:-1, tree] and
+    b = [-s, d] (reference tree_BI.py:74-76).  Needs a spanning tree (N - 1 arcs)."""
+    dev = _dev()
+    S, D = ot.s.size, ot.d.size
+    tree = np.asarray(tree, dtype=np.int64)
+    b = np.hstack([-np.asarray(ot.s, dtype=np.float64), np.asarray(ot.d, dtype=np.float64)])
+    return dev.tree_flows(_cuda(tree), int(tree.size), S + D, _cuda(b), S + D - 1, S=S, D=D).cpu().numpy()
+
+
+def push_tree_to_bfs(ot_manager: OTManager, tree: np.ndarray, _flows: np.ndarray = None) -> Tuple[np.ndarray, int]:
     """Tree primal flows, then 'irrigation' pushes until no tree flow is negative.
-    Returns (vbasis, push_iter) with vbasis = 0 on arcs carrying positive flow, -1 elsewhere."""
+    Returns (vbasis, push_iter) with vbasis = 0 on arcs carrying positive flow, -1 elsewhere.
+    `_flows` (tests of the host loop) supplies the tree flows instead of computing them on the GPU."""
     ot = ot_manager.ot
     S, D = ot.s.size, ot.d.size
     tree = np.asarray(tree, dtype=np.int64)
-    T = tree.size
     ti, tj = tree // D, tree % D
-    # B = A[:-1, tree]: -1 at row i, +1 at row S + j, last node row dropped
-    rows = np.concatenate([ti, S + tj])
-    cols = np.concatenate([np.arange(T), np.arange(T)])
-    vals = np.concatenate([-np.ones(T), np.ones(T)])
-    keep = rows < S + D - 1
-    B = sp.csc_matrix((vals[keep], (rows[keep], cols[keep])), shape=(S + D - 1, T))
-    b = np.hstack([-ot.s, ot.d])[:-1]
-    flow = sp.linalg.spsolve(B, b)
+    flow = np.asarray(_flows, dtype=np.float64) if _flows is not None else tree_flows(ot, tree)
 
     row_nz = [dict() for _ in range(S)]
     col_nz = [dict() for _ in range(D)]

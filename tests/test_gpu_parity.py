@@ -219,6 +219,51 @@ def test_tree_from_prefix_equals_tree_from_full_sort(dev):
         tree_BI.PREFIX_FACTOR = old
 
 
+@pytest.mark.parametrize("name", OT_FULL)
+def test_tree_flows_golden(dev, name):
+    """Tree primal flows (SuperLU in the reference, tree_BI.py:74-76) from the Euler tour, and the push
+    phase driven by them: same basis and push count as the reference."""
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.net_manager import OTManager
+    from smart_crossover.network_methods.tree_BI import push_tree_to_bfs, tree_flows
+    fx = Fixture(name)
+    s, d, M = fx.inp["s"], fx.inp["d"], fx.inp["M"]
+    ot = OptTransport(s, d, M)
+    flows = tree_flows(ot, fx.out["tree"])
+    np.testing.assert_allclose(flows, fx.out["tree_flows"], rtol=1e-9, atol=1e-12 * max(s.max(), d.max()))
+    vbasis, push_iter = push_tree_to_bfs(OTManager(ot), fx.out["tree"])
+    assert push_iter == int(fx.out["push_iter"])
+    assert np.array_equal(vbasis.astype(np.int64), fx.out["vbasis_tree"])
+
+
+def test_tree_flows_are_exact_subtree_sums(dev):
+    """Integer supplies: every subtree sum is exactly representable, so the flows must be exact,
+    and A[:, tree] @ flows == b on every node but the root (conservation)."""
+    S, D = 300, 500
+    rng = np.random.default_rng(8)
+    s = rng.integers(1, 1000, S).astype(np.float64)
+    d = rng.integers(1, 1000, D).astype(np.float64)
+    d[-1] += s.sum() - d.sum()
+    M = rng.random((S, D))
+    F = rng.random(S * D)
+    tree = orc.max_weight_spanning_tree(F, S, D)
+    b = np.hstack([-s, d])
+    flows = dev.tree_flows(cu(tree), tree.size, S + D, cu(b), S + D - 1, S=S, D=D).cpu().numpy()
+    assert np.array_equal(flows, np.round(flows))
+    bal = np.zeros(S + D)
+    np.add.at(bal, tree // D, -flows)
+    np.add.at(bal, S + tree % D, flows)
+    assert np.array_equal(bal[:-1], b[:-1])
+    # arc-list form, min2mcf sign convention (+1 at the tail)
+    tail = (S + tree % D).astype(np.int32)
+    head = (tree // D).astype(np.int32)
+    from smart_crossover._native import SX_PLUS_IS_TAIL
+    ids = np.arange(tree.size, dtype=np.int64)
+    f2 = dev.tree_flows(cu(ids), tree.size, S + D, cu(b), S + D - 1, tail=cu(tail), head=cu(head),
+                        plus=SX_PLUS_IS_TAIL).cpu().numpy()
+    assert np.array_equal(f2, flows)
+
+
 # ---- K4 ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", OT_FULL)
 @pytest.mark.parametrize("variant", [-1, 0, 1, 2])

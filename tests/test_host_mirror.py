@@ -41,7 +41,9 @@ def test_to_mcf_matches_the_reference_layout():
 def test_push_tree_to_bfs_matches_golden(name):
     fx = Fixture(name)
     mgr = OTManager(OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"]))
-    vbasis, push_iter = push_tree_to_bfs(mgr, fx.out["tree"])
+    # the host push loop, fed the reference's own tree flows (the device computes them in production:
+    # tests/test_gpu_parity.py::test_tree_flows_golden and test_gpu_e2e.py run that path)
+    vbasis, push_iter = push_tree_to_bfs(mgr, fx.out["tree"], _flows=fx.out["tree_flows"])
     assert push_iter == int(fx.out["push_iter"])
     assert np.array_equal(vbasis.astype(np.int64), fx.out["vbasis_tree"])
 
