@@ -265,6 +265,21 @@ SX_API size_t sx_exchange_epoch_offset(int64_t block_len, int G);
 SX_API int    sx_exchange_blocks(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev,
                           int rank, int G, int32_t *status_dev, void *stream);
 
+/* ---- warm start: entropic Sinkhorn point for the crossover (scripts/run_network_crossover.py:96) ----
+ * The reference's OT experiments cross over `ot.sinkhorn(s, d, M, reg=10, numItermax=1000)` (POT,
+ * third party, Sinkhorn-Knopp).  sx_sinkhorn_ot runs the same iteration in the log domain on the
+ * device-resident cost matrix: v = b / (K^T u), u = a / (K v) from u = 1 / S, K = exp(-M / reg),
+ * carried as potentials f = reg log u, g = reg log v; stops after max_iter iterations or when the
+ * column-marginal error || X^T 1 - b ||_2, examined every check_every iterations, is below stop_thr
+ * (<= 0: never examined).  x_out (S * D, may be NULL) receives X = exp((f_i + g_j - M_ij) / reg).
+ *   f (S), g (D): device outputs.  iters_h / err_h (HOST, may be NULL): iterations run, last error.
+ */
+SX_API size_t sx_sinkhorn_workspace_bytes(int64_t S, int64_t D);
+SX_API int    sx_sinkhorn_ot(const double *M, int64_t ld, int64_t S, int64_t D, const double *a,
+                      const double *b, double reg, int64_t max_iter, double stop_thr,
+                      int64_t check_every, double *f, double *g, double *x_out, int64_t *iters_h,
+                      double *err_h, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- host-buffer entry point (what a reference-side binding calls with NumPy arrays) ----
  * One pricing pass with HOST buffers: uploads y (and M if M_dev == NULL), prices, selects
  * the top K, and returns count / min / top-k on the host.  Synchronises before returning.

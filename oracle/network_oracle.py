@@ -331,3 +331,25 @@ def column_chunks(m: int, n: int, queue_len: int, rounds: int):
         num = int(2 * num)
         left = right
     return out
+
+
+def sinkhorn_knopp(a, b, M, reg, num_iter_max=1000, stop_thr=1e-9, check_every=10):
+    """Sinkhorn-Knopp as POT runs it for `ot.sinkhorn(a, b, M, reg, numItermax)` -- the warm start of the
+    reference's OT experiments (scripts/run_network_crossover.py:96; POT is a third-party package, not
+    in the reference tree: its published algorithm restated): K = exp(-M / reg), u = 1 / S, then
+    v = b / (K^T u), u = a / (K v); every `check_every` iterations the column-marginal error
+    || v * (K^T u) - b ||_2 is compared with stop_thr.  Plain (not log-domain) arithmetic, so only for
+    reg large enough that K does not underflow.  Returns (plan, iterations, last error)."""
+    a, b, M = (np.asarray(t, dtype=np.float64) for t in (a, b, M))
+    K = np.exp(-M / reg)
+    u = np.full(a.size, 1.0 / a.size)
+    v = np.full(b.size, 1.0 / b.size)
+    err, it = np.inf, 0
+    for it in range(1, num_iter_max + 1):
+        v = b / (K.T @ u)
+        u = a / (K @ v)
+        if stop_thr > 0 and (it - 1) % check_every == 0:
+            err = float(np.linalg.norm(v * (K.T @ u) - b))
+            if err < stop_thr:
+                break
+    return u[:, None] * K * v[None, :], it, err

@@ -120,25 +120,47 @@ __global__ void __launch_bounds__(1024) pf_bound_kernel(PrefixCtl *ctl, unsigned
     }
 }
 
-// Append every arc whose 24-bit prefix is >= (b1, b2).
+// Append every arc whose 24-bit prefix is >= (b1, b2).  Two arcs per thread and iteration (128-bit
+// loads); selected arcs are rare, so the ballots are almost always empty.
 __global__ void __launch_bounds__(kPfThreads)
 pf_filter_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, double *__restrict__ cand_w,
                  unsigned long long *__restrict__ cand_id, long long cap) {
     const unsigned thr = (ctl->b1 << 12) | ctl->b2;
     const unsigned lt = (1u << lane_id()) - 1u;
     const long long stride = (long long)gridDim.x * kPfThreads;
-    const long long n_ceil = (n + 31) / 32 * 32;
-    for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < n_ceil; i += stride) {
-        double v = 0.0;
-        bool keep = false;
-        if (i < n) { v = __ldcs(w + i); keep = (unsigned)(f64_to_sort_key(v) >> 40) >= thr; }
+    const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+    const long long n2 = aligned ? n / 2 : 0;                    // pairs handled by the vector loop
+    const double2 *w2 = reinterpret_cast<const double2 *>(w);
+    auto emit = [&](bool keep, double v, long long id) {
         const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m == 0) continue;
+        if (m == 0) return;
         unsigned long long base = 0;
         if (lane_id() == 0) base = atomicAdd(&ctl->n_sel, (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         const long long slot = (long long)base + __popc(m & lt);
-        if (keep && slot < cap) { cand_w[slot] = v; cand_id[slot] = (unsigned long long)i; }
+        if (keep && slot < cap) { cand_w[slot] = v; cand_id[slot] = (unsigned long long)id; }
+    };
+    const long long n2_ceil = (n2 + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < n2_ceil; i += stride) {
+        double2 v = make_double2(0.0, 0.0);
+        bool k0 = false, k1 = false;
+        if (i < n2) {
+            v = __ldcs(w2 + i);
+            k0 = (unsigned)(f64_to_sort_key(v.x) >> 40) >= thr;
+            k1 = (unsigned)(f64_to_sort_key(v.y) >> 40) >= thr;
+        }
+        if (!__any_sync(0xffffffffu, k0 || k1)) continue;
+        emit(k0, v.x, 2 * i);
+        emit(k1, v.y, 2 * i + 1);
+    }
+    // tail (odd n) or the whole array when it is not 16-byte aligned
+    const long long t0 = 2 * n2, nt = n - t0;
+    const long long nt_ceil = (nt + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < nt_ceil; i += stride) {
+        double v = 0.0;
+        bool keep = false;
+        if (i < nt) { v = __ldcs(w + t0 + i); keep = (unsigned)(f64_to_sort_key(v) >> 40) >= thr; }
+        emit(keep, v, t0 + i);
     }
 }
 

@@ -579,3 +579,24 @@ def test_c3_full_size_mcf_path(dev):
     cnt, mn, ids, vals = orc.price_summary(rc_ref, K=1000)
     assert res.n_violating == cnt and res.min_rc == mn
     assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
+
+
+# ---- warm start ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,D,reg,iters", [(40, 40, 0.05, 200), (257, 130, 0.02, 500), (300, 1000, 10.0, 1000)])
+def test_sinkhorn_warm_start_matches_sinkhorn_knopp(dev, S, D, reg, iters):
+    """Device log-domain Sinkhorn == the Sinkhorn-Knopp iteration POT runs (oracle restatement), to
+    1e-9 relative on the plan; marginals are met; the plan is a valid interior point for TNET."""
+    from smart_crossover.warm_start import sinkhorn
+    s, d, M = cases.ot_points(S, D, 40 + S)
+    if reg >= 1.0:
+        M = np.round(50 * M)                                       # MNIST-like integer costs with reg = 10
+    X_ref, it_ref, err_ref = orc.sinkhorn_knopp(s, d, M, reg, iters, stop_thr=0.0)
+    X, info = sinkhorn(s, d, M, reg, numItermax=iters, stopThr=0.0, log=True)
+    assert info["niter"] == iters and X.shape == (S, D)
+    np.testing.assert_allclose(X, X_ref, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(X.sum(axis=1), s, rtol=1e-9)            # the last half-step fixes the rows
+    assert np.all(X > 0)
+    # with the stopping rule: stops early, within one check interval of the oracle, error below the threshold
+    X2, info2 = sinkhorn(s, d, M, reg, numItermax=10000, stopThr=1e-7, log=True)
+    _, it2, _ = orc.sinkhorn_knopp(s, d, M, reg, 10000, stop_thr=1e-7)
+    assert info2["err"] < 1e-7 and abs(info2["niter"] - it2) <= 1
