@@ -120,48 +120,92 @@ __global__ void __launch_bounds__(1024) pf_bound_kernel(PrefixCtl *ctl, unsigned
     }
 }
 
-// Append every arc whose 24-bit prefix is >= (b1, b2).  Two arcs per thread and iteration (128-bit
-// loads); selected arcs are rare, so the ballots are almost always empty.
+// Append every arc whose 24-bit prefix is >= (b1, b2).  Each thread keeps kPfBatch 128-bit loads in
+// flight before it looks at any of them.  Selected arcs are staged in shared memory and flushed with
+// ONE global reservation per CTA and flush: hundreds of thousands of atomicAdds on the single global
+// counter would otherwise serialise in L2 and bound the kernel.
+constexpr int kPfBatch = 4;
+constexpr int kPfStage = 2048;                 // staged candidates per CTA (32 KB)
+
 __global__ void __launch_bounds__(kPfThreads)
 pf_filter_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, double *__restrict__ cand_w,
                  unsigned long long *__restrict__ cand_id, long long cap) {
+    __shared__ double             s_w[kPfStage];
+    __shared__ unsigned long long s_id[kPfStage];
+    __shared__ unsigned           s_cnt;
+    __shared__ unsigned long long s_base;
     const unsigned thr = (ctl->b1 << 12) | ctl->b2;
     const unsigned lt = (1u << lane_id()) - 1u;
     const long long stride = (long long)gridDim.x * kPfThreads;
     const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
     const long long n2 = aligned ? n / 2 : 0;                    // pairs handled by the vector loop
     const double2 *w2 = reinterpret_cast<const double2 *>(w);
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     auto emit = [&](bool keep, double v, long long id) {
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (m == 0) return;
-        unsigned long long base = 0;
-        if (lane_id() == 0) base = atomicAdd(&ctl->n_sel, (unsigned long long)__popc(m));
+        unsigned base = 0;
+        if (lane_id() == 0) base = atomicAdd(&s_cnt, (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        const long long slot = (long long)base + __popc(m & lt);
-        if (keep && slot < cap) { cand_w[slot] = v; cand_id[slot] = (unsigned long long)id; }
-    };
-    const long long n2_ceil = (n2 + 31) / 32 * 32;
-    for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < n2_ceil; i += stride) {
-        double2 v = make_double2(0.0, 0.0);
-        bool k0 = false, k1 = false;
-        if (i < n2) {
-            v = __ldcs(w2 + i);
-            k0 = (unsigned)(f64_to_sort_key(v.x) >> 40) >= thr;
-            k1 = (unsigned)(f64_to_sort_key(v.y) >> 40) >= thr;
+        const unsigned slot = base + __popc(m & lt);
+        if (!keep) return;
+        if (slot < (unsigned)kPfStage) { s_w[slot] = v; s_id[slot] = (unsigned long long)id; }
+        else {                                                   // stage full (dense selection): straight to global
+            const unsigned long long g = atomicAdd(&ctl->n_sel, 1ull);
+            if ((long long)g < cap) { cand_w[g] = v; cand_id[g] = (unsigned long long)id; }
         }
-        if (!__any_sync(0xffffffffu, k0 || k1)) continue;
-        emit(k0, v.x, 2 * i);
-        emit(k1, v.y, 2 * i + 1);
+    };
+    auto flush = [&]() {                                         // whole CTA
+        __syncthreads();
+        const unsigned c = s_cnt < (unsigned)kPfStage ? s_cnt : (unsigned)kPfStage;
+        if (threadIdx.x == 0 && c) s_base = atomicAdd(&ctl->n_sel, (unsigned long long)c);
+        __syncthreads();
+        for (unsigned q = threadIdx.x; q < c; q += kPfThreads) {
+            const long long g = (long long)(s_base + q);
+            if (g < cap) { cand_w[g] = s_w[q]; cand_id[g] = s_id[q]; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+    };
+    // CTA-uniform trip count (flush holds barriers): the CTA walks blocks of kPfThreads pairs
+    const long long n2_blocks = (n2 + kPfThreads - 1) / kPfThreads;
+    for (long long blk = blockIdx.x; blk < n2_blocks; blk += (long long)gridDim.x * kPfBatch) {
+        double2 v[kPfBatch];
+#pragma unroll
+        for (int u = 0; u < kPfBatch; ++u) {
+            const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
+            v[u] = i < n2 ? __ldcs(w2 + i) : make_double2(-INFINITY, -INFINITY);
+        }
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < kPfBatch; ++u)
+            any = any || (unsigned)(f64_to_sort_key(v[u].x) >> 40) >= thr || (unsigned)(f64_to_sort_key(v[u].y) >> 40) >= thr;
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int u = 0; u < kPfBatch; ++u) {
+                const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
+                const bool in = i < n2;
+                emit(in && (unsigned)(f64_to_sort_key(v[u].x) >> 40) >= thr, v[u].x, 2 * i);
+                emit(in && (unsigned)(f64_to_sort_key(v[u].y) >> 40) >= thr, v[u].y, 2 * i + 1);
+            }
+        }
+        // an iteration adds at most 8 * kPfThreads entries; flush while there is still room for a typical one
+        if (__syncthreads_or(s_cnt > (unsigned)kPfStage / 2)) flush();    // uniform decision, then barriers
     }
     // tail (odd n) or the whole array when it is not 16-byte aligned
     const long long t0 = 2 * n2, nt = n - t0;
-    const long long nt_ceil = (nt + 31) / 32 * 32;
-    for (long long i = (long long)blockIdx.x * kPfThreads + threadIdx.x; i < nt_ceil; i += stride) {
+    const long long nt_blocks = (nt + kPfThreads - 1) / kPfThreads;
+    for (long long blk = blockIdx.x; blk < nt_blocks; blk += gridDim.x) {
+        const long long i = blk * kPfThreads + threadIdx.x;
         double v = 0.0;
         bool keep = false;
         if (i < nt) { v = __ldcs(w + t0 + i); keep = (unsigned)(f64_to_sort_key(v) >> 40) >= thr; }
         emit(keep, v, t0 + i);
+        if (__syncthreads_or(s_cnt > (unsigned)kPfStage / 2)) flush();
     }
+    flush();
 }
 
 __global__ void pf_gather_kernel(const double *__restrict__ w, const unsigned long long *__restrict__ id,
@@ -227,7 +271,12 @@ extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int
     SX_LAUNCH_CHECK();
     pf_bound_kernel<1><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
     SX_LAUNCH_CHECK();
-    pf_filter_kernel<<<grid, kPfThreads, 0, st>>>(weight, n, ctl, cand_w, cand_id, T_cap);
+    int occ = 1;
+    SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pf_filter_kernel, kPfThreads, 0));
+    long long fgrid = (long long)kNumSMs * (occ > 0 ? occ : 1);
+    const long long fneed = (n / 2 + (long long)kPfThreads * kPfBatch - 1) / ((long long)kPfThreads * kPfBatch);
+    if (fgrid > fneed) fgrid = fneed > 0 ? fneed : 1;
+    pf_filter_kernel<<<(int)fgrid, kPfThreads, 0, st>>>(weight, n, ctl, cand_w, cand_id, T_cap);
     SX_LAUNCH_CHECK();
     unsigned long long n_sel = 0;
     SX_CUDA(cudaMemcpyAsync(&n_sel, &ctl->n_sel, sizeof(n_sel), cudaMemcpyDeviceToHost, st));
