@@ -54,8 +54,9 @@ def parse():
     ap.add_argument("--violators", type=float, default=1e-4, help="target fraction of violating arcs")
     ap.add_argument("--no-tree", action="store_true", help="skip the tree-basis build timings")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: NVLink peer-store exchange of the result blocks (default) or NCCL all-gather")
+    ap.add_argument("--exchange", default="ll", choices=["ll", "p2p", "nccl"],
+                    help="N > 1: exchange of the result blocks: NVLink flag-in-data stores polled by the merge "
+                         "kernel (default), peer stores + flag + wait kernel, or NCCL all-gather")
     ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
     ap.add_argument("--sweep-ab", default="", metavar="I,J,..",
                     help="with --sweep: interleaved A/B timing of these TMA shape indices only")
@@ -437,9 +438,25 @@ def main():
         out = sp.enqueue(y_dev, kernel_events=(k0[i], k1[i]))
     e1.record()
     barrier()
+    # where a step's time goes (separate short loop: the extra events are not in the timed region)
+    n_st = 5 if world > 1 else 3
+    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_st)] for _ in range(20)]
+    for i in range(20):
+        sp.enqueue(y_dev, stage_events=sev[i])
+    torch.cuda.synchronize()
+    stage_names = ["begin+pricing", "selection", "exchange", "merge"][:n_st - 1]
+    stages = {nm: round(float(np.median([sev[i][q].elapsed_time(sev[i][q + 1]) for i in range(20)])) * 1e3, 1)
+              for q, nm in enumerate(stage_names)}
+    barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = sp.launches - launches0
     kern_ms = float(np.mean([k0[i].elapsed_time(k1[i]) for i in range(steps)]))
+    per_rank_kern = [kern_ms]
+    if world > 1:                                        # the slowest GPU paces a strong-scaled, exchanged step
+        t = torch.zeros(world, dtype=torch.float64, device=device)
+        t[rank] = kern_ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        per_rank_kern = [round(float(v), 4) for v in t.tolist()]
     count_dev = int(out[3].item())
     assert int(out[6].item()) == 0, "selection status not clean: the timed pass would have to be repeated"
     value = S * D * steps / (ms_total * 1e-3)
@@ -492,7 +509,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "kernel": "price_dense_tma_kernel" if args.variant in (-1, 0) else "price_dense_direct_kernel",
-                "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_arc": 8,
+                "kernel_ms": round(kern_ms, 4), "kernel_ms_per_rank": per_rank_kern, "algorithmic_bytes_per_arc": 8,
                 "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
 
     cpu_baseline = None
@@ -528,7 +545,7 @@ def main():
                     "inputs": "host vector of duals y every step (copied to pinned memory, this rank's S_loc + D "
                               "entries uploaded), result block read back; cost matrix resident (uploaded once "
                               "per problem, see e2e_cold)"},
-            "e2e_cold": cold, "gpu_launches": launches, "clocks": clocks, "tree_build": tree}
+            "stage_us_rank0": stages, "e2e_cold": cold, "gpu_launches": launches, "clocks": clocks, "tree_build": tree}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -231,7 +231,7 @@ SX_API int    sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm);
  *   parity_ctr (device, may be NULL): when the blocks sit in a double-buffered exchange buffer
  *   (sx_exchange_blocks), the epoch counter of that buffer; the kernel then reads the half
  *   (*parity_ctr & 1), i.e. blocks_* / headers + (*parity_ctr & 1) * parity_stride, so that the
- *   launch carries no per-step argument (CUDA graphs).  Needs G * K <= 16384.
+ *   launch carries no per-step argument (CUDA graphs).
  */
 #define SX_TOPK_MAX_K 1024
 SX_API size_t sx_topk_workspace_bytes(int64_t cand_cap, int64_t K);
@@ -264,6 +264,22 @@ SX_API size_t sx_exchange_buffer_bytes(int64_t block_len, int G);
 SX_API size_t sx_exchange_epoch_offset(int64_t block_len, int G);
 SX_API int    sx_exchange_blocks(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev,
                           int rank, int G, int32_t *status_dev, void *stream);
+
+/* Low-latency form of the same exchange (default of the package): sx_exchange_push_ll only STORES --
+ * every 8-byte word of the block travels as one 16-byte slot {lo32, flag, hi32, flag}, flag = epoch --
+ * and sx_topk_merge_ll polls the slots of its local buffer while it stages the G blocks in shared
+ * memory, then merges them like sx_topk_merge.  No fence, no flag round trip, no separate wait.
+ *   Buffer: sx_exchange_ll_buffer_bytes() bytes, zeroed, peer-mapped; the epoch counter sits right
+ *   after the 2 * G * block_len slots.  block = [K rc | K ids | 4 header words | ...], block_len >= 2 K + 4.
+ *   G * K * 16 bytes must fit in shared memory (200 KB), else SX_ERR_TOO_LARGE.
+ *   out_summary (4 words, may be NULL) as in sx_topk_merge; status_dev as in sx_exchange_blocks.
+ */
+SX_API size_t sx_exchange_ll_buffer_bytes(int64_t block_len, int G);
+SX_API int    sx_exchange_push_ll(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev,
+                           int rank, int G, void *stream);
+SX_API int    sx_topk_merge_ll(const void *ll_buf_local, int64_t block_len, int64_t G, int64_t K,
+                        double *out_rc, int64_t *out_id, int64_t *out_n, int64_t *out_summary,
+                        int32_t *status_dev, void *stream);
 
 /* ---- warm start: entropic Sinkhorn point for the crossover (scripts/run_network_crossover.py:96) ----
  * The reference's OT experiments cross over `ot.sinkhorn(s, d, M, reg=10, numItermax=1000)` (POT,

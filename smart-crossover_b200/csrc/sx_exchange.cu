@@ -73,6 +73,38 @@ exchange_blocks_kernel(const long long *__restrict__ block, long long block_len,
     }
 }
 
+// ---- low-latency variant: flag-in-data ("LL") push --------------------------------------------
+// Every 8-byte word travels as one 16-byte store {lo32, flag, hi32, flag} with flag = (uint32) epoch,
+// so the receiver needs no separate flag, no fence and no second NVLink round trip: it polls each
+// slot until both flags show the epoch (8-byte units are written atomically; sx_topk_merge_ll does
+// the polling while it stages the blocks in shared memory).  The kernel only stores, it never waits.
+__global__ void __launch_bounds__(kXcThreads)
+exchange_push_ll_kernel(const unsigned long long *__restrict__ block, long long block_len, char *const *peer_bufs,
+                        int rank, int G) {
+    const int p = blockIdx.x;
+    const size_t slots_bytes = (size_t)2 * G * block_len * 16;
+    char *local = peer_bufs[rank];
+    unsigned long long *ctr = reinterpret_cast<unsigned long long *>(local + slots_bytes);
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(ctr) + 1ull;
+    const unsigned flag = (unsigned)epoch;
+    uint4 *dst = reinterpret_cast<uint4 *>(peer_bufs[p]) + ((size_t)(epoch & 1ull) * G + rank) * block_len;
+    for (long long i = threadIdx.x; i < block_len; i += kXcThreads) {
+        const unsigned long long v = block[i];
+        const uint4 w = make_uint4((unsigned)v, flag, (unsigned)(v >> 32), flag);
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "r"(w.x), "r"(w.y), "r"(w.z),
+                     "r"(w.w)
+                     : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                       // the last CTA to finish advances the epoch for the next launch
+        __threadfence();
+        if (atomicAdd(ctr + 1, 1ull) == (unsigned long long)(G - 1)) {
+            ctr[1] = 0ull;
+            *reinterpret_cast<volatile unsigned long long *>(ctr) = epoch;
+        }
+    }
+}
+
 }  // namespace sx
 
 using namespace sx;
@@ -96,6 +128,20 @@ extern "C" int sx_exchange_blocks(const int64_t *block, int64_t block_len, void 
     exchange_blocks_kernel<<<G, kXcThreads, 0, (cudaStream_t)stream>>>(
         (const long long *)block, block_len, (char *const *)peer_bufs_dev, rank, G,
         /*timeout_ns=*/10ull * 1000 * 1000 * 1000, status_dev);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}
+
+extern "C" size_t sx_exchange_ll_buffer_bytes(int64_t block_len, int G) {
+    if (block_len < 0 || G < 1) return 0;
+    return (size_t)2 * G * block_len * 16 + 64;
+}
+
+extern "C" int sx_exchange_push_ll(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev, int rank,
+                                   int G, void *stream) {
+    if (!block || !peer_bufs_dev || block_len <= 0 || G < 1 || rank < 0 || rank >= G) return SX_ERR_INVALID;
+    exchange_push_ll_kernel<<<G, kXcThreads, 0, (cudaStream_t)stream>>>((const unsigned long long *)block, block_len,
+                                                                        (char *const *)peer_bufs_dev, rank, G);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }

@@ -585,54 +585,183 @@ topk_select_kernel(const double *__restrict__ cand_rc, const long long *__restri
         });
 }
 
-// Merge of G sorted, padded blocks of K (all-gathered from G ranks): all-pairs rank over G * K.
-__global__ void __launch_bounds__(kApThreads)
+// Merge of G sorted, padded blocks of K (exchanged between G ranks).  One thread per element: its
+// position in the merged order is its index in its own block plus, for every other block, the number
+// of entries below it (binary search; (rc, id) is a strict total order and ids are distinct across
+// blocks).  G * 10 dependent L1/L2 loads per element instead of an all-pairs pass over G * K.
+__device__ __forceinline__ KeyId merge_load(const double *rc, const long long *id, long long off) {
+    const long long i = id[off];
+    return i < 0 ? KeyId{~0ull, 0x7fffffffffffffffll} : KeyId{f64_to_sort_key(rc[off]), i};
+}
+
+__global__ void __launch_bounds__(1024)
 merge_rank_kernel(const double *blocks_rc, const long long *blocks_id, long long LS, int G,
                   int K, const long long *headers, double *__restrict__ out_rc, long long *__restrict__ out_id,
                   long long *out_n, long long *out_summary, const unsigned long long *parity_ctr,
-                  long long parity_stride) {
+                  long long parity_stride, int use_smem) {
     if (parity_ctr) {   // double-buffered exchange: the blocks of this epoch are in half (epoch & 1)
         const long long off = (long long)(*parity_ctr & 1ull) * parity_stride;
         blocks_rc += off; blocks_id += off;
         if (headers) headers += off;
     }
     const int n = G * K;
-    auto load = [&](int e) {
-        const long long off = (long long)(e / K) * LS + (e % K);
-        const long long id = blocks_id[off];
-        return id < 0 ? KeyId{~0ull, 0x7fffffffffffffffll} : KeyId{f64_to_sort_key(blocks_rc[off]), id};
-    };
+    // Stage every block's (key, id) in shared memory when it fits (coalesced loads, then ~G * 10 shared
+    // loads per element); otherwise search the blocks in global memory.
+    extern __shared__ __align__(16) unsigned char mg_raw[];
+    KeyId *stage = reinterpret_cast<KeyId *>(mg_raw);
+    __shared__ int s_real;
+    __shared__ long long s_hdr[4];
+    if (threadIdx.x == 0) { s_real = 0; s_hdr[0] = 0; s_hdr[1] = 0x7fffffffffffffffll; s_hdr[2] = 0; s_hdr[3] = 0; }
+    __syncthreads();
+    int my_real = 0;
+    if (use_smem) {
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int g = e / K;
+            const KeyId v = merge_load(blocks_rc, blocks_id, (long long)g * LS + (e - g * K));
+            stage[e] = v;
+            my_real += v.key != ~0ull;
+        }
+    }
     if (blockIdx.x == 0) {
-        __shared__ int s_cnt[kApThreads / 32];
-        int c = 0;
-        for (int e = threadIdx.x; e < n; e += kApThreads) c += blocks_id[(long long)(e / K) * LS + (e % K)] >= 0;
-        c = warp_sum(c);
-        if (lane_id() == 0) s_cnt[threadIdx.x >> 5] = c;
-        __syncthreads();
-        int n_real = 0;
-        for (int w = 0; w < kApThreads / 32; ++w) n_real += s_cnt[w];
-        const int n_out = n_real < K ? n_real : K;
-        for (int i = n_out + threadIdx.x; i < K; i += kApThreads) { out_rc[i] = INFINITY; out_id[i] = -1; }
+        if (!use_smem) {
+            // real entries per block = first padding slot (ids are -1 from there on)
+            for (int g = threadIdx.x; g < G; g += blockDim.x) {
+                int lo = 0, hi = K;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (blocks_id[(long long)g * LS + mid] >= 0) lo = mid + 1; else hi = mid; }
+                my_real += lo;
+            }
+        }
+        my_real = warp_sum(my_real);
+        if (lane_id() == 0 && my_real) atomicAdd(&s_real, my_real);
+        if (headers && out_summary) {
+            // fold the per-rank pricing headers: total count, min key, largest single count, status bits
+            for (int g = threadIdx.x; g < G; g += blockDim.x) {
+                const long long *h = headers + (long long)g * LS;
+                atomicAdd((unsigned long long *)&s_hdr[0], (unsigned long long)h[0]);
+                atomicMin(&s_hdr[1], h[1]);
+                atomicMax(&s_hdr[2], h[0]);
+                atomicOr((unsigned long long *)&s_hdr[3], (unsigned long long)h[3]);
+            }
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        const int n_out = s_real < K ? s_real : K;             // outputs past the total are padding
+        for (int i = n_out + threadIdx.x; i < K; i += blockDim.x) { out_rc[i] = INFINITY; out_id[i] = -1; }
         if (threadIdx.x == 0) {
             *out_n = n_out;
             if (headers && out_summary) {
-                // fold the per-rank pricing headers: total count, min key, largest single count, status bits
-                long long tot = 0, mn = 0x7fffffffffffffffll, mx = 0, stt = 0;
-                for (int g = 0; g < G; ++g) {
-                    const long long *h = headers + (long long)g * LS;
-                    tot += h[0]; mn = h[1] < mn ? h[1] : mn; mx = h[0] > mx ? h[0] : mx; stt |= h[3];
-                }
-                out_summary[0] = tot; out_summary[1] = mn; out_summary[2] = mx; out_summary[3] = stt;
+                out_summary[0] = s_hdr[0]; out_summary[1] = s_hdr[1]; out_summary[2] = s_hdr[2]; out_summary[3] = s_hdr[3];
             }
         }
-        __syncthreads();
     }
-    all_pairs_rank(n, load, [&](int e, int rank) {
-        if (rank < K) {
-            const long long off = (long long)(e / K) * LS + (e % K);
-            out_rc[rank] = blocks_rc[off]; out_id[rank] = blocks_id[off];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int g = e / K, i = e - g * K;
+        const KeyId mine = use_smem ? stage[e] : merge_load(blocks_rc, blocks_id, (long long)g * LS + i);
+        if (mine.key == ~0ull) continue;                       // padding
+        int rank = i;
+        for (int h = 0; h < G && rank < K; ++h) {
+            if (h == g) continue;
+            const long long base = (long long)h * LS;
+            int lo = 0, hi = K;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const KeyId other = use_smem ? stage[h * K + mid] : merge_load(blocks_rc, blocks_id, base + mid);
+                if (keyid_less(other, mine)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
         }
-    });
+        if (rank < K) { out_rc[rank] = blocks_rc[(long long)g * LS + i]; out_id[rank] = mine.id; }
+    }
+}
+
+// Merge straight out of the LL exchange buffer (sx_exchange_push_ll): staging a block in shared memory
+// IS the wait for it -- every slot is polled until both of its flags show this epoch.
+__device__ __forceinline__ bool ll_poll(const uint4 *slot, unsigned flag, unsigned long long &v,
+                                        unsigned long long t0, unsigned long long timeout_ns) {
+    for (;;) {
+        uint4 w;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(slot) : "memory");
+        if (w.y == flag && w.w == flag) { v = (unsigned long long)w.x | ((unsigned long long)w.z << 32); return true; }
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) { v = 0; return false; }
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+merge_ll_kernel(const char *ll_buf, long long block_len, int G, int K, double *__restrict__ out_rc,
+                long long *__restrict__ out_id, long long *out_n, long long *out_summary, int *status,
+                unsigned long long timeout_ns) {
+    extern __shared__ __align__(16) unsigned char mg_raw[];
+    KeyId *stage = reinterpret_cast<KeyId *>(mg_raw);
+    __shared__ int s_real;
+    __shared__ long long s_hdr[4];
+    const size_t slots_bytes = (size_t)2 * G * block_len * 16;
+    const unsigned long long epoch = *reinterpret_cast<const unsigned long long *>(ll_buf + slots_bytes);   // advanced by the push
+    const unsigned flag = (unsigned)epoch;
+    const uint4 *slots = reinterpret_cast<const uint4 *>(ll_buf) + (size_t)(epoch & 1ull) * G * block_len;
+    if (threadIdx.x == 0) { s_real = 0; s_hdr[0] = 0; s_hdr[1] = 0x7fffffffffffffffll; s_hdr[2] = 0; s_hdr[3] = 0; }
+    __syncthreads();
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const int n = G * K;
+    int my_real = 0;
+    bool ok = true;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int g = e / K, i = e - g * K;
+        const uint4 *blk = slots + (size_t)g * block_len;
+        unsigned long long rc_bits, id_bits;
+        ok = ll_poll(blk + i, flag, rc_bits, t0, timeout_ns) && ok;
+        ok = ll_poll(blk + K + i, flag, id_bits, t0, timeout_ns) && ok;
+        const long long id = (long long)id_bits;
+        const KeyId v = (id < 0 || !ok) ? KeyId{~0ull, 0x7fffffffffffffffll}
+                                        : KeyId{f64_to_sort_key(__longlong_as_double((long long)rc_bits)), id};
+        stage[e] = v;
+        my_real += v.key != ~0ull;
+    }
+    if (blockIdx.x == 0) {
+        my_real = warp_sum(my_real);
+        if (lane_id() == 0 && my_real) atomicAdd(&s_real, my_real);
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {      // fold the per-rank pricing headers
+            const uint4 *hdr = slots + (size_t)g * block_len + 2 * K;
+            unsigned long long h0, h1, h3;
+            ok = ll_poll(hdr, flag, h0, t0, timeout_ns) && ok;
+            ok = ll_poll(hdr + 1, flag, h1, t0, timeout_ns) && ok;
+            ok = ll_poll(hdr + 3, flag, h3, t0, timeout_ns) && ok;
+            atomicAdd((unsigned long long *)&s_hdr[0], h0);
+            atomicMin(&s_hdr[1], (long long)h1);
+            atomicMax(&s_hdr[2], (long long)h0);
+            atomicOr((unsigned long long *)&s_hdr[3], h3);
+        }
+    }
+    if (!ok) atomicExch(status, SX_ERR_PEER_TIMEOUT);
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        const int n_out = s_real < K ? s_real : K;
+        for (int i = n_out + threadIdx.x; i < K; i += blockDim.x) { out_rc[i] = INFINITY; out_id[i] = -1; }
+        if (threadIdx.x == 0) {
+            *out_n = n_out;
+            if (out_summary) { out_summary[0] = s_hdr[0]; out_summary[1] = s_hdr[1]; out_summary[2] = s_hdr[2]; out_summary[3] = s_hdr[3]; }
+        }
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int g = e / K, i = e - g * K;
+        const KeyId mine = stage[e];
+        if (mine.key == ~0ull) continue;
+        int rank = i;
+        for (int h = 0; h < G && rank < K; ++h) {
+            if (h == g) continue;
+            int lo = 0, hi = K;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (keyid_less(stage[h * K + mid], mine)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < K) { out_rc[rank] = sort_key_to_f64(mine.key); out_id[rank] = mine.id; }
+    }
 }
 
 // ---- large-K path helpers ---------------------------------------------------------------
@@ -779,16 +908,23 @@ extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, 
                              int64_t *out_summary, const unsigned long long *parity_ctr, int64_t parity_stride,
                              void *ws, size_t ws_bytes, void *stream) {
     if (G <= 0 || K <= 0 || !blocks_rc || !blocks_id || !out_rc || !out_id || !out_n) return SX_ERR_INVALID;
-    if (parity_ctr && G * K > 2 * kSurvCap) return SX_ERR_TOO_LARGE;
+    if (parity_ctr && G * K > (1 << 22)) return SX_ERR_TOO_LARGE;
     if (block_stride < K || ((headers == nullptr) != (out_summary == nullptr))) return SX_ERR_INVALID;
     if (G > (1 << 20) || K > (1ll << 30)) return SX_ERR_TOO_LARGE;
     if (!ws || ws_bytes < sx_topk_merge_workspace_bytes(G)) return SX_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (G * K <= 2 * kSurvCap) {
-        merge_rank_kernel<<<kNumSMs, kApThreads, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G,
+    if (G * K <= (1 << 22)) {
+        const size_t stage_bytes = (size_t)G * K * sizeof(KeyId);
+        const int use_smem = stage_bytes <= 200 * 1024;
+        const int threads = use_smem ? 1024 : 256;
+        long long mg = (G * K + threads - 1) / threads;
+        if (mg > kNumSMs * 4) mg = kNumSMs * 4;
+        if (use_smem) SX_CUDA(cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        merge_rank_kernel<<<(int)mg, threads, use_smem ? stage_bytes : 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G,
                                                           (int)K, (const long long *)headers, out_rc,
                                                           (long long *)out_id, (long long *)out_n,
-                                                          (long long *)out_summary, parity_ctr, parity_stride);
+                                                          (long long *)out_summary, parity_ctr, parity_stride,
+                                                          use_smem);
         SX_LAUNCH_CHECK();
         return SX_OK;
     }
@@ -800,6 +936,22 @@ extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, 
     SX_LAUNCH_CHECK();
     topk_rank_kernel<<<kNumSMs * 2, 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G, (int)K,
                                                   plen, poff, out_rc, (long long *)out_id);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}
+
+extern "C" int sx_topk_merge_ll(const void *ll_buf_local, int64_t block_len, int64_t G, int64_t K, double *out_rc,
+                                int64_t *out_id, int64_t *out_n, int64_t *out_summary, int32_t *status_dev,
+                                void *stream) {
+    if (!ll_buf_local || G <= 0 || K <= 0 || block_len < 2 * K + 4 || !out_rc || !out_id || !out_n || !status_dev)
+        return SX_ERR_INVALID;
+    const size_t stage_bytes = (size_t)G * K * sizeof(KeyId);
+    if (stage_bytes > 200 * 1024) return SX_ERR_TOO_LARGE;
+    SX_CUDA(cudaFuncSetAttribute(merge_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long mg = (G * K + 1023) / 1024;
+    merge_ll_kernel<<<(int)mg, 1024, stage_bytes, (cudaStream_t)stream>>>(
+        (const char *)ll_buf_local, block_len, (int)G, (int)K, out_rc, (long long *)out_id, (long long *)out_n,
+        (long long *)out_summary, status_dev, /*timeout_ns=*/10ull * 1000 * 1000 * 1000);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }

@@ -83,6 +83,9 @@ SIGNATURES = {
     "sx_exchange_buffer_bytes": (_sz, [_i64, _int]),
     "sx_exchange_epoch_offset": (_sz, [_i64, _int]),
     "sx_exchange_blocks": (_int, [_p, _i64, _p, _int, _int, _p, _p]),
+    "sx_exchange_ll_buffer_bytes": (_sz, [_i64, _int]),
+    "sx_exchange_push_ll": (_int, [_p, _i64, _p, _int, _int, _p]),
+    "sx_topk_merge_ll": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "sx_sinkhorn_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_sinkhorn_ot": (_int, [_p, _i64, _i64, _i64, _p, _p, _dbl, _i64, _dbl, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sx_price_dense_ot_h": (_int, [_p, _p, _i64, _i64, _p, _dbl, _i64, _p, _p, _p, _p, _p]),

@@ -44,7 +44,7 @@ class ShardedDensePricer:
     row-major, device resident for the life of the problem, like the reference keeps `ot.M`)."""
 
     def __init__(self, M_loc: torch.Tensor, S: int, row0: int, K: int, tol: float = dev.TOL_RC,
-                 group=None, variant: int = -1, exchange: str = "p2p", use_graph: bool = True):
+                 group=None, variant: int = -1, exchange: str = "ll", use_graph: bool = True):
         self.M = M_loc
         self.S, self.D = int(S), int(M_loc.shape[1])
         self.S_loc, self.row0 = int(M_loc.shape[0]), int(row0)
@@ -69,10 +69,14 @@ class ShardedDensePricer:
         self._m_id = self.d_out[Kp:2 * Kp]
         self._m_n = self.d_out[2 * Kp:2 * Kp + 1]
         self._m_sum = self.d_out[2 * Kp + 1:2 * Kp + 5]
-        # exchange of the result blocks: "p2p" = direct peer stores over NVLink into a symmetric buffer
-        # (sx_exchange_blocks), "nccl" = all_gather_into_tensor.  p2p needs torch symmetric memory.
+        # exchange of the result blocks over NVLink peer memory (torch symmetric memory):
+        #   "ll"   flag-in-data stores, polled by the merge kernel itself (sx_exchange_push_ll + sx_topk_merge_ll)
+        #   "p2p"  stores + release flag + wait kernel (sx_exchange_blocks), then sx_topk_merge
+        #   "nccl" all_gather_into_tensor, then sx_topk_merge
         self.exchange = exchange if self.world > 1 else "none"
-        if self.exchange == "p2p":
+        if self.exchange == "ll" and 16 * self.world * Kp > 200 * 1024:
+            self.exchange = "p2p"                       # blocks do not fit the merge kernel's shared memory
+        if self.exchange in ("ll", "p2p"):
             try:
                 self._setup_p2p(Kp)
             except Exception as e:                      # no peer access on this box: say so, use NCCL
@@ -83,14 +87,18 @@ class ShardedDensePricer:
     def _setup_p2p(self, Kp: int):
         import torch.distributed._symmetric_memory as symm
         blk = self.blk
-        n64 = lib.sx_exchange_buffer_bytes(blk, self.world) // 8
+        if self.exchange == "ll":
+            n64 = lib.sx_exchange_ll_buffer_bytes(blk, self.world) // 8
+        else:
+            n64 = lib.sx_exchange_buffer_bytes(blk, self.world) // 8
         self._symm = symm.empty(n64, dtype=torch.int64, device=self.M.device)
         self._symm.zero_()
         torch.cuda.synchronize()
         self._hdl = symm.rendezvous(self._symm, group=self.group if self.group is not None else dist.group.WORLD)
         self._rank = dist.get_rank(self.group)
-        off = lib.sx_exchange_epoch_offset(blk, self.world) // 8
-        self._epoch_ctr = self._symm[off:off + 1]
+        if self.exchange == "p2p":
+            off = lib.sx_exchange_epoch_offset(blk, self.world) // 8
+            self._epoch_ctr = self._symm[off:off + 1]
         self._xstatus = torch.zeros(1, dtype=torch.int32, device=self.M.device)
         self._h_xstatus = torch.zeros(1, dtype=torch.int32).pin_memory()
         dist.barrier(group=self.group)
@@ -101,13 +109,16 @@ class ShardedDensePricer:
         return self.pricer.launches + self._merge_launches + self._replayed_launches - self._capture_overcount
 
     # -- device-only step: everything stays on the GPU(s) --------------------------------------
-    def enqueue(self, y_dev: torch.Tensor, kernel_events=None, sorted_path: bool = False):
+    def enqueue(self, y_dev: torch.Tensor, kernel_events=None, sorted_path: bool = False, stage_events=None):
         """Enqueue one pricing pass; returns device tensors
         (rc[K], id[K], n_out, count, min key, largest per-rank count, status).  A non-zero status
         (SX_STATUS_*) means the pass must be repeated (`price` does that).  `kernel_events` =
         (start, end) CUDA events recorded around the pricing kernel launch (bench.py's roofline
-        measurement)."""
+        measurement); `stage_events` = 5 events recorded at pass start, after pricing, after the
+        selection, after the exchange and after the merge (the last two only when world > 1)."""
         p = self.pricer
+        mark = (lambda i: stage_events[i].record()) if stage_events is not None else (lambda i: None)
+        mark(0)
         p.reset()
         if kernel_events is not None:
             kernel_events[0].record()
@@ -116,11 +127,24 @@ class ShardedDensePricer:
                       self.tol, None, self.variant)
         if kernel_events is not None:
             kernel_events[1].record()
+        mark(1)
         p.select(sorted_path=sorted_path)
+        mark(2)
         Kp = max(self.K, 1)
         if self.world == 1:
             return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0], p.header[3]
         # one exchange: every rank's block (top-K + header) lands in `gathered`, consumed in place
+        if self.exchange == "ll":
+            check(lib.sx_exchange_push_ll(dev._ptr(p.block), self.blk, self._hdl.buffer_ptrs_dev, self._rank,
+                                          self.world, dev._stream()), "sx_exchange_push_ll")
+            mark(3)
+            check(lib.sx_topk_merge_ll(dev._ptr(self._symm), self.blk, self.world, Kp, dev._ptr(self._m_rc),
+                                       dev._ptr(self._m_id), dev._ptr(self._m_n), dev._ptr(self._m_sum),
+                                       dev._ptr(self._xstatus), dev._stream()), "sx_topk_merge_ll")
+            self._merge_launches += 2
+            mark(4)
+            return (self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2],
+                    self._m_sum[3])
         if self.exchange == "p2p":
             check(lib.sx_exchange_blocks(dev._ptr(p.block), self.blk, self._hdl.buffer_ptrs_dev, self._rank,
                                          self.world, dev._ptr(self._xstatus), dev._stream()), "sx_exchange_blocks")
@@ -132,12 +156,14 @@ class ShardedDensePricer:
             dist.all_gather_into_tensor(self.gathered.view(-1), p.block, group=self.group)
             gathered = self.gathered
             parity_ctr, parity_stride = None, 0
+        mark(3)
         rc, ids, hdr = block_views(gathered, Kp)
         check(lib.sx_topk_merge(dev._ptr(rc), dev._ptr(ids), gathered.stride(0), self.world, Kp, dev._ptr(hdr),
                                 dev._ptr(self._m_rc), dev._ptr(self._m_id), dev._ptr(self._m_n), dev._ptr(self._m_sum),
                                 parity_ctr, parity_stride,
                                 dev._ptr(self._merge_ws), self._merge_ws.numel(), dev._stream()), "sx_topk_merge")
         self._merge_launches += 1
+        mark(4)
         return self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2], self._m_sum[3]
 
     # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
@@ -151,7 +177,7 @@ class ShardedDensePricer:
             self.pricer.h_block.copy_(self.pricer.block, non_blocking=True)
         else:
             self.h_out.copy_(self.d_out, non_blocking=True)
-            if self.exchange == "p2p":
+            if self.exchange in ("ll", "p2p"):
                 self._h_xstatus.copy_(self._xstatus, non_blocking=True)
 
     def _capture(self):
@@ -186,8 +212,8 @@ class ShardedDensePricer:
             res = dev.PriceResult(count, float(lib.sx_key_to_f64(int(h[2 * K + 1]))),
                                   h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
             return res, status, count
-        if self.exchange == "p2p" and int(self._h_xstatus[0]) != 0:
-            check(int(self._h_xstatus[0]), "sx_exchange_blocks")
+        if self.exchange in ("ll", "p2p") and int(self._h_xstatus[0]) != 0:
+            check(int(self._h_xstatus[0]), "peer exchange")
         h = self.h_out.numpy()
         n_out = int(h[2 * K]) if self.K > 0 else 0
         res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),

@@ -449,6 +449,53 @@ def test_price_row_slabs_and_merge(dev):
     assert np.array_equal(out_rc[:k].cpu().numpy(), whole.topk_rc)
 
 
+@pytest.mark.parametrize("G,K", [(2, 128), (8, 1024), (5, 33)])
+def test_ll_exchange_and_merge_with_emulated_ranks(dev, G, K):
+    """The flag-in-data exchange on one GPU: G buffers stand for G ranks, every "rank" pushes its block
+    into all of them (a push never waits), then the merge polls / stages / ranks out of buffer 0.
+    Result == sx_topk_merge on the same blocks == the oracle's global top-K.  Two epochs (both halves)."""
+    import ctypes
+    from smart_crossover._native import check, lib
+    S, D = 64 * G, 700
+    s, d, M = cases.ot_points(S, D, 5 + G)
+    Mt = cu(M)
+    blk = 2 * K + dev.Pricer.BLOCK_TAIL
+    nbytes = lib.sx_exchange_ll_buffer_bytes(blk, G)
+    bufs = [torch.zeros(nbytes // 8, dtype=torch.int64, device="cuda") for _ in range(G)]
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rows = S // G
+    for epoch, noise in ((1, 0.05), (2, 0.2)):
+        y = cases.planted_duals(M, 7 * epoch, noise)
+        yt = cu(y)
+        whole = dev.price_dense_ot(Mt, yt, K=K)
+        blocks = []
+        for g in range(G):
+            pr = dev.Pricer(torch.device("cuda"), K)
+            pr.reset()
+            pr.price_dense(Mt[g * rows:(g + 1) * rows], D, g * rows, rows, D, yt[g * rows:(g + 1) * rows], yt[S:])
+            pr.select()
+            blocks.append(pr.block.clone())
+            # rank g's view of the peers: entry g is its own buffer, which holds the epoch counter it reads
+            ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+            check(lib.sx_exchange_push_ll(dev._ptr(blocks[-1]), blk, dev._ptr(ptrs), g, G, dev._stream()), "push")
+        torch.cuda.synchronize()
+        out = torch.zeros(2 * K + 6, dtype=torch.int64, device="cuda")
+        check(lib.sx_topk_merge_ll(dev._ptr(bufs[0]), blk, G, K, dev._ptr(out[:K]), dev._ptr(out[K:2 * K]),
+                                   dev._ptr(out[2 * K:]), dev._ptr(out[2 * K + 1:]), dev._ptr(status), dev._stream()),
+              "merge_ll")
+        h = out.cpu().numpy()
+        k = int(h[2 * K])
+        assert int(status.item()) == 0 and k == whole.topk_id.size
+        assert np.array_equal(h[K:K + k], whole.topk_id) and np.array_equal(h[:k].view(np.float64), whole.topk_rc)
+        assert int(h[2 * K + 1]) == whole.n_violating and h[2 * K + 2] == np.float64(whole.min_rc).view(np.int64) \
+            or lib.sx_key_to_f64(int(h[2 * K + 2])) == whole.min_rc
+        assert int(h[2 * K + 4]) == 0 and np.all(h[K + k:2 * K] == -1)
+        # the plain merge on the same blocks agrees
+        stack = torch.stack(blocks)
+        o_rc, o_id, o_n = dev.topk_merge(stack[:, :K].view(torch.float64), stack[:, K:2 * K])
+        assert int(o_n.item()) == k and np.array_equal(o_id[:k].cpu().numpy(), whole.topk_id)
+
+
 @pytest.mark.parametrize("name", MCF_FULL)
 def test_mcf_scores_queue_and_arc_pricing_golden(dev, name):
     import scipy.sparse as sp
