@@ -709,17 +709,39 @@ merge_ll_kernel(const char *ll_buf, long long block_len, int G, int K, double *_
     const int n = G * K;
     int my_real = 0;
     bool ok = true;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        const int g = e / K, i = e - g * K;
-        const uint4 *blk = slots + (size_t)g * block_len;
-        unsigned long long rc_bits, id_bits;
-        ok = ll_poll(blk + i, flag, rc_bits, t0, timeout_ns) && ok;
-        ok = ll_poll(blk + K + i, flag, id_bits, t0, timeout_ns) && ok;
-        const long long id = (long long)id_bits;
-        const KeyId v = (id < 0 || !ok) ? KeyId{~0ull, 0x7fffffffffffffffll}
-                                        : KeyId{f64_to_sort_key(__longlong_as_double((long long)rc_bits)), id};
-        stage[e] = v;
-        my_real += v.key != ~0ull;
+    // kLlBatch elements per thread are requested before any is examined (one L2 round trip per batch
+    // when the data is already there); a slot that is not ready yet is polled again by ll_poll
+    constexpr int kLlBatch = 4;
+    for (int e0 = threadIdx.x; e0 < n; e0 += blockDim.x * kLlBatch) {
+        uint4 wr[kLlBatch], wi[kLlBatch];
+#pragma unroll
+        for (int u = 0; u < kLlBatch; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < n) {
+                const int g = e / K, i = e - g * K;
+                const uint4 *blk = slots + (size_t)g * block_len;
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(wr[u].x), "=r"(wr[u].y), "=r"(wr[u].z), "=r"(wr[u].w) : "l"(blk + i) : "memory");
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(wi[u].x), "=r"(wi[u].y), "=r"(wi[u].z), "=r"(wi[u].w) : "l"(blk + K + i) : "memory");
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kLlBatch; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e >= n) continue;
+            const int g = e / K, i = e - g * K;
+            const uint4 *blk = slots + (size_t)g * block_len;
+            unsigned long long rc_bits = (unsigned long long)wr[u].x | ((unsigned long long)wr[u].z << 32);
+            unsigned long long id_bits = (unsigned long long)wi[u].x | ((unsigned long long)wi[u].z << 32);
+            if (wr[u].y != flag || wr[u].w != flag) ok = ll_poll(blk + i, flag, rc_bits, t0, timeout_ns) && ok;
+            if (wi[u].y != flag || wi[u].w != flag) ok = ll_poll(blk + K + i, flag, id_bits, t0, timeout_ns) && ok;
+            const long long id = (long long)id_bits;
+            const KeyId v = (id < 0 || !ok) ? KeyId{~0ull, 0x7fffffffffffffffll}
+                                            : KeyId{f64_to_sort_key(__longlong_as_double((long long)rc_bits)), id};
+            stage[e] = v;
+            my_real += v.key != ~0ull;
+        }
     }
     if (blockIdx.x == 0) {
         my_real = warp_sum(my_real);
