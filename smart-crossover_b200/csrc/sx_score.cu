@@ -5,6 +5,8 @@
 // (net_manager.py:165-182).  Both must be bit-exact with NumPy/SciPy: correctly rounded
 // IEEE fp64 division, NumPy `maximum` semantics, no FMA contraction (built with -fmad=false)
 // and, for K1b, per-node sums taken sequentially in ascending arc id (csr_matvec order).
+#include <math.h>
+
 #include "sx_common.cuh"
 
 namespace sx {
@@ -12,6 +14,15 @@ namespace sx {
 // NumPy: maximum(a, b) = isnan(a) ? a : (a > b ? a : b)
 __device__ __forceinline__ double np_maximum(double a, double b) {
     return (a != a) ? a : (a > b ? a : b);
+}
+
+// max(x / s, x / d) with ONE division when that is provably the same double: correctly rounded
+// division is monotone in the divisor, so for finite x >= 0 and s, d > 0 the larger quotient is
+// x / min(s, d), bit for bit (equal quotients are the same value either way).  Anything else
+// (negative, NaN or infinite x, non-positive or NaN marginals) takes the literal two-division form.
+__device__ __forceinline__ double ot_score(double x, double s, double d) {
+    if (x >= 0.0 && x < INFINITY && s > 0.0 && d > 0.0) return x / (s < d ? s : d);
+    return np_maximum(x / s, x / d);
 }
 
 constexpr int kScThreads = 256;
@@ -34,7 +45,7 @@ score_ot_kernel(const double *__restrict__ x, const double *__restrict__ s, cons
 #pragma unroll
         for (int q = 0; q < kScCols; ++q) {
             const long long j = j0 + (long long)q * kScThreads;
-            if (j < D) out[i * D + j] = np_maximum(xv[q] / si, xv[q] / dv[q]);
+            if (j < D) out[i * D + j] = ot_score(xv[q], si, dv[q]);
         }
     }
 }

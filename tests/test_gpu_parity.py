@@ -45,6 +45,33 @@ def sort_pipeline(dev, key_t):
 
 
 # ---- K1a + K1c ------------------------------------------------------------------------------
+def test_ot_scores_special_values_bitwise(dev):
+    """K1a against NumPy on the awkward inputs: negative / zero / -0.0 / inf / NaN flows, zero, negative,
+    infinite and NaN marginals, denormals, and 2e5 random positive triples (the one-division fast path
+    must give the same bits as max(x / s, x / d))."""
+    rng = np.random.default_rng(0)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 3.3e-310, 1e-300, 1e300, np.inf, -np.inf, np.nan, 0.1, 7.0])
+    S = D = special.size
+    s = special.copy()
+    d = special[::-1].copy()
+    X = np.tile(special, (S, 1)).T.copy()                      # x varies along rows, d along columns
+    X2 = rng.permuted(np.tile(special, (S, 1)), axis=1)
+    for xs in (X, X2):
+        with np.errstate(all="ignore"):
+            ref = np.maximum(xs / s[:, None], xs / d[None, :]).ravel()
+        got = dev.score_ot(cu(xs.ravel()), cu(s), cu(d)).cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        ok = ~np.isnan(ref)
+        assert got[ok].tobytes() == ref[ok].tobytes()
+    S, D = 400, 500
+    s = 10.0 ** rng.uniform(-8, 3, S)
+    d = 10.0 ** rng.uniform(-8, 3, D)
+    x = 10.0 ** rng.uniform(-12, 2, S * D)
+    x[rng.random(x.size) < 0.05] = 0.0
+    ref = np.maximum(x.reshape(S, D) / s[:, None], x.reshape(S, D) / d[None, :]).ravel()
+    assert dev.score_ot(cu(x), cu(s), cu(d)).cpu().numpy().tobytes() == ref.tobytes()
+
+
 @pytest.mark.parametrize("name", OT_FULL + ["ot_zero_3x3"])
 def test_ot_scores_and_orders_golden(dev, name):
     fx = Fixture(name)
