@@ -37,9 +37,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // Arrive that cannot be issued before `dep` is known.  A consumer releases a stage once its data
 // is in registers; "the loads were issued" is not enough (an LDS queued behind global atomics can
 // still be in flight when the arrive lets the producer's TMA overwrite the stage), so the release
