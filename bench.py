@@ -273,9 +273,9 @@ def time_tree_build(S, D, device, reps=3):
     for _ in range(reps + 1):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         ev[0].record()
-        F = dev.score_ot(x, s, d)
+        F, hist = dev.score_ot(x, s, d, want_hist=True)
         ev[1].record()
-        head = dev.kruskal_prefix(F, 16 * N)
+        head = dev.kruskal_prefix(F, 16 * N, hist=hist)
         ev[2].record()
         tree, n_tree = dev.kruskal(head, N, S=S, D=D)
         ev[3].record()

@@ -79,14 +79,16 @@ SX_API double      sx_key_to_f64(long long key);        /* decode sx_price_heade
 /* ---- K1: flow indicators ------------------------------------------------------------
  * sx_score_ot replaces `np.maximum(X / s[:,None], X / d[None,:])`, net_manager.py:377-378.
  *   x (S*D), s (S), d (D) -> score_out (S*D).  Correctly rounded IEEE divisions; NumPy
- *   `maximum` semantics (NaN propagates).
+ *   `maximum` semantics (NaN propagates).  hist12_out (may be NULL; 4096 uint32, zeroed by the
+ *   caller): histogram of the scores' top 12 key bits, accumulated while the scores are written,
+ *   which sx_kruskal_prefix accepts instead of taking it with a pass of its own.
  * sx_score_mcf replaces net_manager.py:165-182: reversal of arcs with x > u/2, per-node
  *   out/in sums in ascending arc id (SciPy csr_matvec order), f_inv = 1/max(f1,f2),
  *   indicator = max over the two end nodes of |f_inv * x_hat|.  node_ptr (N+1) /
  *   node_arc / node_sign are the CSR arrays of the incidence matrix A (formats.py:118).
  */
 SX_API int    sx_score_ot(const double *x, const double *s, const double *d, int64_t S, int64_t D,
-                   double *score_out, void *stream);
+                   double *score_out, uint32_t *hist12_out, void *stream);
 SX_API size_t sx_score_mcf_workspace_bytes(int64_t N, int64_t E);
 SX_API int    sx_score_mcf(const double *x, const double *u, const int32_t *tail, const int32_t *head,
                     const int64_t *node_ptr, const int32_t *node_arc, const int8_t *node_sign,
@@ -122,15 +124,18 @@ SX_API int    sx_kruskal_order(const double *sorted_key, const uint32_t *order_a
  * bits of its order-preserving image), in Kruskal order (descending weight, ties by ascending
  * arc id), i.e. exactly the first *n_prefix_h entries of what sx_argsort_f64 + sx_kruskal_order
  * would produce.  Three streaming passes over the weights (24 B per arc) instead of ~256 B per arc.
+ *   hist12 (may be NULL): the 4096-bin histogram of the weights' top 12 key bits if the caller has
+ *   it already (sx_score_ot / sx_hist12_f64), which saves the first pass.
  *   korder_out: capacity T_cap >= T.  *n_prefix_h (HOST) = number of arcs written, or -1 when more
  *   than T_cap arcs tie at the threshold (use the full argsort then).  Synchronises the stream once.
  * The caller runs sx_kruskal on the prefix and falls back to the full order if the forest is not
  * complete within it.
  */
 SX_API size_t sx_kruskal_prefix_workspace_bytes(int64_t T_cap);
+SX_API int    sx_hist12_f64(const double *weight, int64_t n, uint32_t *hist12, void *stream);
 SX_API int    sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int64_t T_cap,
-                         uint32_t *korder_out, int64_t *n_prefix_h, void *ws, size_t ws_bytes,
-                         void *stream);
+                         const uint32_t *hist12, uint32_t *korder_out, int64_t *n_prefix_h,
+                         void *ws, size_t ws_bytes, void *stream);
 
 /* ---- K2: spanning-tree basis identification -------------------------------------------
  * Replaces `sp.csgraph.minimum_spanning_tree(-w)` + flatnonzero, tree_BI.py:32-59.

@@ -35,7 +35,7 @@ struct PrefixCtl {
 // LEVEL 0: digit = bits 63..52 of the image.  LEVEL 1: bits 51..40, only for keys whose level-0 digit is b1.
 template <int LEVEL>
 __global__ void __launch_bounds__(kPfThreads)
-pf_hist_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl) {
+pf_hist_kernel(const double *__restrict__ w, long long n, const PrefixCtl *ctl, unsigned *__restrict__ hist_out) {
     __shared__ unsigned sh[kPfSub][kPfBins];
     for (int i = threadIdx.x; i < kPfSub * kPfBins; i += kPfThreads) (&sh[0][0])[i] = 0;
     __syncthreads();
@@ -74,7 +74,7 @@ pf_hist_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl) {
         unsigned c = 0;
 #pragma unroll
         for (int s = 0; s < kPfSub; ++s) c += sh[s][i];
-        if (c) atomicAdd(&ctl->hist[LEVEL][i], c);
+        if (c) atomicAdd(&hist_out[i], c);
     }
 }
 
@@ -240,8 +240,17 @@ extern "C" size_t sx_kruskal_prefix_workspace_bytes(int64_t T_cap) {
            sx_argsort_workspace_bytes(T_cap) + sx_kruskal_order_workspace_bytes(T_cap) + 256;
 }
 
-extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int64_t T_cap, uint32_t *korder_out,
-                                 int64_t *n_prefix_h, void *ws, size_t ws_bytes, void *stream) {
+// hist[bin] += number of weights whose order-preserving image has top 12 bits == bin (4096 bins).
+extern "C" int sx_hist12_f64(const double *weight, int64_t n, uint32_t *hist12, void *stream) {
+    if (!weight || !hist12 || n < 0) return SX_ERR_INVALID;
+    if (n == 0) return SX_OK;
+    pf_hist_kernel<0><<<pf_grid(n, 16), kPfThreads, 0, (cudaStream_t)stream>>>(weight, n, nullptr, hist12);
+    SX_LAUNCH_CHECK();
+    return SX_OK;
+}
+
+extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int64_t T_cap, const uint32_t *hist12,
+                                 uint32_t *korder_out, int64_t *n_prefix_h, void *ws, size_t ws_bytes, void *stream) {
     if (!weight || n <= 0 || T <= 0 || T_cap < T || !korder_out || !n_prefix_h) return SX_ERR_INVALID;
     if (n >= (1ll << 32)) return SX_ERR_TOO_LARGE;
     if (!ws || ws_bytes < sx_kruskal_prefix_workspace_bytes(T_cap)) return SX_ERR_WORKSPACE;
@@ -263,11 +272,15 @@ extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int
 
     SX_CUDA(cudaMemsetAsync(ctl, 0, sizeof(PrefixCtl), st));
     const int grid = pf_grid(n, 16);
-    pf_hist_kernel<0><<<grid, kPfThreads, 0, st>>>(weight, n, ctl);
-    SX_LAUNCH_CHECK();
+    if (hist12) {   // level-0 histogram already taken (sx_score_ot produced it while writing the scores)
+        SX_CUDA(cudaMemcpyAsync(ctl->hist[0], hist12, sizeof(unsigned) * kPfBins, cudaMemcpyDeviceToDevice, st));
+    } else {
+        pf_hist_kernel<0><<<grid, kPfThreads, 0, st>>>(weight, n, ctl, ctl->hist[0]);
+        SX_LAUNCH_CHECK();
+    }
     pf_bound_kernel<0><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
     SX_LAUNCH_CHECK();
-    pf_hist_kernel<1><<<grid, kPfThreads, 0, st>>>(weight, n, ctl);
+    pf_hist_kernel<1><<<grid, kPfThreads, 0, st>>>(weight, n, ctl, ctl->hist[1]);
     SX_LAUNCH_CHECK();
     pf_bound_kernel<1><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
     SX_LAUNCH_CHECK();

@@ -50,6 +50,65 @@ score_ot_kernel(const double *__restrict__ x, const double *__restrict__ s, cons
     }
 }
 
+// Vector form: two adjacent columns per 128-bit access (needs even D and 16-byte aligned x / out),
+// kScCols pairs per thread.  Optionally accumulates the 4096-bin histogram of the scores' top 12 key
+// bits (sign + exponent) that sx_kruskal_prefix would otherwise compute with a pass of its own: the
+// scores are already in registers here.  Shared-memory privatised (two sub-histograms, run-length
+// cached), flushed once per CTA.
+constexpr int kScBins = 4096;
+
+template <bool HIST>
+__global__ void __launch_bounds__(kScThreads)
+score_ot_vec_kernel(const double *__restrict__ x, const double *__restrict__ s, const double *__restrict__ d,
+                    long long S, long long D, long long col_blocks, double *__restrict__ out,
+                    unsigned *__restrict__ hist) {
+    __shared__ unsigned sh[HIST ? 2 : 1][HIST ? kScBins : 1];
+    unsigned *mine = sh[HIST ? (threadIdx.x & 1) : 0];
+    unsigned run_d = 0xffffffffu, run_c = 0;
+    if (HIST) {
+        for (int i = threadIdx.x; i < 2 * kScBins; i += kScThreads) (&sh[0][0])[i] = 0;
+        __syncthreads();
+    }
+    auto count = [&](double v) {
+        const unsigned dg = (unsigned)(f64_to_sort_key(v) >> 52);
+        if (dg == run_d) { ++run_c; return; }
+        if (run_c) atomicAdd(&mine[run_d], run_c);
+        run_d = dg; run_c = 1;
+    };
+    const long long D2 = D / 2;
+    const long long tiles = S * col_blocks;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long i = t / col_blocks;
+        const long long p0 = (t - i * col_blocks) * (kScThreads * kScCols) + threadIdx.x;   // pair index in the row
+        const double si = __ldg(s + i);
+        const double2 *xr = reinterpret_cast<const double2 *>(x + i * D);
+        double2 *orow = reinterpret_cast<double2 *>(out + i * D);
+        double2 xv[kScCols], dv[kScCols];
+#pragma unroll
+        for (int q = 0; q < kScCols; ++q) {
+            const long long pj = p0 + (long long)q * kScThreads;
+            if (pj < D2) { xv[q] = __ldcs(xr + pj); dv[q] = __ldg(reinterpret_cast<const double2 *>(d) + pj); }
+        }
+#pragma unroll
+        for (int q = 0; q < kScCols; ++q) {
+            const long long pj = p0 + (long long)q * kScThreads;
+            if (pj < D2) {
+                const double2 r = make_double2(ot_score(xv[q].x, si, dv[q].x), ot_score(xv[q].y, si, dv[q].y));
+                orow[pj] = r;
+                if (HIST) { count(r.x); count(r.y); }
+            }
+        }
+    }
+    if (HIST) {
+        if (run_c) atomicAdd(&mine[run_d], run_c);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kScBins; i += kScThreads) {
+            const unsigned c = sh[0][i] + sh[1][i];
+            if (c) atomicAdd(&hist[i], c);
+        }
+    }
+}
+
 // ---- K1b ----------------------------------------------------------------------------------
 // x_hat and the reversal flag, net_manager.py:166-168 evaluated literally:
 //   x_hat = x * (~mask) + u * mask - x * mask ;  x_hat[(x < 0) | (x > u)] = 0
@@ -117,15 +176,28 @@ static int grid_for(long long n, int threads) {
 using namespace sx;
 
 extern "C" int sx_score_ot(const double *x, const double *s, const double *d, int64_t S, int64_t D,
-                           double *score_out, void *stream) {
+                           double *score_out, uint32_t *hist12_out, void *stream) {
     if (S < 0 || D < 0) return SX_ERR_INVALID;
     if (S == 0 || D == 0) return SX_OK;
     if (!x || !s || !d || !score_out) return SX_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (D % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(score_out) |
+                                       reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+    if (vec) {
+        const long long col_blocks = (D / 2 + kScThreads * kScCols - 1) / (kScThreads * kScCols);
+        const long long tiles = S * col_blocks;
+        const long long grid = tiles < (long long)kNumSMs * 8 ? tiles : (long long)kNumSMs * 8;
+        if (hist12_out) score_ot_vec_kernel<true><<<(int)grid, kScThreads, 0, st>>>(x, s, d, S, D, col_blocks, score_out, hist12_out);
+        else score_ot_vec_kernel<false><<<(int)grid, kScThreads, 0, st>>>(x, s, d, S, D, col_blocks, score_out, nullptr);
+        SX_LAUNCH_CHECK();
+        return SX_OK;
+    }
     const long long col_blocks = (D + kScThreads * kScCols - 1) / (kScThreads * kScCols);
     long long tiles = S * col_blocks;
     long long grid = tiles < (long long)kNumSMs * 16 ? tiles : (long long)kNumSMs * 16;
-    score_ot_kernel<<<(int)grid, kScThreads, 0, (cudaStream_t)stream>>>(x, s, d, S, D, col_blocks, score_out);
+    score_ot_kernel<<<(int)grid, kScThreads, 0, st>>>(x, s, d, S, D, col_blocks, score_out);
     SX_LAUNCH_CHECK();
+    if (hist12_out) return sx_hist12_f64(score_out, S * D, hist12_out, stream);      // unaligned shapes: separate pass
     return SX_OK;
 }
 

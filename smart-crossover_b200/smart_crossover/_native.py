@@ -53,7 +53,7 @@ SIGNATURES = {
     "sx_error_string": (ctypes.c_char_p, [_int]),
     "sx_last_cuda_error": (_int, []),
     "sx_key_to_f64": (_dbl, [ctypes.c_longlong]),
-    "sx_score_ot": (_int, [_p, _p, _p, _i64, _i64, _p, _p]),
+    "sx_score_ot": (_int, [_p, _p, _p, _i64, _i64, _p, _p, _p]),
     "sx_score_mcf_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_score_mcf": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "sx_sort_set_tuning": (_int, [_int]),
@@ -64,7 +64,8 @@ SIGNATURES = {
     "sx_kruskal_order_workspace_bytes": (_sz, [_i64]),
     "sx_kruskal_order": (_int, [_p, _p, _i64, _p, _p, _sz, _p]),
     "sx_kruskal_prefix_workspace_bytes": (_sz, [_i64]),
-    "sx_kruskal_prefix": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "sx_hist12_f64": (_int, [_p, _i64, _p, _p]),
+    "sx_kruskal_prefix": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "sx_kruskal_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_kruskal": (_int, [_p, _i64, _p, _p, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "sx_tree_potentials_workspace_bytes": (_sz, [_i64]),

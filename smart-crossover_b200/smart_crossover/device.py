@@ -45,12 +45,14 @@ def _f64(t, device=None):
 
 
 # ---- K1 ------------------------------------------------------------------------------------
-def score_ot(x: torch.Tensor, s: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
-    """Flow indicators max(x_ij/s_i, x_ij/d_j); reference net_manager.py:377-378."""
+def score_ot(x: torch.Tensor, s: torch.Tensor, d: torch.Tensor, want_hist: bool = False):
+    """Flow indicators max(x_ij/s_i, x_ij/d_j); reference net_manager.py:377-378.  With want_hist also
+    returns the 4096-bin histogram of the scores' top key bits (input of `kruskal_prefix`)."""
     S, D = s.numel(), d.numel()
     out = torch.empty(S * D, dtype=torch.float64, device=x.device)
-    check(lib.sx_score_ot(_ptr(x), _ptr(s), _ptr(d), S, D, _ptr(out), _stream()), "sx_score_ot")
-    return out
+    hist = torch.zeros(4096, dtype=torch.int32, device=x.device) if want_hist else None
+    check(lib.sx_score_ot(_ptr(x), _ptr(s), _ptr(d), S, D, _ptr(out), _ptr(hist), _stream()), "sx_score_ot")
+    return (out, hist) if want_hist else out
 
 
 def score_mcf(x, u, tail, head, node_ptr, node_arc, node_sign) -> torch.Tensor:
@@ -92,7 +94,7 @@ def kruskal_order(sorted_key: torch.Tensor, order: torch.Tensor) -> torch.Tensor
     return out
 
 
-def kruskal_prefix(weights: torch.Tensor, T: int, T_cap: int | None = None):
+def kruskal_prefix(weights: torch.Tensor, T: int, T_cap: int | None = None, hist: torch.Tensor | None = None):
     """Head of the Kruskal order (descending weight, ties by ascending id): every arc at least as heavy
     as the T-th heaviest.  Returns an int32 tensor (uint32 bit patterns) or None when more than T_cap
     arcs tie at the threshold (the caller then sorts everything).  One stream synchronisation."""
@@ -102,8 +104,8 @@ def kruskal_prefix(weights: torch.Tensor, T: int, T_cap: int | None = None):
     out = torch.empty(T_cap, dtype=torch.int32, device=weights.device)
     ws = _ws(lib.sx_kruskal_prefix_workspace_bytes(T_cap), weights.device)
     n_prefix = ctypes.c_int64(0)
-    check(lib.sx_kruskal_prefix(_ptr(weights), n, T, T_cap, _ptr(out), ctypes.byref(n_prefix), _ptr(ws), ws.numel(),
-                                _stream()), "sx_kruskal_prefix")
+    check(lib.sx_kruskal_prefix(_ptr(weights), n, T, T_cap, _ptr(hist), _ptr(out), ctypes.byref(n_prefix), _ptr(ws),
+                                ws.numel(), _stream()), "sx_kruskal_prefix")
     if n_prefix.value < 0:
         return None
     return out[:n_prefix.value]

@@ -197,8 +197,16 @@ class ShardedDensePricer:
             dist.barrier(group=self.group)                 # every rank did the same number of exchanges
         launches = self.launches
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._step()
+        try:
+            with torch.cuda.graph(g):
+                self._step()
+        except Exception as e:                             # capture refused (driver / allocator state): stay eager
+            import warnings
+            warnings.warn(f"CUDA graph capture of the pricing step failed ({type(e).__name__}: {e}); running eagerly")
+            self._capture_overcount += self.launches - launches
+            self.use_graph = False
+            torch.cuda.synchronize()
+            return
         self._graph_launches = self.launches - launches
         self._capture_overcount += self._graph_launches       # recorded, not executed
         self._graph = g
@@ -223,7 +231,10 @@ class ShardedDensePricer:
     def price(self, y_host: np.ndarray) -> dev.PriceResult:
         """One pass from a host vector of duals: copy into pinned memory, replay the captured step
         (H2D, pricing, selection, exchange + merge, D2H), one synchronisation, read the result."""
-        self.h_y.numpy()[:] = y_host
+        r0, r1 = self.row0, self.row0 + self.S_loc
+        hy = self.h_y.numpy()
+        hy[r0:r1] = y_host[r0:r1]                          # only what this rank uploads
+        hy[self.S:] = y_host[self.S:self.S + self.D]
         if self._graph is None and self.use_graph and not self._capture_tried:
             self._capture_tried = True
             self._capture()

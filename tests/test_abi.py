@@ -55,7 +55,7 @@ def test_workspace_queries_and_argument_validation_without_gpu():
     assert lib.sx_kruskal_workspace_bytes(80, 1600) > 0
     assert lib.sx_tree_potentials_workspace_bytes(80) > 0
     assert lib.sx_topk_workspace_bytes(1 << 20, 1024) > 0
-    assert lib.sx_score_ot(None, None, None, 3, 3, None, None) == -1
+    assert lib.sx_score_ot(None, None, None, 3, 3, None, None, None) == -1
     assert lib.sx_argsort_f64(None, 10, None, None, None, 0, None) == -1
     assert lib.sx_price_dense_ot(None, 4, 0, 4, 4, None, None, 1e-6, None, None, None, None, 0, None, 0, -1, None) == -1
     assert lib.sx_select_state_bytes() >= 2 * 1024 * 1024

@@ -221,6 +221,14 @@ def test_kruskal_prefix_is_the_head_of_the_full_order(dev, S, D, T, kind):
     # capacity too small for the ties at the threshold: the caller is told to sort everything
     if kind == "ties":
         assert dev.kruskal_prefix(cu(F), 10, T_cap=12) is None
+    # the level-0 histogram taken by the score kernel (vector path when D is even) gives the same head
+    Ft, hist = dev.score_ot(cu(x), cu(s), cu(d), want_hist=True)
+    assert Ft.cpu().numpy().tobytes() == F.tobytes()
+    keys = F.view(np.uint64) | np.uint64(1 << 63)                     # scores are >= 0: image = bits | sign
+    ref_hist = np.bincount((keys >> np.uint64(52)).astype(np.int64), minlength=4096)
+    assert np.array_equal(hist.cpu().numpy().astype(np.int64), ref_hist)
+    head2 = dev.kruskal_prefix(Ft, T, T_cap=S * D, hist=hist)
+    assert np.array_equal(head2.cpu().numpy().view(np.uint32), head)
 
 
 def test_tree_from_prefix_equals_tree_from_full_sort(dev):
