@@ -514,7 +514,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu:
-        rows_h = min(S_loc, 2048)
+        rows_h = min(S_loc, 16384)                       # ~5e8-1e9 arcs: a few seconds of single-core NumPy per repetition
         M_h = M_loc[:rows_h].cpu().numpy()
         y_h = np.concatenate([y_host[row0:row0 + rows_h], y_host[S:]])
         rate, dt = cpu_price_rate(M_h, y_h, K, 1, 2)

@@ -56,14 +56,15 @@ class ShardedDensePricer:
         self.use_graph = bool(use_graph)
         self._graph, self._capture_tried, self._graph_launches, self._replayed_launches = None, False, 0, 0
         self._capture_overcount = 0
-        self.y_dev = torch.empty(self.S + self.D, dtype=torch.float64, device=M_loc.device)
-        self.h_y = torch.empty(self.S + self.D, dtype=torch.float64).pin_memory()
+        self.y_loc = torch.empty(self.S_loc + self.D, dtype=torch.float64, device=M_loc.device)
+        self.h_yloc = torch.empty(self.S_loc + self.D, dtype=torch.float64).pin_memory()
         Kp = max(self.K, 1)
         self.blk = 2 * Kp + dev.Pricer.BLOCK_TAIL
         self.gathered = torch.empty(self.world, self.blk, dtype=torch.int64, device=M_loc.device)
-        # merged result: [K rc | K ids | n_out | total count, min key, largest per-rank count, status]
+        # merged result: [K rc | K ids | n_out | total count, min key, largest per-rank count, status | exchange status]
         self.h_out = torch.empty(2 * Kp + 6, dtype=torch.int64).pin_memory()
         self.d_out = torch.zeros(2 * Kp + 6, dtype=torch.int64, device=M_loc.device)
+        self._xstatus = self.d_out[2 * Kp + 5:2 * Kp + 6].view(torch.int32)[:1]   # written by the exchange / merge kernels
         self._merge_ws = dev._ws(lib.sx_topk_merge_workspace_bytes(self.world), M_loc.device)
         self._m_rc = self.d_out[:Kp].view(torch.float64)
         self._m_id = self.d_out[Kp:2 * Kp]
@@ -99,8 +100,6 @@ class ShardedDensePricer:
         if self.exchange == "p2p":
             off = lib.sx_exchange_epoch_offset(blk, self.world) // 8
             self._epoch_ctr = self._symm[off:off + 1]
-        self._xstatus = torch.zeros(1, dtype=torch.int32, device=self.M.device)
-        self._h_xstatus = torch.zeros(1, dtype=torch.int32).pin_memory()
         dist.barrier(group=self.group)
 
     @property
@@ -109,21 +108,24 @@ class ShardedDensePricer:
         return self.pricer.launches + self._merge_launches + self._replayed_launches - self._capture_overcount
 
     # -- device-only step: everything stays on the GPU(s) --------------------------------------
-    def enqueue(self, y_dev: torch.Tensor, kernel_events=None, sorted_path: bool = False, stage_events=None):
+    def enqueue(self, y_dev: torch.Tensor, kernel_events=None, sorted_path: bool = False, stage_events=None,
+                y_parts=None):
         """Enqueue one pricing pass; returns device tensors
         (rc[K], id[K], n_out, count, min key, largest per-rank count, status).  A non-zero status
         (SX_STATUS_*) means the pass must be repeated (`price` does that).  `kernel_events` =
         (start, end) CUDA events recorded around the pricing kernel launch (bench.py's roofline
         measurement); `stage_events` = 5 events recorded at pass start, after pricing, after the
-        selection, after the exchange and after the merge (the last two only when world > 1)."""
+        selection, after the exchange and after the merge (the last two only when world > 1).
+        `y_parts` = (source duals of this rank's rows, sink duals) replaces the slices of `y_dev`."""
         p = self.pricer
+        y_src, y_dst = y_parts if y_parts is not None else (y_dev[self.row0:self.row0 + self.S_loc],
+                                                              y_dev[self.S:self.S + self.D])
         mark = (lambda i: stage_events[i].record()) if stage_events is not None else (lambda i: None)
         mark(0)
         p.reset()
         if kernel_events is not None:
             kernel_events[0].record()
-        p.price_dense(self.M, self.M.stride(0), self.row0, self.S_loc, self.D,
-                      y_dev[self.row0:self.row0 + self.S_loc], y_dev[self.S:self.S + self.D],
+        p.price_dense(self.M, self.M.stride(0), self.row0, self.S_loc, self.D, y_src, y_dst,
                       self.tol, None, self.variant)
         if kernel_events is not None:
             kernel_events[1].record()
@@ -169,16 +171,12 @@ class ShardedDensePricer:
     # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
     def _step(self, sorted_path: bool = False):
         """H2D of the duals this rank needs (its rows + every sink), one pass, D2H of the result."""
-        r0, r1 = self.row0, self.row0 + self.S_loc
-        self.y_dev[r0:r1].copy_(self.h_y[r0:r1], non_blocking=True)
-        self.y_dev[self.S:].copy_(self.h_y[self.S:], non_blocking=True)
-        self.enqueue(self.y_dev, sorted_path=sorted_path)
+        self.y_loc.copy_(self.h_yloc, non_blocking=True)          # [this rank's S_loc source duals | D sink duals]
+        self.enqueue(None, sorted_path=sorted_path, y_parts=(self.y_loc[:self.S_loc], self.y_loc[self.S_loc:]))
         if self.world == 1:
             self.pricer.h_block.copy_(self.pricer.block, non_blocking=True)
         else:
-            self.h_out.copy_(self.d_out, non_blocking=True)
-            if self.exchange in ("ll", "p2p"):
-                self._h_xstatus.copy_(self._xstatus, non_blocking=True)
+            self.h_out.copy_(self.d_out, non_blocking=True)        # result, summary and exchange status in one copy
 
     def _capture(self):
         """Record one step (copies + kernels) in a CUDA graph: one launch call per pass instead of ~8.
@@ -220,9 +218,10 @@ class ShardedDensePricer:
             res = dev.PriceResult(count, float(lib.sx_key_to_f64(int(h[2 * K + 1]))),
                                   h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
             return res, status, count
-        if self.exchange in ("ll", "p2p") and int(self._h_xstatus[0]) != 0:
-            check(int(self._h_xstatus[0]), "peer exchange")
         h = self.h_out.numpy()
+        xs = int(h[2 * K + 5]) & 0xFFFFFFFF                    # int32 status word of the exchange / merge kernels
+        if self.exchange in ("ll", "p2p") and xs:
+            check(xs - (1 << 32) if xs >= (1 << 31) else xs, "peer exchange")
         n_out = int(h[2 * K]) if self.K > 0 else 0
         res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
                               h[K:K + n_out].copy(), h[:n_out].view(np.float64).copy())
@@ -231,10 +230,9 @@ class ShardedDensePricer:
     def price(self, y_host: np.ndarray) -> dev.PriceResult:
         """One pass from a host vector of duals: copy into pinned memory, replay the captured step
         (H2D, pricing, selection, exchange + merge, D2H), one synchronisation, read the result."""
-        r0, r1 = self.row0, self.row0 + self.S_loc
-        hy = self.h_y.numpy()
-        hy[r0:r1] = y_host[r0:r1]                          # only what this rank uploads
-        hy[self.S:] = y_host[self.S:self.S + self.D]
+        hy = self.h_yloc.numpy()                           # only what this rank uploads, packed
+        hy[:self.S_loc] = y_host[self.row0:self.row0 + self.S_loc]
+        hy[self.S_loc:] = y_host[self.S:self.S + self.D]
         if self._graph is None and self.use_graph and not self._capture_tried:
             self._capture_tried = True
             self._capture()
