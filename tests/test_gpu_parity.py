@@ -612,6 +612,63 @@ def test_c4_full_size_planted_violators(dev):
         assert alt.n_violating == 300 and np.array_equal(alt.topk_id, got.topk_id)
 
 
+def test_c5_full_size_arc_ids_beyond_2_31(dev):
+    """BASELINE.json configs[4]: 60 000 x 60 000 (28.8 GB, 3.6e9 arcs: ids past 2^31, where int32 indexing breaks).  A constant cost
+    matrix with zero duals prices to rc = 1 everywhere; 3 000 planted negative entries (most of them in
+    the last rows, where arc ids exceed 2^31) must come back exactly, in order, through the TMA path,
+    and row slabs priced separately must merge to the same answer."""
+    free, _ = torch.cuda.mem_get_info()
+    S = D = 60000
+    if free < 8 * S * D + (4 << 30):
+        pytest.skip("needs ~33 GB of free device memory")
+    M = torch.ones(S, D, dtype=torch.float64, device="cuda")
+    y = torch.zeros(S + D, dtype=torch.float64, device="cuda")
+    rng = np.random.default_rng(60)
+    rows = np.concatenate([rng.integers(0, S, 500), rng.integers(S - 4000, S, 2500)])
+    cols = rng.integers(0, D, rows.size)
+    ids = np.unique(rows.astype(np.int64) * D + cols)
+    vals = -(1.0 + rng.permutation(ids.size)).astype(np.float64) / 7.0          # distinct, not dyadic
+    M.view(-1)[cu(ids)] = cu(vals)
+    K = 1024
+    res = dev.price_dense_ot(M, y, K=K)
+    o = np.argsort(vals, kind="stable")[:K]
+    assert ids.max() > (1 << 31) and res.n_violating == ids.size and res.min_rc == vals.min()
+    assert np.array_equal(res.topk_id, ids[o]) and np.array_equal(res.topk_rc, vals[o])
+    # two row slabs (as two ranks would hold them), merged
+    blocks_rc, blocks_id = [], []
+    for r0, r1 in ((0, 31000), (31000, S)):
+        pr = dev.Pricer(torch.device("cuda"), K)
+        pr.reset()
+        pr.price_dense(M[r0:r1], D, r0, r1 - r0, D, y[r0:r1], y[S:])
+        pr.select()
+        torch.cuda.synchronize()
+        blocks_rc.append(pr.out_rc.clone())
+        blocks_id.append(pr.out_id.clone())
+    m_rc, m_id, m_n = dev.topk_merge(torch.stack(blocks_rc), torch.stack(blocks_id))
+    assert int(m_n.item()) == K and np.array_equal(m_id.cpu().numpy(), ids[o])
+    del M
+
+
+def test_kruskal_prefix_large_properties(dev):
+    """1.3e8 weights: the head returned by sx_kruskal_prefix is sorted (descending weight, ties by
+    ascending id), holds at least T arcs, and nothing outside it is heavier than its lightest arc."""
+    n, T = 1 << 27, 500000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    w = torch.rand(n, generator=g, device="cuda", dtype=torch.float64) ** 8       # skewed toward 0, like scores
+    w[::1000003] = 0.75                                                           # a run of exact ties near the top
+    head = dev.kruskal_prefix(w, T)
+    assert head is not None
+    idx = head.to(torch.int64) & 0xFFFFFFFF
+    hw = w[idx]
+    assert idx.numel() >= T and idx.unique().numel() == idx.numel()
+    assert bool((hw[1:] <= hw[:-1]).all())
+    same = hw[1:] == hw[:-1]
+    assert bool((idx[1:][same] > idx[:-1][same]).all())
+    rest = torch.ones(n, dtype=torch.bool, device="cuda")
+    rest[idx] = False
+    assert float(w[rest].max()) < float(hw[-1])
+
+
 def test_large_sort_properties(dev):
     """2^25 keys: output is a permutation, keys non-decreasing, ties in ascending id."""
     n = 1 << 25
