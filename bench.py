@@ -555,12 +555,15 @@ def sweep(args, sp, y_dev, S_loc, D, lib, dev):
     """Pricing-kernel variants and tunings, kernel-only GB/s (CUDA events, 20 reps after 3 warm-ups)."""
     import torch
     if args.sweep_ab:
-        idx = [int(t) for t in args.sweep_ab.split(",")]
+        # entries: shape index, or shape:l2promo:evict (TMA options)
+        idx = [t for t in args.sweep_ab.split(",")]
         ms = {i: [] for i in idx}
         sp.variant = 0
         for rnd in range(8):
             for i in idx:
-                lib.sx_price_set_tuning(i, 0)
+                parts = [int(v) for v in i.split(":")]
+                lib.sx_price_set_tuning(parts[0], 0)
+                lib.sx_price_set_tma_options(parts[1] if len(parts) > 1 else 3, parts[2] if len(parts) > 2 else 1)
                 for _ in range(2):
                     sp.enqueue(y_dev)
                 k0 = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
@@ -574,6 +577,7 @@ def sweep(args, sp, y_dev, S_loc, D, lib, dev):
                               "kernel_ms_min": round(float(min(ms[i])), 4),
                               "GBs_median": round(8.0 * S_loc * D / (np.median(ms[i]) * 1e-3) / 1e9, 1)}), flush=True)
         lib.sx_price_set_tuning(6, 16)
+        lib.sx_price_set_tma_options(3, 1)
         return
     res = []
     shapes = ["16x6 8w", "16x6 16w", "32x3 8w", "32x3 16w", "16x7 16w", "8x12 16w", "16x3 8w x2cta", "8x6 8w x2cta",

@@ -216,6 +216,9 @@ SX_API int    sx_price_arcs(const double *c, const int32_t *tail, const int32_t 
  * {rows per box, stages, consumer warps, CTAs per SM} of variant 0 (see sx_price.cu), and the
  * CTAs per SM of the direct-load variants.  Negative / zero values leave a knob unchanged. */
 SX_API int    sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm);
+/* TMA descriptor / cache options of variant 0: l2_promotion 0..3 = none, 64 B, 128 B, 256 B (default);
+ * evict_first 1 (default) / 0 = L2 evict-first or normal policy on the loads.  Negative = unchanged. */
+SX_API int    sx_price_set_tma_options(int l2_promotion, int evict_first);
 
 /* ---- top-k most violating arcs (north_star extension) -------
  * Among the candidates (rc, id) left by a pricing pass select the K smallest by (rc ascending,

@@ -63,6 +63,11 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ uint64_t l2_evict_normal_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
                                             int c0, int c1, uint64_t policy) {
     asm volatile(
@@ -193,6 +198,7 @@ struct DenseParams {
     long long     ld_out;
     long long     n_col_blocks, n_row_tiles;
     uint32_t      zero;    // 0, but only the host knows: see mbar_arrive_after
+    uint32_t      evict_first;
 };
 
 // Lazy epilogue of one warp's share of a tile: RPT rows x 2 columns per thread already in registers
@@ -257,7 +263,7 @@ price_dense_tma_kernel(const __grid_constant__ CUtensorMap tmap, const DensePara
     if (warp == CWARPS) {
         // ===== producer warp: one elected lane issues the TMA loads =====
         if (lane_id() == 0) {
-            const uint64_t pol = l2_evict_first_policy();
+            const uint64_t pol = p.evict_first ? l2_evict_first_policy() : l2_evict_normal_policy();
             uint32_t it = 0;
             for (long long t = blockIdx.x; t < total; t += G, ++it) {
                 const int s = it % STAGES;
@@ -555,6 +561,7 @@ static const TmaShape kTmaShapes[] = {
     {12, 4, 8, 2}, {8, 7, 8, 2}, {8, 4, 8, 3},
 };
 constexpr int kNumTmaShapes = sizeof(kTmaShapes) / sizeof(kTmaShapes[0]);
+static int g_tma_l2promo = 3, g_tma_evict_first = 1;    // CU_TENSOR_MAP_L2_PROMOTION_L2_256B, L2 evict-first hint
 static int g_tma_shape = 6, g_ctas_per_sm_direct = 16;   // 16 rows x 3 stages, 8 consumer warps, 2 CTAs per SM
 
 template <int ROWS, int STAGES, int CWARPS, int MINB, bool WRITE_RC>
@@ -596,6 +603,13 @@ static int dispatch_tma(int shape, const CUtensorMap &map, const DenseParams &p,
 
 using namespace sx;
 
+extern "C" int sx_price_set_tma_options(int l2_promotion, int evict_first) {
+    if (l2_promotion > 3) return SX_ERR_INVALID;
+    if (l2_promotion >= 0) g_tma_l2promo = l2_promotion;
+    if (evict_first >= 0) g_tma_evict_first = evict_first ? 1 : 0;
+    return SX_OK;
+}
+
 extern "C" int sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm) {
     if (tma_shape >= kNumTmaShapes) return SX_ERR_INVALID;
     if (tma_shape >= 0) g_tma_shape = tma_shape;
@@ -633,7 +647,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
     p.y_src = y_src; p.y_dst = y_dst; p.S_loc = S_loc; p.D = D; p.row0 = row0; p.thr = -tol;
     p.sink.hdr = header; p.sink.sel = (SelState *)sel; p.sink.rc = cand_rc; p.sink.id = (int64_t *)cand_id;
     p.sink.cap = cand_cap;
-    p.rc_out = rc_out; p.ld_out = ld_out; p.zero = 0;
+    p.rc_out = rc_out; p.ld_out = ld_out; p.zero = 0; p.evict_first = (uint32_t)g_tma_evict_first;
     p.n_col_blocks = (D + kBoxCols - 1) / kBoxCols;
 
     int rc = SX_OK;
@@ -649,7 +663,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
         cuuint32_t estr[2]    = {1, 1};
         CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)M, gdim, gstride, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         (CUtensorMapL2promotion)g_tma_l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { g_last_cuda_error = (int)r; return SX_ERR_CUDA; }
         rc = rc_out ? dispatch_tma<true>(g_tma_shape, map, p, st) : dispatch_tma<false>(g_tma_shape, map, p, st);
     } else {

@@ -76,6 +76,7 @@ SIGNATURES = {
     "sx_price_dense_ot": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _dbl, _p, _p, _p, _p, _i64, _p, _i64, _int, _p]),
     "sx_price_arcs": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _dbl, _p, _p, _p, _p, _i64, _p, _p]),
     "sx_price_set_tuning": (_int, [_int, _int]),
+    "sx_price_set_tma_options": (_int, [_int, _int]),
     "sx_topk_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_topk_select": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "sx_topk_select_sorted": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
