@@ -65,6 +65,8 @@ typedef struct sx_price_header {
 #define SX_STATUS_CAND_OVERFLOW  1   /* candidate buffer too small: enlarge it and price again */
 #define SX_STATUS_NEED_SORTED    2   /* too many ties at the K-th reduced cost for the fast selection:
                                         call sx_topk_select_sorted on the same candidates */
+#define SX_STATUS_K_MISMATCH     4   /* sx_topk_select asked for more arcs than sx_price_pass_begin
+                                        announced: the candidates were pruned for the smaller K */
 
 /* Selection state of a pricing pass (opaque device memory, sx_select_state_bytes() bytes, 16 B
  * aligned): candidate counter, pruning bound and the reduced-cost histogram the bound is derived

@@ -468,6 +468,8 @@ topk_select_kernel(const double *__restrict__ cand_rc, const long long *__restri
         n = cand_cap;
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&hdr->status, kStatusCandOverflow);
     }
+    // the candidate list was pruned for the K given to sx_price_pass_begin: a larger K here cannot be served
+    if ((unsigned)K > st->K && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&hdr->status, kStatusKMismatch);
     const long long gtid = (long long)blockIdx.x * kApThreads + threadIdx.x;
     const long long gsz = (long long)gridDim.x * kApThreads;
 

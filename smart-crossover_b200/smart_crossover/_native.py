@@ -17,6 +17,7 @@ SX_PLUS_IS_TAIL = 1
 SX_TOPK_MAX_K = 1024
 SX_STATUS_CAND_OVERFLOW = 1
 SX_STATUS_NEED_SORTED = 2
+SX_STATUS_K_MISMATCH = 4
 SX_ABI_VERSION = 2
 
 

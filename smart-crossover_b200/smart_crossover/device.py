@@ -239,6 +239,8 @@ class Pricer:
             h = self.h_block.numpy()
             Kp = self.Kp
             self.status = int(h[2 * Kp + 3])
+            if self.status & _native.SX_STATUS_K_MISMATCH:
+                raise ValueError("top-k selection asked for more arcs than the pricing pass was started for")
             if self.K > 0 and (self.status & _native.SX_STATUS_NEED_SORTED) \
                     and not (self.status & _native.SX_STATUS_CAND_OVERFLOW):
                 self.header[3:4].zero_()
