@@ -255,9 +255,14 @@ class Pricer:
     def overflowed(self, res: PriceResult | None = None) -> bool:
         return self.K > 0 and bool(self.status & _native.SX_STATUS_CAND_OVERFLOW)
 
+    MAX_CAP = 1 << 28      # 256 M candidates (4 GB + 8 GB of selection lists): beyond this the pass cannot be pruned
+
     def grow(self, n_violating: int = 0):
         """Enlarge the candidate buffer after SX_STATUS_CAND_OVERFLOW (x4, at most every violator)."""
-        self.cap = max(4 * self.cap, 1024)
+        if self.cap >= self.MAX_CAP:
+            raise RuntimeError("pricing candidates cannot be pruned below %d entries: more arcs than that tie "
+                               "(to 0.4 %%) with the K-th most violating one" % self.MAX_CAP)
+        self.cap = min(max(4 * self.cap, 1024), self.MAX_CAP)
         if n_violating:
             self.cap = min(self.cap, max(int(n_violating), 1024))
         self._alloc()

@@ -57,7 +57,10 @@ class ShardedDensePricer:
         self._graph, self._capture_tried, self._graph_launches, self._replayed_launches = None, False, 0, 0
         self._capture_overcount = 0
         self.y_loc = torch.empty(self.S_loc + self.D, dtype=torch.float64, device=M_loc.device)
-        self.h_yloc = torch.empty(self.S_loc + self.D, dtype=torch.float64).pin_memory()
+        # pinned staging of the full dual vector; `y_pinned` hands it to callers that can write their duals
+        # straight into it (the solver's output buffer) and so skip one host-side copy per pass
+        self.h_y = torch.zeros(self.S + self.D, dtype=torch.float64).pin_memory()
+        self._h_y_np = self.h_y.numpy()
         Kp = max(self.K, 1)
         self.blk = 2 * Kp + dev.Pricer.BLOCK_TAIL
         self.gathered = torch.empty(self.world, self.blk, dtype=torch.int64, device=M_loc.device)
@@ -171,7 +174,9 @@ class ShardedDensePricer:
     # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
     def _step(self, sorted_path: bool = False):
         """H2D of the duals this rank needs (its rows + every sink), one pass, D2H of the result."""
-        self.y_loc.copy_(self.h_yloc, non_blocking=True)          # [this rank's S_loc source duals | D sink duals]
+        r0 = self.row0                                             # y_loc = [this rank's S_loc source duals | D sink duals]
+        self.y_loc[:self.S_loc].copy_(self.h_y[r0:r0 + self.S_loc], non_blocking=True)
+        self.y_loc[self.S_loc:].copy_(self.h_y[self.S:], non_blocking=True)
         self.enqueue(None, sorted_path=sorted_path, y_parts=(self.y_loc[:self.S_loc], self.y_loc[self.S_loc:]))
         if self.world == 1:
             self.pricer.h_block.copy_(self.pricer.block, non_blocking=True)
@@ -230,9 +235,10 @@ class ShardedDensePricer:
     def price(self, y_host: np.ndarray) -> dev.PriceResult:
         """One pass from a host vector of duals: copy into pinned memory, replay the captured step
         (H2D, pricing, selection, exchange + merge, D2H), one synchronisation, read the result."""
-        hy = self.h_yloc.numpy()                           # only what this rank uploads, packed
-        hy[:self.S_loc] = y_host[self.row0:self.row0 + self.S_loc]
-        hy[self.S_loc:] = y_host[self.S:self.S + self.D]
+        if y_host is not self._h_y_np:                     # duals already written into `y_pinned`: nothing to copy
+            r0 = self.row0
+            self._h_y_np[r0:r0 + self.S_loc] = y_host[r0:r0 + self.S_loc]      # only what this rank uploads
+            self._h_y_np[self.S:] = y_host[self.S:self.S + self.D]
         if self._graph is None and self.use_graph and not self._capture_tried:
             self._capture_tried = True
             self._capture()
@@ -256,6 +262,12 @@ class ShardedDensePricer:
                 self._graph, self._capture_tried = None, False      # buffers moved: record again next time
             else:
                 sorted_path = True
+
+    @property
+    def y_pinned(self) -> np.ndarray:
+        """The pinned host vector (S + D) that `price` uploads from.  Write the duals into it and pass this
+        very array to `price` to skip the pageable-to-pinned copy."""
+        return self._h_y_np
 
     @property
     def h2d_bytes(self):
