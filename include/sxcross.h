@@ -125,7 +125,9 @@ SX_API int    sx_kruskal_order(const double *sorted_key, const uint32_t *order_a
  * returns only the head of that order: every arc whose weight is >= the T-th largest one (to 24
  * bits of its order-preserving image), in Kruskal order (descending weight, ties by ascending
  * arc id), i.e. exactly the first *n_prefix_h entries of what sx_argsort_f64 + sx_kruskal_order
- * would produce.  Three streaming passes over the weights (24 B per arc) instead of ~256 B per arc.
+ * would produce.  One to three streaming passes over the weights (8-24 B per arc: the top-12-bit
+ * histogram unless the caller has it, one split pass, and two more passes only when the threshold
+ * bin is too crowded for the boundary list) instead of ~256 B per arc.
  *   hist12 (may be NULL): the 4096-bin histogram of the weights' top 12 key bits if the caller has
  *   it already (sx_score_ot / sx_hist12_f64), which saves the first pass.
  *   korder_out: capacity T_cap >= T.  *n_prefix_h (HOST) = number of arcs written, or -1 when more

@@ -8,14 +8,14 @@
 // to the full argsort otherwise; the tree is identical either way because the prefix of a strict
 // total order is unique).
 //
-//   1. histogram of the top 12 bits (sign + exponent) of every weight's order-preserving image,
-//      then of the next 12 bits inside the bin where the T-th largest weight lies: two streaming
-//      passes, 8 B per arc each;
-//   2. filter: every arc whose 24-bit prefix is >= the T-th largest one is appended to a candidate
-//      list (unordered): one more pass, 8 B per arc;
+//   1. histogram of the top 12 bits (sign + exponent) of every weight's order-preserving image (a
+//      streaming pass, 8 B per arc -- or free, when sx_score_ot took it while writing the scores);
+//   2. split: one more pass appends every arc above the bin b1 that holds the T-th largest weight to
+//      the candidate list and sets the arcs of bin b1 aside; the next 12 bits are histogrammed and
+//      filtered on that short list (if bin b1 is too crowded for it, two more passes over all weights);
 //   3. the few candidates are sorted by id, then stably by weight (radix argsort, sx_sort.cu), and
 //      the tie runs are flipped into the Kruskal order (sx_kruskal_order).
-// HBM-bound: 24 B per arc instead of the ~256 B per arc of the full 8-pass argsort.
+// HBM-bound: 8-16 B per arc (24 B in the crowded-bin case) instead of the ~256 B per arc of the full 8-pass argsort.
 #include "sx_common.cuh"
 
 namespace sx {
@@ -28,7 +28,8 @@ struct PrefixCtl {
     unsigned long long n_sel;      // candidates appended by the filter
     unsigned long long above;      // arcs in bins strictly above the threshold bin (level 0, then level 0 + 1)
     unsigned int       b1, b2;     // threshold bin of level 0 / level 1
-    unsigned int       pad[10];
+    unsigned long long n_bnd;      // arcs of bin b1 set aside by the split pass
+    unsigned int       pad[8];
     unsigned int       hist[2][kPfBins];
 };
 
@@ -128,8 +129,8 @@ constexpr int kPfBatch = 4;
 constexpr int kPfStage = 2048;                 // staged candidates per CTA (32 KB)
 
 __global__ void __launch_bounds__(kPfThreads)
-pf_filter_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, double *__restrict__ cand_w,
-                 unsigned long long *__restrict__ cand_id, long long cap) {
+pf_filter_kernel(const double *__restrict__ w, const unsigned long long *__restrict__ ids_in, long long n,
+                 PrefixCtl *ctl, double *__restrict__ cand_w, unsigned long long *__restrict__ cand_id, long long cap) {
     __shared__ double             s_w[kPfStage];
     __shared__ unsigned long long s_id[kPfStage];
     __shared__ unsigned           s_cnt;
@@ -150,10 +151,11 @@ pf_filter_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, doub
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned slot = base + __popc(m & lt);
         if (!keep) return;
-        if (slot < (unsigned)kPfStage) { s_w[slot] = v; s_id[slot] = (unsigned long long)id; }
+        const unsigned long long gid = ids_in ? ids_in[id] : (unsigned long long)id;     // position -> arc id
+        if (slot < (unsigned)kPfStage) { s_w[slot] = v; s_id[slot] = gid; }
         else {                                                   // stage full (dense selection): straight to global
             const unsigned long long g = atomicAdd(&ctl->n_sel, 1ull);
-            if ((long long)g < cap) { cand_w[g] = v; cand_id[g] = (unsigned long long)id; }
+            if ((long long)g < cap) { cand_w[g] = v; cand_id[g] = gid; }
         }
     };
     auto flush = [&]() {                                         // whole CTA
@@ -208,6 +210,102 @@ pf_filter_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, doub
     flush();
 }
 
+// One pass that needs only the level-0 bound: arcs above bin b1 are selected outright, arcs inside bin
+// b1 are set aside in a boundary list for the second level, which then works on that (short) list
+// instead of streaming all the weights twice more.  Two shared-memory stages, flushed like the filter's.
+constexpr int kPfHalf = kPfStage / 2;
+
+__global__ void __launch_bounds__(kPfThreads)
+pf_split_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, double *__restrict__ cand_w,
+                unsigned long long *__restrict__ cand_id, long long cap, double *__restrict__ bnd_w,
+                unsigned long long *__restrict__ bnd_id, long long bnd_cap) {
+    __shared__ double             s_w[2][kPfHalf];
+    __shared__ unsigned long long s_id[2][kPfHalf];
+    __shared__ unsigned           s_cnt[2];
+    __shared__ unsigned long long s_base[2];
+    const unsigned b1 = ctl->b1;
+    const unsigned lt = (1u << lane_id()) - 1u;
+    const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+    const long long n2 = aligned ? n / 2 : 0;
+    const double2 *w2 = reinterpret_cast<const double2 *>(w);
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    // which = 0: selected (bin > b1), 1: boundary (bin == b1)
+    auto emit = [&](int which, bool keep, double v, long long id) {
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0) return;
+        unsigned base = 0;
+        if (lane_id() == 0) base = atomicAdd(&s_cnt[which], (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned slot = base + __popc(m & lt);
+        if (!keep) return;
+        if (slot < (unsigned)kPfHalf) { s_w[which][slot] = v; s_id[which][slot] = (unsigned long long)id; }
+        else {                                                   // stage full: straight to global
+            const unsigned long long g = atomicAdd(which ? &ctl->n_bnd : &ctl->n_sel, 1ull);
+            if (which == 0) { if ((long long)g < cap) { cand_w[g] = v; cand_id[g] = (unsigned long long)id; } }
+            else { if ((long long)g < bnd_cap) { bnd_w[g] = v; bnd_id[g] = (unsigned long long)id; } }
+        }
+    };
+    auto flush = [&]() {                                         // whole CTA, both stages
+        __syncthreads();
+        const unsigned c0 = s_cnt[0] < (unsigned)kPfHalf ? s_cnt[0] : (unsigned)kPfHalf;
+        const unsigned c1 = s_cnt[1] < (unsigned)kPfHalf ? s_cnt[1] : (unsigned)kPfHalf;
+        if (threadIdx.x == 0 && c0) s_base[0] = atomicAdd(&ctl->n_sel, (unsigned long long)c0);
+        if (threadIdx.x == 32 && c1) s_base[1] = atomicAdd(&ctl->n_bnd, (unsigned long long)c1);
+        __syncthreads();
+        for (unsigned q = threadIdx.x; q < c0; q += kPfThreads) {
+            const long long g = (long long)(s_base[0] + q);
+            if (g < cap) { cand_w[g] = s_w[0][q]; cand_id[g] = s_id[0][q]; }
+        }
+        for (unsigned q = threadIdx.x; q < c1; q += kPfThreads) {
+            const long long g = (long long)(s_base[1] + q);
+            if (g < bnd_cap) { bnd_w[g] = s_w[1][q]; bnd_id[g] = s_id[1][q]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+    };
+    const long long n2_blocks = (n2 + kPfThreads - 1) / kPfThreads;
+    for (long long blk = blockIdx.x; blk < n2_blocks; blk += (long long)gridDim.x * kPfBatch) {
+        double2 v[kPfBatch];
+#pragma unroll
+        for (int u = 0; u < kPfBatch; ++u) {
+            const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
+            v[u] = i < n2 ? __ldcs(w2 + i) : make_double2(-INFINITY, -INFINITY);
+        }
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < kPfBatch; ++u)
+            any = any || (unsigned)(f64_to_sort_key(v[u].x) >> 52) >= b1 || (unsigned)(f64_to_sort_key(v[u].y) >> 52) >= b1;
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int u = 0; u < kPfBatch; ++u) {
+                const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
+                const bool in = i < n2;
+                const unsigned bx = (unsigned)(f64_to_sort_key(v[u].x) >> 52), by = (unsigned)(f64_to_sort_key(v[u].y) >> 52);
+                emit(0, in && bx > b1, v[u].x, 2 * i);
+                emit(1, in && bx == b1, v[u].x, 2 * i);
+                emit(0, in && by > b1, v[u].y, 2 * i + 1);
+                emit(1, in && by == b1, v[u].y, 2 * i + 1);
+            }
+        }
+        if (__syncthreads_or(s_cnt[0] > (unsigned)kPfHalf / 2 || s_cnt[1] > (unsigned)kPfHalf / 2)) flush();
+    }
+    const long long t0 = 2 * n2, nt = n - t0;
+    const long long nt_blocks = (nt + kPfThreads - 1) / kPfThreads;
+    for (long long blk = blockIdx.x; blk < nt_blocks; blk += gridDim.x) {
+        const long long i = blk * kPfThreads + threadIdx.x;
+        double v = 0.0;
+        unsigned b = 0;
+        const bool in = i < nt;
+        if (in) { v = __ldcs(w + t0 + i); b = (unsigned)(f64_to_sort_key(v) >> 52); }
+        emit(0, in && b > b1, v, t0 + i);
+        emit(1, in && b == b1, v, t0 + i);
+        if (__syncthreads_or(s_cnt[0] > (unsigned)kPfHalf / 2 || s_cnt[1] > (unsigned)kPfHalf / 2)) flush();
+    }
+    flush();
+}
+
 __global__ void pf_gather_kernel(const double *__restrict__ w, const unsigned long long *__restrict__ id,
                                  const uint32_t *__restrict__ perm, long long n, double *w_out, uint32_t *id_out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -221,6 +319,8 @@ __global__ void pf_gather_ids_kernel(const uint32_t *__restrict__ id, const uint
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         id_out[i] = id[perm[i]];
 }
+
+constexpr size_t kPfBndFactor = 4;     // boundary list capacity = 4 x T_cap arcs of the threshold bin
 
 static int pf_grid(long long n, int per_thread) {
     long long g = (n + (long long)kPfThreads * per_thread - 1) / ((long long)kPfThreads * per_thread);
@@ -237,7 +337,8 @@ extern "C" size_t sx_kruskal_prefix_workspace_bytes(int64_t T_cap) {
     if (T_cap < 0) return 0;
     const size_t c = (size_t)T_cap;
     return carve_bytes(1, sizeof(PrefixCtl)) + 3 * carve_bytes(c, 8) + 4 * carve_bytes(c, 4) + carve_bytes(c, 8) +
-           sx_argsort_workspace_bytes(T_cap) + sx_kruskal_order_workspace_bytes(T_cap) + 256;
+           2 * carve_bytes(kPfBndFactor * c, 8) + sx_argsort_workspace_bytes(T_cap) +
+           sx_kruskal_order_workspace_bytes(T_cap) + 256;
 }
 
 // hist[bin] += number of weights whose order-preserving image has top 12 bits == bin (4096 bins).
@@ -265,6 +366,8 @@ extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int
     uint32_t *perm2 = cv.take<uint32_t>(T_cap);
     uint32_t *order_asc = cv.take<uint32_t>(T_cap);
     double *sorted_w = cv.take<double>(T_cap);
+    double *bnd_w = cv.take<double>(kPfBndFactor * (size_t)T_cap);
+    unsigned long long *bnd_id = cv.take<unsigned long long>(kPfBndFactor * (size_t)T_cap);
     void *sort_ws = cv.base + cv.off;
     const size_t sort_ws_bytes = sx_argsort_workspace_bytes(T_cap);
     void *ko_ws = (char *)sort_ws + align_up(sort_ws_bytes, 256);
@@ -280,17 +383,48 @@ extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int
     }
     pf_bound_kernel<0><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
     SX_LAUNCH_CHECK();
-    pf_hist_kernel<1><<<grid, kPfThreads, 0, st>>>(weight, n, ctl, ctl->hist[1]);
-    SX_LAUNCH_CHECK();
-    pf_bound_kernel<1><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
-    SX_LAUNCH_CHECK();
+    // level 1.  Preferred: ONE more pass over the weights that selects everything above bin b1 and sets
+    // the arcs of bin b1 aside; the second histogram and the filter then run on that short list.  If the
+    // threshold bin is too crowded for the list, both run over all the weights instead.
     int occ = 1;
-    SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pf_filter_kernel, kPfThreads, 0));
+    SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pf_split_kernel, kPfThreads, 0));
     long long fgrid = (long long)kNumSMs * (occ > 0 ? occ : 1);
     const long long fneed = (n / 2 + (long long)kPfThreads * kPfBatch - 1) / ((long long)kPfThreads * kPfBatch);
     if (fgrid > fneed) fgrid = fneed > 0 ? fneed : 1;
-    pf_filter_kernel<<<(int)fgrid, kPfThreads, 0, st>>>(weight, n, ctl, cand_w, cand_id, T_cap);
+    const long long bnd_cap = (long long)(kPfBndFactor * (size_t)T_cap);
+    pf_split_kernel<<<(int)fgrid, kPfThreads, 0, st>>>(weight, n, ctl, cand_w, cand_id, T_cap, bnd_w, bnd_id, bnd_cap);
     SX_LAUNCH_CHECK();
+    unsigned long long n_bnd = 0;
+    SX_CUDA(cudaMemcpyAsync(&n_bnd, &ctl->n_bnd, sizeof(n_bnd), cudaMemcpyDeviceToHost, st));
+    SX_CUDA(cudaStreamSynchronize(st));
+    SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pf_filter_kernel, kPfThreads, 0));
+    const long long filter_ctas = (long long)kNumSMs * (occ > 0 ? occ : 1);
+    auto filter_grid = [&](long long cnt) {
+        long long need = (cnt / 2 + (long long)kPfThreads * kPfBatch - 1) / ((long long)kPfThreads * kPfBatch);
+        if (need < 1) need = 1;
+        return (int)(need < filter_ctas ? need : filter_ctas);
+    };
+    if (n_bnd <= (unsigned long long)bnd_cap) {
+        const long long mb = (long long)n_bnd;
+        if (mb > 0) {
+            pf_hist_kernel<1><<<pf_grid(mb, 16), kPfThreads, 0, st>>>(bnd_w, mb, ctl, ctl->hist[1]);
+            SX_LAUNCH_CHECK();
+        }
+        pf_bound_kernel<1><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
+        SX_LAUNCH_CHECK();
+        if (mb > 0) {
+            pf_filter_kernel<<<filter_grid(mb), kPfThreads, 0, st>>>(bnd_w, bnd_id, mb, ctl, cand_w, cand_id, T_cap);
+            SX_LAUNCH_CHECK();
+        }
+    } else {
+        SX_CUDA(cudaMemsetAsync(&ctl->n_sel, 0, sizeof(unsigned long long), st));       // the filter selects from scratch
+        pf_hist_kernel<1><<<grid, kPfThreads, 0, st>>>(weight, n, ctl, ctl->hist[1]);
+        SX_LAUNCH_CHECK();
+        pf_bound_kernel<1><<<1, 1024, 0, st>>>(ctl, (unsigned long long)T);
+        SX_LAUNCH_CHECK();
+        pf_filter_kernel<<<filter_grid(n), kPfThreads, 0, st>>>(weight, nullptr, n, ctl, cand_w, cand_id, T_cap);
+        SX_LAUNCH_CHECK();
+    }
     unsigned long long n_sel = 0;
     SX_CUDA(cudaMemcpyAsync(&n_sel, &ctl->n_sel, sizeof(n_sel), cudaMemcpyDeviceToHost, st));
     SX_CUDA(cudaStreamSynchronize(st));

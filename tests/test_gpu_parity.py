@@ -231,6 +231,24 @@ def test_kruskal_prefix_is_the_head_of_the_full_order(dev, S, D, T, kind):
     assert np.array_equal(head2.cpu().numpy().view(np.uint32), head)
 
 
+@pytest.mark.parametrize("n,T,T_cap", [(1 << 20, 1000, 4096), (300001, 2000, 3000), (1 << 20, 1000, 1 << 20)])
+def test_kruskal_prefix_crowded_threshold_bin(dev, n, T, T_cap):
+    """All weights share one exponent (one level-0 bin): with a small T_cap the boundary list of the
+    split pass overflows and the second level streams every weight again; with a large T_cap it is
+    resolved from the list.  Either way the head equals the head of the full sort."""
+    rng = np.random.default_rng(n + T)
+    w = 1.0 + rng.random(n)
+    w[rng.integers(0, n, 200)] = 1.9999                               # exact ties inside the head
+    order, skey, queue, korder = sort_pipeline(dev, cu(w))
+    full = korder.cpu().numpy().view(np.uint32)
+    head = dev.kruskal_prefix(cu(w), T, T_cap=T_cap)
+    assert head is not None
+    head = head.cpu().numpy().view(np.uint32)
+    assert T <= head.size <= T_cap
+    assert np.array_equal(head, full[:head.size])
+    assert w[full[head.size]] < w[head[-1]]
+
+
 def test_tree_from_prefix_equals_tree_from_full_sort(dev):
     from smart_crossover.formats import OptTransport
     from smart_crossover.network_methods import tree_BI
