@@ -91,6 +91,7 @@ SX_API double      sx_key_to_f64(long long key);        /* decode sx_price_heade
  */
 SX_API int    sx_score_ot(const double *x, const double *s, const double *d, int64_t S, int64_t D,
                    double *score_out, uint32_t *hist12_out, void *stream);
+SX_API int    sx_score_set_tuning(int min_ctas_per_sm);   /* 4 (default, 64 registers) or 3 (78 registers) resident CTAs per SM */
 SX_API size_t sx_score_mcf_workspace_bytes(int64_t N, int64_t E);
 SX_API int    sx_score_mcf(const double *x, const double *u, const int32_t *tail, const int32_t *head,
                     const int64_t *node_ptr, const int32_t *node_arc, const int8_t *node_sign,

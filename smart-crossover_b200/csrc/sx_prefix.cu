@@ -137,7 +137,6 @@ pf_filter_kernel(const double *__restrict__ w, const unsigned long long *__restr
     __shared__ unsigned long long s_base;
     const unsigned thr = (ctl->b1 << 12) | ctl->b2;
     const unsigned lt = (1u << lane_id()) - 1u;
-    const long long stride = (long long)gridDim.x * kPfThreads;
     const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
     const long long n2 = aligned ? n / 2 : 0;                    // pairs handled by the vector loop
     const double2 *w2 = reinterpret_cast<const double2 *>(w);
@@ -213,6 +212,15 @@ pf_filter_kernel(const double *__restrict__ w, const unsigned long long *__restr
 // One pass that needs only the level-0 bound: arcs above bin b1 are selected outright, arcs inside bin
 // b1 are set aside in a boundary list for the second level, which then works on that (short) list
 // instead of streaming all the weights twice more.  Two shared-memory stages, flushed like the filter's.
+// Top 32 bits of f64_to_sort_key(v) from the high word of v: exact for every v with the sign bit clear
+// (a positive NaN lands in bin 4095 like the all-ones key); negative values, -0.0 and negative NaNs take
+// the full conversion.  image32 >> 20 is the level-0 bin.
+__device__ __forceinline__ unsigned pf_image32(double v) {
+    const int hi = __double2hiint(v);
+    if (hi < 0) return (unsigned)(f64_to_sort_key(v) >> 32);
+    return (unsigned)hi | 0x80000000u;
+}
+
 constexpr int kPfHalf = kPfStage / 2;
 
 __global__ void __launch_bounds__(kPfThreads)
@@ -265,6 +273,19 @@ pf_split_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, doubl
         if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
         __syncthreads();
     };
+    // Hot loop.  A weight's level-0 bin is decided from the high word of the double (pf_image32); every
+    // lane packs its hits into bit masks, and only a warp that holds a hit (a fraction of a percent of
+    // the arcs are hits) runs ONE packed warp scan to reserve stage slots in both lists.
+    const bool     none_above = b1 >= (unsigned)kPfBins - 1;
+    const unsigned sel_lo = none_above ? 0xffffffffu : (b1 + 1) << 20;             // image32 >= sel_lo: bin > b1
+    auto put = [&](int which, unsigned slot, double v, long long id) {
+        if (slot < (unsigned)kPfHalf) { s_w[which][slot] = v; s_id[which][slot] = (unsigned long long)id; }
+        else {                                                   // stage full: straight to global
+            const unsigned long long g = atomicAdd(which ? &ctl->n_bnd : &ctl->n_sel, 1ull);
+            if (which == 0) { if ((long long)g < cap) { cand_w[g] = v; cand_id[g] = (unsigned long long)id; } }
+            else { if ((long long)g < bnd_cap) { bnd_w[g] = v; bnd_id[g] = (unsigned long long)id; } }
+        }
+    };
     const long long n2_blocks = (n2 + kPfThreads - 1) / kPfThreads;
     for (long long blk = blockIdx.x; blk < n2_blocks; blk += (long long)gridDim.x * kPfBatch) {
         double2 v[kPfBatch];
@@ -273,20 +294,43 @@ pf_split_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, doubl
             const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
             v[u] = i < n2 ? __ldcs(w2 + i) : make_double2(-INFINITY, -INFINITY);
         }
-        bool any = false;
+        unsigned sel = 0, bnd = 0;                               // bit 2u: .x, bit 2u + 1: .y
 #pragma unroll
-        for (int u = 0; u < kPfBatch; ++u)
-            any = any || (unsigned)(f64_to_sort_key(v[u].x) >> 52) >= b1 || (unsigned)(f64_to_sort_key(v[u].y) >> 52) >= b1;
-        if (__any_sync(0xffffffffu, any)) {
+        for (int u = 0; u < kPfBatch; ++u) {
+            const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
+            if (i < n2) {
+                const unsigned ix = pf_image32(v[u].x), iy = pf_image32(v[u].y);
+                sel |= (unsigned)(!none_above && ix >= sel_lo) << (2 * u) |
+                       (unsigned)(!none_above && iy >= sel_lo) << (2 * u + 1);
+                bnd |= (unsigned)((ix >> 20) == b1) << (2 * u) | (unsigned)((iy >> 20) == b1) << (2 * u + 1);
+            }
+        }
+        const unsigned mine = (unsigned)__popc(sel) | ((unsigned)__popc(bnd) << 16);
+        if (__any_sync(0xffffffffu, mine != 0)) {
+            unsigned incl = mine;                                // packed inclusive scan: <= 256 hits per list and warp
 #pragma unroll
-            for (int u = 0; u < kPfBatch; ++u) {
-                const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
-                const bool in = i < n2;
-                const unsigned bx = (unsigned)(f64_to_sort_key(v[u].x) >> 52), by = (unsigned)(f64_to_sort_key(v[u].y) >> 52);
-                emit(0, in && bx > b1, v[u].x, 2 * i);
-                emit(1, in && bx == b1, v[u].x, 2 * i);
-                emit(0, in && by > b1, v[u].y, 2 * i + 1);
-                emit(1, in && by == b1, v[u].y, 2 * i + 1);
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane_id() >= (unsigned)o) incl += t;
+            }
+            const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned base0 = 0, base1 = 0;
+            if (lane_id() == 31) {
+                if (tot & 0xffffu) base0 = atomicAdd(&s_cnt[0], tot & 0xffffu);
+                if (tot >> 16) base1 = atomicAdd(&s_cnt[1], tot >> 16);
+            }
+            base0 = __shfl_sync(0xffffffffu, base0, 31);
+            base1 = __shfl_sync(0xffffffffu, base1, 31);
+            if (mine) {
+                unsigned slot0 = base0 + ((incl - mine) & 0xffffu), slot1 = base1 + ((incl - mine) >> 16);
+#pragma unroll
+                for (int u = 0; u < kPfBatch; ++u) {
+                    const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
+                    if ((sel >> (2 * u)) & 1u) put(0, slot0++, v[u].x, 2 * i);
+                    if ((bnd >> (2 * u)) & 1u) put(1, slot1++, v[u].x, 2 * i);
+                    if ((sel >> (2 * u + 1)) & 1u) put(0, slot0++, v[u].y, 2 * i + 1);
+                    if ((bnd >> (2 * u + 1)) & 1u) put(1, slot1++, v[u].y, 2 * i + 1);
+                }
             }
         }
         if (__syncthreads_or(s_cnt[0] > (unsigned)kPfHalf / 2 || s_cnt[1] > (unsigned)kPfHalf / 2)) flush();

@@ -46,6 +46,16 @@ __device__ __forceinline__ unsigned long long rs_load_key(const RsSrc &s, long l
     return s.keys[i];
 }
 
+// Lowest byte of f64_to_sort_key(v) from the raw bits b of v: for an ordinary value it is the low byte of
+// b, complemented when v is negative; zeros, infinities and NaNs take the full conversion.
+__device__ __forceinline__ unsigned f64_bits_low_digit(unsigned long long b) {
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned h2 = hi << 1;
+    if (h2 >= 0xffe00000u || (h2 | lo) == 0u)
+        return (unsigned)f64_to_sort_key(__longlong_as_double((long long)b)) & 0xffu;
+    return (lo ^ (unsigned)((int)hi >> 31)) & 0xffu;
+}
+
 // ---- upsweep: per-block digit histogram ------------------------------------------------
 // Every lane owns a private 16-bit counter per digit (cnt[warp][digit][lane], 64 KB per CTA), so
 // counting a key is a plain shared-memory read-modify-write: no atomics (shared atomics cost ~2
@@ -70,6 +80,7 @@ rs_upsweep_kernel(RsSrc src, long long n, int shift, long long keys_per_block, u
     const long long beg = (long long)blockIdx.x * keys_per_block;
     long long end = beg + keys_per_block;
     if (end > n) end = n;
+    const bool raw_f64 = SRC == kFromF64 && shift == 0;      // the first pass of an f64 sort: low byte only
     const void *base_ptr = (SRC == kFromF64) ? (const void *)src.f64 : (const void *)src.keys;
     const bool vec = (reinterpret_cast<uintptr_t>(base_ptr) & 15) == 0;   // beg is even
     for (long long base = beg; base < end; base += (long long)kUpThreads * 2 * kUpUnroll) {
@@ -81,21 +92,31 @@ rs_upsweep_kernel(RsSrc src, long long n, int shift, long long keys_per_block, u
             if (i + 1 < end && vec) {
                 if (SRC == kFromF64) {
                     const double2 q = *reinterpret_cast<const double2 *>(src.f64 + i);
-                    k0[u] = f64_to_sort_key(q.x); k1[u] = f64_to_sort_key(q.y);
+                    if (raw_f64) {      // digit taken straight from the double's bits below
+                        k0[u] = (unsigned long long)__double_as_longlong(q.x);
+                        k1[u] = (unsigned long long)__double_as_longlong(q.y);
+                    } else {
+                        k0[u] = f64_to_sort_key(q.x); k1[u] = f64_to_sort_key(q.y);
+                    }
                 } else {
                     const ulonglong2 q = *reinterpret_cast<const ulonglong2 *>(src.keys + i);
                     k0[u] = q.x; k1[u] = q.y;
                 }
             } else {
-                if (i < end) k0[u] = rs_load_key<SRC>(src, i);
-                if (i + 1 < end) k1[u] = rs_load_key<SRC>(src, i + 1);
+                if (i < end) k0[u] = raw_f64 ? (unsigned long long)__double_as_longlong(src.f64[i]) : rs_load_key<SRC>(src, i);
+                if (i + 1 < end) k1[u] = raw_f64 ? (unsigned long long)__double_as_longlong(src.f64[i + 1]) : rs_load_key<SRC>(src, i + 1);
             }
         }
 #pragma unroll
         for (int u = 0; u < kUpUnroll; ++u) {
             const long long i = base + 2ll * (u * kUpThreads + threadIdx.x);
-            if (i < end) mine[((k0[u] >> shift) & 0xff) * 32] += 1;
-            if (i + 1 < end) mine[((k1[u] >> shift) & 0xff) * 32] += 1;
+            if (raw_f64) {
+                if (i < end) mine[f64_bits_low_digit(k0[u]) * 32] += 1;
+                if (i + 1 < end) mine[f64_bits_low_digit(k1[u]) * 32] += 1;
+            } else {
+                if (i < end) mine[((k0[u] >> shift) & 0xff) * 32] += 1;
+                if (i + 1 < end) mine[((k1[u] >> shift) & 0xff) * 32] += 1;
+            }
         }
     }
     __syncthreads();
@@ -342,16 +363,26 @@ __device__ __forceinline__ bool ko_is_head(const double *key, long long p) {
     return p == 0 || key[p] != key[p - 1];
 }
 
-// pass 1: first / last run head inside each block
+// pass 1: first / last run head inside each block.  Position p is a head when key[p] != key[p - 1]; the
+// previous key comes from the neighbouring lane (one extra load per warp and row, not per thread).
 __global__ void __launch_bounds__(kKoThreads)
 ko_block_heads_kernel(const double *__restrict__ key, long long n, long long *first_head, long long *last_head) {
     __shared__ long long s_min[32], s_max[32];
     const long long base = (long long)blockIdx.x * kKoTile;
+    double k[kKoItems], prev0[kKoItems];
+#pragma unroll
+    for (int q = 0; q < kKoItems; ++q) {
+        const long long p = base + (long long)q * kKoThreads + threadIdx.x;
+        k[q] = p < n ? __ldcs(key + p) : 0.0;
+        prev0[q] = (lane_id() == 0 && p > 0 && p < n) ? key[p - 1] : 0.0;
+    }
     long long mn = n, mx = -1;
 #pragma unroll
     for (int q = 0; q < kKoItems; ++q) {
         const long long p = base + (long long)q * kKoThreads + threadIdx.x;
-        if (p < n && ko_is_head(key, p)) {
+        double pv = __shfl_up_sync(0xffffffffu, k[q], 1);
+        if (lane_id() == 0) pv = prev0[q];
+        if (p < n && (p == 0 || k[q] != pv)) {
             mn = p < mn ? p : mn;
             mx = p > mx ? p : mx;
         }
@@ -414,14 +445,39 @@ ko_scatter_kernel(const double *__restrict__ key, const uint32_t *__restrict__ o
     __shared__ long long s_fwd[32], s_bwd[32];
     const long long base = (long long)blockIdx.x * kKoTile;
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    // blocked arrangement: thread t owns kKoItems consecutive positions
+    // blocked arrangement: thread t owns kKoItems consecutive positions; kk[j] = key[p0 - 1 + j]
     const long long p0 = base + (long long)threadIdx.x * kKoItems;
+    static_assert(kKoItems == 4, "vector loads below assume 4 items per thread");
+    double kk[kKoItems + 2];
+    uint32_t ord[kKoItems];
+    if (p0 + kKoItems <= n && ((reinterpret_cast<uintptr_t>(key) | reinterpret_cast<uintptr_t>(order)) & 15) == 0) {
+        const double2 a = __ldcs(reinterpret_cast<const double2 *>(key + p0));
+        const double2 b = __ldcs(reinterpret_cast<const double2 *>(key + p0 + 2));
+        kk[1] = a.x; kk[2] = a.y; kk[3] = b.x; kk[4] = b.y;
+        const uint4 o = __ldcs(reinterpret_cast<const uint4 *>(order + p0));
+        ord[0] = o.x; ord[1] = o.y; ord[2] = o.z; ord[3] = o.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < kKoItems; ++q) {
+            kk[q + 1] = p0 + q < n ? key[p0 + q] : 0.0;
+            ord[q] = p0 + q < n ? order[p0 + q] : 0u;
+        }
+    }
+    kk[0] = (p0 > 0 && p0 <= n) ? key[p0 - 1] : 0.0;
+    kk[kKoItems + 1] = p0 + kKoItems < n ? key[p0 + kKoItems] : 0.0;
     bool head[kKoItems + 1];
 #pragma unroll
     for (int q = 0; q <= kKoItems; ++q) {
         const long long p = p0 + q;
-        head[q] = (p < n) ? ko_is_head(key, p) : (p == n);   // position n acts as a sentinel head
+        head[q] = (p < n) ? (p == 0 || kk[q + 1] != kk[q]) : (p == n);   // position n acts as a sentinel head
     }
+    // the tile's arcs land (tie runs that cross the tile boundary aside) in the mirrored range
+    // [lo, lo + len): they are staged in shared memory and written out coalesced
+    __shared__ uint32_t s_out[kKoTile];
+    const long long len = n - base < kKoTile ? n - base : kKoTile;
+    const long long lo = n - base - len;
+#pragma unroll
+    for (int q = 0; q < kKoItems; ++q) s_out[threadIdx.x + q * kKoThreads] = 0xffffffffu;   // no arc id (ids < n < 2^32 - 1)
     // forward: last head <= p   (thread-local, then warp / block max-scan)
     long long lastb[kKoItems];
     long long run = -1;
@@ -474,8 +530,17 @@ ko_scatter_kernel(const double *__restrict__ key, const uint32_t *__restrict__ o
             const long long b = lastb[q] >= 0 ? lastb[q] : pre;
             long long e = nexte[q] <= n ? nexte[q] : suf;
             const long long dstq = (n - e) + (p - b);
-            korder[dstq] = order[p];
+            const long long r = dstq - lo;
+            if (r >= 0 && r < len) s_out[r] = ord[q];
+            else korder[dstq] = ord[q];
         }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kKoItems; ++q) {
+        const int i = threadIdx.x + q * kKoThreads;
+        const uint32_t v = s_out[i];
+        if (i < len && v != 0xffffffffu) korder[lo + i] = v;
     }
 }
 
