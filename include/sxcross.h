@@ -119,6 +119,13 @@ SX_API int    sx_queue_from_order(const uint32_t *order_asc, int64_t n, int64_t 
 SX_API size_t sx_kruskal_order_workspace_bytes(int64_t n);
 SX_API int    sx_kruskal_order(const double *sorted_key, const uint32_t *order_asc, int64_t n,
                         uint32_t *korder_out, void *ws, size_t ws_bytes, void *stream);
+/* Head of that order when only the heaviest arcs are needed (the tree build reads ~8 N of them): the tie
+ * runs covering the last T ascending positions, flipped.  *n_head_h (HOST) = arcs written (>= T), or -1 when
+ * the runs hold more than T_cap arcs (flip everything instead).  ws: sx_kruskal_order_workspace_bytes(T_cap)
+ * + 256 bytes.  One stream synchronisation. */
+SX_API int    sx_kruskal_order_head(const double *sorted_key, const uint32_t *order_asc, int64_t n, int64_t T,
+                             int64_t T_cap, uint32_t *korder_out, int64_t *n_head_h, void *ws,
+                             size_t ws_bytes, void *stream);
 
 /* ---- K1d: head of the Kruskal order without a full sort ---------------------------------
  * `max_weight_spanning_tree` (tree_BI.py:32-59) passes all n weights to SciPy's Kruskal, which

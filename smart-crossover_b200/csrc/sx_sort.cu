@@ -31,11 +31,19 @@ struct RsDst {
 // random low mantissa bytes); this form costs the same for every distribution.
 __device__ __forceinline__ unsigned match_digit(unsigned d) {
     unsigned peers = 0xffffffffu;
+    // per bit: test (one LOP3 with a predicate result), ballot, select, one three-input logic op.  Written
+    // in PTX because the C++ form is canonicalised into a shift, two predicate set-ups and the same tail.
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const unsigned bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t, bal, m;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+            "selp.b32 m, 0xffffffff, 0, p;\n\t"
+            "lop3.b32 %0, %0, bal, m, 0x90;\n\t"               // peers & ~(bal ^ m): lanes whose bit equals mine
+            "}" : "+r"(peers) : "r"(d), "r"(1u << b));
     }
     return peers;
 }
@@ -193,16 +201,26 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
         for (int i = threadIdx.x; i < kWarps * 256; i += THREADS) (&sm.cnt[0][0])[i] = 0;
         unsigned long long key[kRsItems];
         uint32_t           val[kRsItems];
+        const int li0 = warp * (32 * kRsItems) + lane;
+        if (valid == kTile) {                                    // every tile but the last: no bounds checks
 #pragma unroll
-        for (int r = 0; r < kRsItems; ++r) {
-            const long long li = (long long)warp * (32 * kRsItems) + r * 32 + lane;
-            const long long gi = tbase + li;
-            if (li < valid) {
+            for (int r = 0; r < kRsItems; ++r) {
+                const long long gi = tbase + li0 + r * 32;
                 key[r] = rs_load_key<SRC>(src, gi);
                 val[r] = (SRC == kFromBuffer) ? src.vals[gi] : (uint32_t)gi;
-            } else {
-                key[r] = ~0ull;
-                val[r] = 0xffffffffu;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kRsItems; ++r) {
+                const int li = li0 + r * 32;
+                const long long gi = tbase + li;
+                if (li < valid) {
+                    key[r] = rs_load_key<SRC>(src, gi);
+                    val[r] = (SRC == kFromBuffer) ? src.vals[gi] : (uint32_t)gi;
+                } else {
+                    key[r] = ~0ull;
+                    val[r] = 0xffffffffu;
+                }
             }
         }
         __syncthreads();
@@ -544,6 +562,17 @@ ko_scatter_kernel(const double *__restrict__ key, const uint32_t *__restrict__ o
     }
 }
 
+// First position of the tie run that holds position `pos` of the ascending keys (lower bound of key[pos]).
+__global__ void ko_run_start_kernel(const double *__restrict__ key, long long pos, long long *out) {
+    const double v = key[pos];
+    long long lo = 0, hi = pos;
+    while (lo < hi) {
+        const long long mid = lo + (hi - lo) / 2;
+        if (key[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    *out = lo;
+}
+
 }  // namespace sx
 
 using namespace sx;
@@ -608,4 +637,26 @@ extern "C" int sx_kruskal_order(const double *sorted_key, const uint32_t *order_
     ko_scatter_kernel<<<(int)nb, kKoThreads, 0, st>>>(sorted_key, order_asc, n, carry_left, carry_right, korder_out);
     SX_LAUNCH_CHECK();
     return SX_OK;
+}
+
+// Head of the Kruskal order from the ascending sort: the tie runs that cover the last T positions, flipped.
+// The slice starts at a run head, so it is flipped exactly like the whole array would be.
+extern "C" int sx_kruskal_order_head(const double *sorted_key, const uint32_t *order_asc, int64_t n, int64_t T,
+                                     int64_t T_cap, uint32_t *korder_out, int64_t *n_head_h, void *ws,
+                                     size_t ws_bytes, void *stream) {
+    if (n <= 0 || T <= 0 || T_cap < T || !sorted_key || !order_asc || !korder_out || !n_head_h) return SX_ERR_INVALID;
+    if (!ws || ws_bytes < sx_kruskal_order_workspace_bytes(T_cap) + 256) return SX_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long start = 0;
+    if (T < n) {
+        long long *start_d = (long long *)ws;
+        ko_run_start_kernel<<<1, 1, 0, st>>>(sorted_key, n - T, start_d);
+        SX_LAUNCH_CHECK();
+        SX_CUDA(cudaMemcpyAsync(&start, start_d, sizeof(start), cudaMemcpyDeviceToHost, st));
+        SX_CUDA(cudaStreamSynchronize(st));
+    }
+    const long long m = n - start;
+    if (m > T_cap) { *n_head_h = -1; return SX_OK; }
+    *n_head_h = m;
+    return sx_kruskal_order(sorted_key + start, order_asc + start, m, korder_out, (char *)ws + 256, ws_bytes - 256, stream);
 }

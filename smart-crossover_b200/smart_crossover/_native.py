@@ -65,6 +65,7 @@ SIGNATURES = {
     "sx_queue_from_order": (_int, [_p, _i64, _p, _p]),
     "sx_kruskal_order_workspace_bytes": (_sz, [_i64]),
     "sx_kruskal_order": (_int, [_p, _p, _i64, _p, _p, _sz, _p]),
+    "sx_kruskal_order_head": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "sx_kruskal_prefix_workspace_bytes": (_sz, [_i64]),
     "sx_hist12_f64": (_int, [_p, _i64, _p, _p]),
     "sx_kruskal_prefix": (_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),

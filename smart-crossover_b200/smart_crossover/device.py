@@ -94,6 +94,22 @@ def kruskal_order(sorted_key: torch.Tensor, order: torch.Tensor) -> torch.Tensor
     return out
 
 
+def kruskal_order_head(sorted_key: torch.Tensor, order: torch.Tensor, T: int, T_cap: int | None = None):
+    """The first arcs of `kruskal_order` (at least T, whole tie runs) without flipping the whole array.
+    Returns an int32 tensor or None when the tie runs at the cut hold more than T_cap arcs."""
+    n = order.numel()
+    T = int(min(T, n))
+    T_cap = int(min(n, T_cap or max(2 * T, T + 65536)))
+    out = torch.empty(T_cap, dtype=torch.int32, device=order.device)
+    ws = _ws(lib.sx_kruskal_order_workspace_bytes(T_cap) + 256, order.device)
+    n_head = ctypes.c_int64(0)
+    check(lib.sx_kruskal_order_head(_ptr(sorted_key), _ptr(order), n, T, T_cap, _ptr(out), ctypes.byref(n_head),
+                                    _ptr(ws), ws.numel(), _stream()), "sx_kruskal_order_head")
+    if n_head.value < 0:
+        return None
+    return out[:n_head.value]
+
+
 def kruskal_prefix(weights: torch.Tensor, T: int, T_cap: int | None = None, hist: torch.Tensor | None = None):
     """Head of the Kruskal order (descending weight, ties by ascending id): every arc at least as heavy
     as the T-th heaviest.  Returns an int32 tensor (uint32 bit patterns) or None when more than T_cap

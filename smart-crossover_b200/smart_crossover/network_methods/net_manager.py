@@ -82,6 +82,10 @@ class _SortedFlows:
     def kruskal_order(self):
         return _dev().kruskal_order(self.sorted_key, self.order)
 
+    def kruskal_order_head(self, T: int):
+        """The first >= T arcs of the Kruskal order (whole tie runs), or None if the runs are too long."""
+        return _dev().kruskal_order_head(self.sorted_key, self.order, T)
+
     def matches(self, weights: np.ndarray) -> bool:
         return weights is self.scores_np or (weights.shape == self.scores_np.shape
                                              and np.array_equal(weights, self.scores_np, equal_nan=True))

@@ -39,9 +39,10 @@ def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlo
 
     Large instances first try the head of the Kruskal order only (`sx_kruskal_prefix`: the 16 N
     heaviest arcs, three streaming passes instead of a full argsort); the spanning tree is almost
-    always complete inside it (last tree arc at rank ~8 N).  If not, or when the
-    full sort already exists (`get_sorted_flows` ran on these weights), the full order is used.  Both
-    give the same tree: a prefix of a strict total order is unique."""
+    always complete inside it (last tree arc at rank ~8 N).  When the full sort
+    already exists (`get_sorted_flows` ran on these weights) the same head is cut from it
+    (`sx_kruskal_order_head`).  If the forest is incomplete the whole order is used.  All give the same
+    tree: a prefix of a strict total order is unique."""
     dev = _dev()
     S, D = np.asarray(ot.M).shape
     N, n = S + D, S * D
@@ -59,6 +60,13 @@ def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlo
         _sorted = _SortedFlows(w_t, flow_weights)
     elif not have_sort:
         _sorted = _SortedFlows(_cuda(flow_weights), flow_weights)
+    if n > 4 * PREFIX_FACTOR * N:
+        # the sort exists: only its heaviest 16 N arcs are put into Kruskal order first
+        head = _sorted.kruskal_order_head(PREFIX_FACTOR * N)
+        if head is not None:
+            tree_t, n_t = dev.kruskal(head, N, S=S, D=D)
+            if int(n_t.item()) == N - 1:
+                return tree_t, N - 1
     tree_t, n_t = dev.kruskal(_sorted.kruskal_order(), N, S=S, D=D)
     return tree_t, int(n_t.item())
 

@@ -44,6 +44,31 @@ def sort_pipeline(dev, key_t):
     return order, skey, queue, korder
 
 
+def test_kruskal_order_head_is_the_head_of_the_flipped_order(dev):
+    """sx_kruskal_order_head cuts whole tie runs from the end of the ascending sort: same arcs, same order
+    as the first entries of the full Kruskal order; too long a run at the cut is reported."""
+    rng = np.random.default_rng(5)
+    for n, T, kind in [(100003, 1000, "random"), (100003, 5000, "ties"), (4096 * 3 + 1, 4097, "ties"),
+                       (777, 777, "random"), (50000, 49999, "ties"), (10, 3, "random")]:
+        key = rng.random(n)
+        if kind == "ties":
+            key = np.round(key * 300) / 300                          # runs of ~n / 300 equal keys
+        order, skey, queue, korder = sort_pipeline(dev, cu(key))
+        full = u32(korder)
+        head = dev.kruskal_order_head(skey, order, T, T_cap=n)
+        assert head is not None
+        head = u32(head)
+        assert T <= head.size <= n
+        assert np.array_equal(head, full[:head.size])
+        if head.size < n:                                            # the cut is at a run boundary
+            assert key[full[head.size]] < key[head[-1]]
+    key = np.zeros(5000)
+    key[:10] = 1.0
+    order, skey = dev.argsort_f64(cu(key))
+    assert np.array_equal(u32(dev.kruskal_order_head(skey, order, 5, T_cap=20)), np.arange(10))
+    assert dev.kruskal_order_head(skey, order, 11, T_cap=20) is None  # the zero run has 4990 arcs
+
+
 # ---- K1a + K1c ------------------------------------------------------------------------------
 def test_ot_scores_special_values_bitwise(dev):
     """K1a against NumPy on the awkward inputs: negative / zero / -0.0 / inf / NaN flows, zero, negative,
