@@ -274,8 +274,9 @@ pf_split_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, doubl
         __syncthreads();
     };
     // Hot loop.  A weight's level-0 bin is decided from the high word of the double (pf_image32); every
-    // lane packs its hits into bit masks, and only a warp that holds a hit (a fraction of a percent of
-    // the arcs are hits) runs ONE packed warp scan to reserve stage slots in both lists.
+    // lane packs its hits into bit masks.  Hits are a fraction of a percent of the arcs: a warp with hits
+    // in a few lanes lets those lanes reserve their own stage slots; a dense warp runs ONE packed warp
+    // scan that reserves the slots of both lists.
     const bool     none_above = b1 >= (unsigned)kPfBins - 1;
     const unsigned sel_lo = none_above ? 0xffffffffu : (b1 + 1) << 20;             // image32 >= sel_lo: bin > b1
     auto put = [&](int which, unsigned slot, double v, long long id) {
@@ -306,7 +307,23 @@ pf_split_kernel(const double *__restrict__ w, long long n, PrefixCtl *ctl, doubl
             }
         }
         const unsigned mine = (unsigned)__popc(sel) | ((unsigned)__popc(bnd) << 16);
-        if (__any_sync(0xffffffffu, mine != 0)) {
+        const unsigned hit_lanes = __ballot_sync(0xffffffffu, mine != 0);
+        if (hit_lanes != 0 && __popc(hit_lanes) <= 8) {
+            // sparse (the usual case: well under one hit per warp and load batch): only the lanes that hold
+            // a hit run, each reserving its stage slots itself
+            if (mine) {
+#pragma unroll
+                for (int u = 0; u < kPfBatch; ++u) {
+                    if (((sel | bnd) >> (2 * u)) & 3u) {
+                        const long long i = (blk + (long long)u * gridDim.x) * kPfThreads + threadIdx.x;
+                        if ((sel >> (2 * u)) & 1u) put(0, atomicAdd(&s_cnt[0], 1u), v[u].x, 2 * i);
+                        else if ((bnd >> (2 * u)) & 1u) put(1, atomicAdd(&s_cnt[1], 1u), v[u].x, 2 * i);
+                        if ((sel >> (2 * u + 1)) & 1u) put(0, atomicAdd(&s_cnt[0], 1u), v[u].y, 2 * i + 1);
+                        else if ((bnd >> (2 * u + 1)) & 1u) put(1, atomicAdd(&s_cnt[1], 1u), v[u].y, 2 * i + 1);
+                    }
+                }
+            }
+        } else if (hit_lanes != 0) {
             unsigned incl = mine;                                // packed inclusive scan: <= 256 hits per list and warp
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {

@@ -138,34 +138,53 @@ rs_upsweep_kernel(RsSrc src, long long n, int shift, long long keys_per_block, u
     }
 }
 
-// ---- scan: exclusive prefix over hist[digit][block] (digit-major), one CTA, 8192 entries per sweep ----
+// ---- scan: exclusive prefix over hist[digit][block] (digit-major), one CTA ----
+// Thread t owns one contiguous chunk of ceil(count / 1024) entries (a multiple of 4: 128-bit accesses):
+// it sums the chunk, the 1024 sums are scanned through shuffles and shared memory, and the chunk is
+// rewritten with the running prefix.  One pass with a single block-wide barrier; the former sweep loop
+// (8192 entries per sweep, three barriers each) took 20 us for the 40 K counters of a 640 K-key sort and
+// 135 us for the 227 K counters of a large one.  count is a multiple of 256.
 __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *hist, int count) {
     __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    constexpr int kPer = 8;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    int per = (count + 1023) / 1024;
+    per = (per + 3) & ~3;
+    const int beg = threadIdx.x * per;
+    int end = beg + per;
+    if (end > count) end = count;
+    uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+    uint32_t sum = 0;
+#pragma unroll 4
+    for (int i = beg; i < end; i += 4) {
+        const uint4 q = h4[i >> 2];
+        sum += q.x + q.y + q.z + q.w;
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    for (int base = 0; base < count; base += 1024 * kPer) {
-        const int i0 = base + threadIdx.x * kPer;
-        uint32_t v[kPer], sum = 0;
+    const uint32_t wt = warp_tot[lane];                      // every warp scans the 32 warp totals
+    uint32_t wincl = wt;
 #pragma unroll
-        for (int q = 0; q < kPer; ++q) { v[q] = (i0 + q < count) ? hist[i0 + q] : 0u; sum += v[q]; }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        uint32_t run = carry + incl - sum;
-        for (int w = 0; w < warp; ++w) run += warp_tot[w];
-#pragma unroll
-        for (int q = 0; q < kPer; ++q) { if (i0 + q < count) hist[i0 + q] = run; run += v[q]; }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = run;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+    }
+    const uint32_t wbase = __shfl_sync(0xffffffffu, wincl - wt, warp);
+    uint32_t run = wbase + incl - sum;
+#pragma unroll 4
+    for (int i = beg; i < end; i += 4) {
+        const uint4 q = h4[i >> 2];
+        uint4 o;
+        o.x = run; run += q.x;
+        o.y = run; run += q.y;
+        o.z = run; run += q.z;
+        o.w = run; run += q.w;
+        h4[i >> 2] = o;
     }
 }
 
