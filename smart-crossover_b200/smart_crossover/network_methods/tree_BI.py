@@ -32,6 +32,12 @@ def tree_basis_identify(ot_manager: OTManager, flow_weights: np.ndarray) -> Tupl
 
 
 PREFIX_FACTOR = 16      # the Kruskal order's head handed to the union-find first: 16 N arcs
+PREFIX_MIN_ARCS = 1 << 21   # below ~2 M arcs a full argsort is as fast as the prefix path's fixed cost (784^2: 0.25 vs 0.35 ms)
+
+
+def use_prefix_path(n: int, N: int) -> bool:
+    """Whether bare weights go through `sx_kruskal_prefix` (large, dense) or a full argsort."""
+    return n >= PREFIX_MIN_ARCS and n > 4 * PREFIX_FACTOR * N
 
 
 def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlows = None):
@@ -50,7 +56,7 @@ def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlo
     have_sort = _sorted is not None and _sorted.matches(flow_weights)
     if np.isnan(flow_weights).any():
         raise ValueError("flow weights contain NaN (a zero marginal?): the spanning tree is undefined")
-    if not have_sort and n > 4 * PREFIX_FACTOR * N:
+    if not have_sort and use_prefix_path(n, N):
         w_t = _cuda(flow_weights.ravel())
         head = dev.kruskal_prefix(w_t, PREFIX_FACTOR * N)
         if head is not None:

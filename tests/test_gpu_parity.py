@@ -284,17 +284,21 @@ def test_tree_from_prefix_equals_tree_from_full_sort(dev):
     F = orc.ot_flow_scores(x, s, d)
     ot = OptTransport(s, d, M)
     tree_ref = orc.max_weight_spanning_tree(F, S, D)
-    assert S * D > 4 * tree_BI.PREFIX_FACTOR * (S + D)              # takes the prefix path
+    assert not tree_BI.use_prefix_path(S * D, S + D)                  # small instance: full argsort by default
     assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F), tree_ref)
-    mgr = OTManager(ot)
-    q, F2 = mgr.get_sorted_flows(x)                                   # full sort exists: reused
-    assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F2, _sorted=mgr._sorted), tree_ref)
-    old = tree_BI.PREFIX_FACTOR
+    old, old_min = tree_BI.PREFIX_FACTOR, tree_BI.PREFIX_MIN_ARCS
     try:
+        tree_BI.PREFIX_MIN_ARCS = 0                                   # force the path large instances take
+        assert tree_BI.use_prefix_path(S * D, S + D)
+        assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F), tree_ref)
+        mgr = OTManager(ot)
+        q, F2 = mgr.get_sorted_flows(x)                               # full sort exists: its head is reused
+        assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F2, _sorted=mgr._sorted), tree_ref)
         tree_BI.PREFIX_FACTOR = 1                                     # head too short: falls back, same tree
         assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F), tree_ref)
+        assert np.array_equal(tree_BI.max_weight_spanning_tree(ot, F2, _sorted=mgr._sorted), tree_ref)
     finally:
-        tree_BI.PREFIX_FACTOR = old
+        tree_BI.PREFIX_FACTOR, tree_BI.PREFIX_MIN_ARCS = old, old_min
 
 
 @pytest.mark.parametrize("name", OT_FULL)
