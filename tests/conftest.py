@@ -15,3 +15,8 @@ for p in (ROOT, os.path.join(ROOT, "smart-crossover_b200"), os.path.join(ROOT, "
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # SX_SORT_TUNING=<code> runs the suite under another radix-downsweep shape (sx_sort_set_tuning)
+    tuning = os.environ.get("SX_SORT_TUNING")
+    if tuning:
+        from smart_crossover._native import lib
+        assert lib.sx_sort_set_tuning(int(tuning)) == 0, f"bad SX_SORT_TUNING={tuning}"
