@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--sweep-ab", default="", metavar="I,J,..",
                     help="with --sweep: interleaved A/B timing of these TMA shape indices only")
     ap.add_argument("--score-ctas", type=int, default=0, help="sx_score_set_tuning (3 or 4 resident CTAs per SM)")
+    ap.add_argument("--kruskal-chunk", type=int, default=0, help="sx_kruskal_set_tuning (first chunk in quarters of N)")
     ap.add_argument("--tree-only", type=int, default=0, metavar="S",
                     help="only time the tree-basis build on an S x S instance and exit")
     return ap.parse_args()
@@ -413,6 +414,9 @@ def main():
     if args.score_ctas:
         from smart_crossover._native import lib as _lib
         assert _lib.sx_score_set_tuning(args.score_ctas) == 0
+    if args.kruskal_chunk:
+        from smart_crossover._native import lib as _lib
+        assert _lib.sx_kruskal_set_tuning(args.kruskal_chunk) == 0
     if args.tree_only:
         if args.tree_only < 0:                           # --tree-only -1: the MCF configuration (1M nodes / 10M arcs)
             print(json.dumps(time_mcf_path(1_000_000, 10_000_000, device, reps=2)), flush=True)

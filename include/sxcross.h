@@ -157,6 +157,7 @@ SX_API int    sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int6
  * the implicit OT graph (arc k = (k / D, S + k % D)), else tail[k], head[k].
  *   tree_out (capacity N-1): kept arc ids, ascending.  n_tree_out: their number.
  */
+SX_API int    sx_kruskal_set_tuning(int first_chunk_quarters_of_N);   /* first chunk of the order = q N / 4 arcs (0: default) */
 SX_API size_t sx_kruskal_workspace_bytes(int64_t N, int64_t n);
 SX_API int    sx_kruskal(const uint32_t *korder, int64_t n, const int32_t *tail, const int32_t *head,
                   int64_t S, int64_t D, int64_t N, int64_t *tree_out, int64_t *n_tree_out,

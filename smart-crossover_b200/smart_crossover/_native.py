@@ -59,6 +59,7 @@ SIGNATURES = {
     "sx_score_mcf": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "sx_sort_set_tuning": (_int, [_int]),
     "sx_score_set_tuning": (_int, [_int]),
+    "sx_kruskal_set_tuning": (_int, [_int]),
     "sx_argsort_workspace_bytes": (_sz, [_i64]),
     "sx_argsort_f64": (_int, [_p, _i64, _p, _p, _p, _sz, _p]),
     "sx_argsort_u64": (_int, [_p, _i64, _int, _p, _p, _p, _sz, _p]),
