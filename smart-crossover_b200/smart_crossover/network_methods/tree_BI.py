@@ -44,7 +44,7 @@ def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlo
     """(tree arc ids on the device, their number) for the complete bipartite graph of `ot`.
 
     Large instances first try the head of the Kruskal order only (`sx_kruskal_prefix`: the 16 N
-    heaviest arcs, three streaming passes instead of a full argsort); the spanning tree is almost
+    heaviest arcs, one or two streaming passes instead of a full argsort); the spanning tree is almost
     always complete inside it (last tree arc at rank ~8 N).  When the full sort
     already exists (`get_sorted_flows` ran on these weights) the same head is cut from it
     (`sx_kruskal_order_head`).  If the forest is incomplete the whole order is used.  All give the same
