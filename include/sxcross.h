@@ -47,6 +47,7 @@ extern "C" {
 #define SX_ERR_UNALIGNED       -6   /* TMA path needs 16-byte aligned base and even ld */
 #define SX_ERR_NO_DEVICE       -7   /* no sm_100 device / driver entry point missing */
 #define SX_ERR_PEER_TIMEOUT    -8   /* sx_exchange_blocks: a peer never raised its flag */
+#define SX_ERR_PUSH_ASSERT     -9   /* sx_push_tree_h: the reference's assertions would fire (tree_BI.py:93-94) */
 
 #define SX_ABI_VERSION 2
 
@@ -190,6 +191,19 @@ SX_API int    sx_tree_flows(const int64_t *tree, int64_t n_tree, const int32_t *
                      int64_t S, int64_t D, int64_t N, const double *b, int plus_convention,
                      int64_t root, double *flow_out, int32_t *status_out, void *ws, size_t ws_bytes,
                      void *stream);
+
+/* ---- f1 (host part): push phase of tree_basis_identify ------------------------------------
+ * Replaces the loop of `push_tree_to_bfs` (tree_BI.py:81-113): for every negative tree flow (row-major
+ * order, fixed before the first push) theta = first minimum of (-x[I1,J1], x[I1,J2], x[I2,J1]) is pushed
+ * around the 4-cycle (I1,J1) (I2,J1) (I2,J2) (I1,J2), with J2 / I2 = np.argmax of row I1 / column J1,
+ * until the flow is >= 0.  HOST buffers (the loop is sequential): tree_h (arc k = i * D + j) with its
+ * primal flows flow_h (from sx_tree_flows).  Works on the sparse support (tree arcs + corners created
+ * by pushes) instead of the reference's dense S x D scratch.  pos_arc_h (capacity cap): the arcs that
+ * carry positive flow afterwards, i.e. vbasis == 0 (tree_BI.py:112-113), in no particular order;
+ * *n_pos_h = their number (returned with SX_ERR_WORKSPACE when cap is too small: call again),
+ * *push_iter_h = pushes made.  SX_ERR_PUSH_ASSERT where the reference's asserts (:93-94) would fire. */
+SX_API int    sx_push_tree_h(const int64_t *tree_h, const double *flow_h, int64_t n_tree, int64_t S, int64_t D,
+                      int64_t *pos_arc_h, int64_t cap, int64_t *n_pos_h, int64_t *push_iter_h);
 
 /* ---- K4: pricing ----------------------------------------------------------------------
  * sx_price_dense_ot replaces `c - A.T @ y` + `np.all(rc >= -tol)` over the dense OT cost

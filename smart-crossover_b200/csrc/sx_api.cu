@@ -21,6 +21,7 @@ extern "C" const char *sx_error_string(int code) {
         case SX_ERR_UNALIGNED: return "cost matrix not 16-byte aligned or odd leading dimension";
         case SX_ERR_NO_DEVICE: return "no usable sm_100 device / driver entry point";
         case SX_ERR_PEER_TIMEOUT: return "a peer GPU did not deliver its block in time";
+        case SX_ERR_PUSH_ASSERT: return "push phase: no positive flow to push against (reference assertion, tree_BI.py:93-94)";
         default: return "unknown error";
     }
 }

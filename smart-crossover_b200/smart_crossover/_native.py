@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libsxcross.so")
 SX_OK = 0
 SX_ERR_NOT_SPANNING = -5
 SX_ERR_UNALIGNED = -6
+SX_ERR_WORKSPACE = -3
+SX_ERR_PUSH_ASSERT = -9
 SX_PLUS_IS_HEAD = 0
 SX_PLUS_IS_TAIL = 1
 SX_TOPK_MAX_K = 1024
@@ -95,6 +97,7 @@ SIGNATURES = {
     "sx_sinkhorn_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_sinkhorn_ot": (_int, [_p, _i64, _i64, _i64, _p, _p, _dbl, _i64, _dbl, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sx_price_dense_ot_h": (_int, [_p, _p, _i64, _i64, _p, _dbl, _i64, _p, _p, _p, _p, _p]),
+    "sx_push_tree_h": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

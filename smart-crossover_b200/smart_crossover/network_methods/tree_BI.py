@@ -7,11 +7,12 @@
   push_tree_to_bfs          -> device: the tree primal flows (`B x = b[:-1]`, tree_BI.py:74-76, SuperLU in
                                the reference) are subtree sums of b on the same Euler tour
                                (sx_tree_flows, double-double prefix sums);
-                               host: the sequential push loop (tree_BI.py:81-110) walks the O(N + pushes)
-                               non-zeros instead of a dense S x D scratch.
+                               host (native, sx_push_tree_h): the sequential push loop (tree_BI.py:81-110)
+                               walks the O(N + pushes) non-zeros instead of a dense S x D scratch.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Tuple
 
 import numpy as np
@@ -113,58 +114,25 @@ def push_tree_to_bfs(ot_manager: OTManager, tree: np.ndarray, _flows: np.ndarray
     ot = ot_manager.ot
     S, D = ot.s.size, ot.d.size
     tree = np.asarray(tree, dtype=np.int64)
-    ti, tj = tree // D, tree % D
     flow = np.asarray(_flows, dtype=np.float64) if _flows is not None else tree_flows(ot, tree)
 
-    row_nz = [dict() for _ in range(S)]
-    col_nz = [dict() for _ in range(D)]
-    for i, j, f in zip(ti.tolist(), tj.tolist(), flow.tolist()):
-        row_nz[i][j] = f
-        col_nz[j][i] = f
-
-    def get(i, j):
-        return row_nz[i].get(j, 0.0)
-
-    def put(i, j, val):
-        row_nz[i][j] = val
-        col_nz[j][i] = val
-
-    def argmax(entries, what):
-        """First index of the maximum, as np.argmax over the dense row/column would give; the
-        maximum must be positive (the reference asserts it, tree_BI.py:93)."""
-        best, best_val = -1, 0.0
-        for idx, val in entries.items():
-            if val > best_val or (val == best_val and best >= 0 and idx < best):
-                best, best_val = idx, val
-        assert best >= 0, f"push_tree_to_bfs: no positive flow in this {what}"
-        return best
-
-    negative = [(i, j) for i, j, f in zip(ti.tolist(), tj.tolist(), flow.tolist()) if f < 0]
-    push_iter = 0
-    for I1, J1 in negative:                      # row-major order, fixed before pushing (tree_BI.py:82)
-        if get(I1, J1) >= 0:
+    # the push loop itself is sequential host work on the sparse support (libsxcross, sx_push_tree_h)
+    from smart_crossover import _native
+    tree = np.ascontiguousarray(tree, dtype=np.int64)
+    flow = np.ascontiguousarray(flow, dtype=np.float64)
+    cap = 2 * int(tree.size) + 1024
+    while True:
+        pos = np.empty(cap, dtype=np.int64)
+        n_pos, push_iter = ctypes.c_int64(0), ctypes.c_int64(0)
+        rc = _native.lib.sx_push_tree_h(tree.ctypes.data, flow.ctypes.data, int(tree.size), S, D, pos.ctypes.data, cap,
+                                        ctypes.byref(n_pos), ctypes.byref(push_iter))
+        if rc == _native.SX_ERR_WORKSPACE:                       # more corners were created than guessed
+            cap = int(n_pos.value)
             continue
-        J2 = argmax(row_nz[I1], "row")
-        I2 = argmax(col_nz[J1], "column")
-        while get(I1, J1) < 0:
-            assert get(I2, J1) > 0 and get(I1, J2) > 0
-            assert get(I2, J2) == 0
-            cands = (-get(I1, J1), get(I1, J2), get(I2, J1))
-            flag = int(np.argmin(cands))
-            theta = cands[flag]
-            put(I1, J1, get(I1, J1) + theta)
-            put(I2, J1, get(I2, J1) - theta)
-            put(I1, J2, get(I1, J2) - theta)
-            put(I2, J2, get(I2, J2) + theta)
-            if flag == 1:
-                J2 = argmax(row_nz[I1], "row")
-            elif flag == 2:
-                I2 = argmax(col_nz[J1], "column")
-            push_iter += 1
-
+        if rc == _native.SX_ERR_PUSH_ASSERT:                     # the reference asserts here (tree_BI.py:93-94)
+            raise AssertionError("push_tree_to_bfs: no positive flow to push against (reference tree_BI.py:93-94)")
+        _native.check(rc, "sx_push_tree_h")
+        break
     vbasis = -np.ones(ot_manager.n)
-    for i in range(S):
-        for j, f in row_nz[i].items():
-            if f > 0:
-                vbasis[i * D + j] = 0
-    return vbasis, push_iter
+    vbasis[pos[:n_pos.value]] = 0
+    return vbasis, int(push_iter.value)

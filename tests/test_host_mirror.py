@@ -4,7 +4,9 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import cases
 from golden_util import OT_FULL, Fixture
+from oracle import network_oracle as orc
 from smart_crossover.formats import MinCostFlow, OptTransport, ot_incidence
 from smart_crossover.network_methods.net_manager import MCFManagerStd, OTManager
 from smart_crossover.network_methods.tree_BI import push_tree_to_bfs
@@ -46,6 +48,52 @@ def test_push_tree_to_bfs_matches_golden(name):
     vbasis, push_iter = push_tree_to_bfs(mgr, fx.out["tree"], _flows=fx.out["tree_flows"])
     assert push_iter == int(fx.out["push_iter"])
     assert np.array_equal(vbasis.astype(np.int64), fx.out["vbasis_tree"])
+
+
+def test_native_push_loop_matches_the_oracle_on_random_instances():
+    """sx_push_tree_h (host C++, sparse support) against the oracle's dense restatement of tree_BI.py:77-114 on
+    random shapes: same basis, same push count; the capacity-retry protocol of the C entry point."""
+    import ctypes
+    from smart_crossover import _native
+    rng = np.random.default_rng(17)
+    total_pushes = 0
+    for trial in range(40):
+        S, D = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+        s, d, M = cases.ot_points(S, D, 500 + trial)
+        x = cases.interior_flow(s, d, M, 500 + trial, 0.33)
+        F = orc.ot_flow_scores(x, s, d)
+        tree = orc.max_weight_spanning_tree(F, S, D)
+        if tree.size != S + D - 1:
+            continue
+        flows = orc.ot_tree_flows(tree, s, d)
+        mgr = OTManager(OptTransport(s, d, M))
+        try:
+            vb_ref, it_ref = orc.push_tree_to_bfs(tree, flows, S, D)
+        except AssertionError:
+            with pytest.raises(AssertionError):
+                push_tree_to_bfs(mgr, tree, _flows=flows)
+            continue
+        vb, it = push_tree_to_bfs(mgr, tree, _flows=flows)
+        assert it == it_ref and np.array_equal(vb.astype(np.int64), vb_ref)
+        total_pushes += it
+        # capacity protocol: too small a buffer reports the size needed, the second call fills it
+        n_pos, n_it = ctypes.c_int64(0), ctypes.c_int64(0)
+        tr, fl = np.ascontiguousarray(tree, np.int64), np.ascontiguousarray(flows, np.float64)
+        small = np.empty(1, dtype=np.int64)
+        rc = _native.lib.sx_push_tree_h(tr.ctypes.data, fl.ctypes.data, tr.size, S, D, small.ctypes.data, 1,
+                                        ctypes.byref(n_pos), ctypes.byref(n_it))
+        assert rc == _native.SX_ERR_WORKSPACE and n_pos.value == int((vb_ref == 0).sum()) and n_it.value == it_ref
+        buf = np.empty(n_pos.value, dtype=np.int64)
+        rc = _native.lib.sx_push_tree_h(tr.ctypes.data, fl.ctypes.data, tr.size, S, D, buf.ctypes.data, buf.size,
+                                        ctypes.byref(n_pos), ctypes.byref(n_it))
+        assert rc == 0 and np.array_equal(np.sort(buf), np.flatnonzero(vb_ref == 0))
+    assert total_pushes > 50                                        # the loop was really exercised
+    # argument validation
+    n_pos, n_it = ctypes.c_int64(0), ctypes.c_int64(0)
+    bad = np.array([99], dtype=np.int64)
+    one = np.array([1.0])
+    assert _native.lib.sx_push_tree_h(bad.ctypes.data, one.ctypes.data, 1, 3, 3, bad.ctypes.data, 1,
+                                      ctypes.byref(n_pos), ctypes.byref(n_it)) == -1
 
 
 @pytest.mark.parametrize("name", OT_FULL)
