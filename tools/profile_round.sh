@@ -2,7 +2,7 @@
 # Round profile (v8): full GPU test suite, bench line, launch lists, ncu full captures of the tree-build kernels.
 # Run under gpurun from the repo root; everything lands in gpurun_out/.  The pricing / selection kernels are
 # unchanged since the v5 captures (r01_price_tma_v5, r01_topk_select_v5); the sort / Kruskal-order captures
-# of the current code are r01_sort_v8 / r01_ko_v8 (tools/probe_call4.sh).
+# of the current code are r01_sort_v8 / r01_ko_v8 (tools/profile_sort.sh).
 O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/pytest_v8_final.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_v8_final.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_v8.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke_v8.log
