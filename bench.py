@@ -243,8 +243,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"dense synthetic OT {S}x{D} pricing pass (row sample)", "S": S, "D": D,
-                       "topk": args.topk, "tol": TOL},
+            "config": {"workload": f"dense synthetic OT {S}x{D} ({S * D:.3g} arcs, {8 * S * D / 1e9:.1f} GB fp64 cost) "
+                                   f"column-generation pricing pass, host CPU on a bounded row sample per step",
+                       "S": S, "D": D, "topk": args.topk, "tol": TOL, "rows_per_step": rows2},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
