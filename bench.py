@@ -21,6 +21,7 @@ arcs (NCCL all-gather + merge when N > 1).
 `roofline`: achieved HBM GB/s of the pricing kernel alone (8 B per arc / CUDA-event time).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -57,6 +58,10 @@ def parse():
     ap.add_argument("--exchange", default="ll", choices=["ll", "p2p", "nccl"],
                     help="N > 1: exchange of the result blocks: NVLink flag-in-data stores polled by the merge "
                          "kernel (default), peer stores + flag + wait kernel, or NCCL all-gather")
+    ap.add_argument("--no-fused", action="store_true",
+                    help="price / select / push as separate launches (round-1 path) instead of the fused kernel")
+    ap.add_argument("--no-c4", action="store_true", help="skip the second leg (dense OT 20 000 x 20 000)")
+    ap.add_argument("--c4-size", type=int, default=20000)
     ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
     ap.add_argument("--sweep-ab", default="", metavar="I,J,..",
                     help="with --sweep: interleaved A/B timing of these TMA shape indices only")
@@ -425,83 +430,224 @@ def main():
         print(json.dumps(time_tree_build(args.tree_only, args.tree_only, device, reps=2)), flush=True)
         return
 
+    ctx = {"world": world, "rank": rank, "device": device, "barrier": barrier, "max_over_ranks": max_over_ranks}
     S = D = args.size
     if args.rows:
         S = args.rows
+    if args.sweep:
+        row0, S_loc = row_partition(S, world, rank)
+        P, Q, a = make_points(S, D, device)
+        M_loc = make_slab(P, Q, row0, S_loc)
+        y_dev = planted_duals(P, Q, a, M_loc, row0, args.violators, world)
+        sp = ShardedDensePricer(M_loc, S, row0, args.topk, TOL, variant=args.variant, exchange=args.exchange)
+        sweep(args, sp, y_dev, S_loc, D, lib, dev)
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    steps, warmup = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    main_leg = pricing_leg(args, S, D, ctx, steps, warmup, sampler=sampler, want_cpu=not args.no_cpu, want_cold=True)
+    # second, shorter leg: BASELINE.json configs[3] (dense OT 20 000 x 20 000, "pricing at 1/2/4/8 B200")
+    c4_leg = None
+    if not args.no_c4 and (S, D) != (args.c4_size, args.c4_size):
+        c4_leg = pricing_leg(args, args.c4_size, args.c4_size, ctx, steps, warmup, sampler=None, want_cpu=False,
+                             want_cold=False)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    tree = None
+    if world == 1 and not args.no_tree:
+        torch.cuda.empty_cache()
+        tree = [time_tree_build(784, 784, device), time_tree_build(20000, 20000, device, reps=1),
+                time_mcf_path(1_000_000, 10_000_000, device, reps=1)]
+
+    def roofline_of(leg):
+        achieved = 8.0 * leg["S_loc"] * leg["D"] / (leg["kernel_ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": committed_traffic(leg["S_loc"], leg["D"]),
+                "peak_source": peak_src, "kernel": leg["kernel"], "kernel_ms": round(leg["kernel_ms"], 4),
+                "kernel_ms_per_rank": leg["kernel_ms_per_rank"], "algorithmic_bytes_per_arc": 8,
+                "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
+
+    def workload_of(leg):
+        S_, D_ = leg["S"], leg["D"]
+        return (f"dense synthetic OT {S_}x{D_} ({S_ * D_:.3g} arcs, {8 * S_ * D_ / 1e9:.1f} GB fp64 cost) "
+                f"column-generation pricing pass, row-sharded over {world} GPU(s)")
+
+    L = main_leg
+    line = {"metric": METRIC, "value": L["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": L["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_of(L),
+                       "S": S, "D": D, "topk": args.topk, "tol": TOL, "violating_arcs": L["violating_arcs"],
+                       "rows_per_gpu": L["S_loc"], "variant": args.variant, "exchange": L["exchange"],
+                       "fused": L["fused"],
+                       "l2": f"inputs larger than L2 ({8 * L['S_loc'] * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
+            "roofline": roofline_of(L), "cpu_baseline": L["cpu_baseline"],
+            "e2e": L["e2e"], "e2e_pinned": L["e2e_pinned"],
+            "topk_digest": L["topk_digest"], "merge_check": L["merge_check"],
+            "stage_us_rank0": L["stage_us"], "e2e_cold": L["e2e_cold"], "gpu_launches": L["gpu_launches"],
+            "clocks": L["clocks"], "tree_build": tree}
+    if c4_leg is not None:
+        C = c4_leg
+        line["c4"] = {"workload": workload_of(C), "value": C["value"], "unit": UNIT, "ms_per_step": C["ms_per_step"],
+                      "steps": steps, "rows_per_gpu": C["S_loc"], "violating_arcs": C["violating_arcs"],
+                      "roofline": roofline_of(C), "stage_us_rank0": C["stage_us"], "e2e": C["e2e"],
+                      "e2e_pinned": C["e2e_pinned"], "topk_digest": C["topk_digest"],
+                      "merge_check": C["merge_check"], "gpu_launches": C["gpu_launches"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def committed_traffic(S_loc, D):
+    """dram read + write bytes of one pricing-kernel launch from the committed `ncu --set full` captures
+    (profiles/price_traffic.json: one entry per slab shape), or None when that shape was not captured."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "price_traffic.json")))
+        for e in tj if isinstance(tj, list) else [tj]:
+            if (e["S_loc"], e["D"]) == (S_loc, D):
+                return e["traffic_bytes"]
+    except Exception:
+        pass
+    return None
+
+
+def topk_digest(ids, rc, count, min_rc):
+    """Digest of a pricing result (top-K ids + reduced-cost bits + violator count + min): one value for every
+    N proves the row-sharded, exchanged and merged result equals the single-GPU one."""
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(ids, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(rc, dtype=np.float64).tobytes())
+    h.update(np.int64(count).tobytes())
+    h.update(np.float64(min_rc).tobytes())
+    return h.hexdigest()[:16]
+
+
+def pricing_leg(args, S, D, ctx, steps, warmup, sampler, want_cpu, want_cold):
+    """Times one dense-OT pricing configuration on the ranks of this job: device-resident arm, stage
+    split, N-rank result check, end-to-end arm(s), optional cold upload and CPU baseline."""
+    import torch
+    import torch.distributed as dist
+    from smart_crossover._native import lib
+    from smart_crossover.network_methods.sharded import ShardedDensePricer, row_partition
+    world, rank, device = ctx["world"], ctx["rank"], ctx["device"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
     K = args.topk
     row0, S_loc = row_partition(S, world, rank)
     P, Q, a = make_points(S, D, device)
     M_loc = make_slab(P, Q, row0, S_loc)
     y_dev = planted_duals(P, Q, a, M_loc, row0, args.violators, world)
     y_host = y_dev.cpu().numpy()
-    sp = ShardedDensePricer(M_loc, S, row0, K, TOL, variant=args.variant, exchange=args.exchange)
-
-    if args.sweep:
-        sweep(args, sp, y_dev, S_loc, D, lib, dev)
-        return
-
-    peak, peak_src = measured_peak_gbs()
-    steps, warmup = args.steps, max(args.warmup, 3)
+    sp = ShardedDensePricer(M_loc, S, row0, K, TOL, variant=args.variant, exchange=args.exchange,
+                            fused=not args.no_fused)
 
     # ---- device-resident arm ---------------------------------------------------------------------
     for _ in range(warmup):
         sp.enqueue(y_dev)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    if sampler is not None and rank == 0:
         sampler.start()
-    launches0 = sp.launches
     k0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = sp.launches
     e0.record()
     for i in range(steps):
         out = sp.enqueue(y_dev, kernel_events=(k0[i], k1[i]))
     e1.record()
+    launches = sp.launches - launches0                   # kernels of libsxcross inside the timed region only
     barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    kern_ms = float(np.mean([k0[i].elapsed_time(k1[i]) for i in range(steps)]))
+    count_dev = int(out[3].item())
+    assert int(out[6].item()) == 0, "selection status not clean: the timed pass would have to be repeated"
+    n_out = int(out[2].item())
+    ids_dev, rc_dev = out[1][:n_out].cpu().numpy(), out[0][:n_out].cpu().numpy()
+    min_dev = float(lib.sx_key_to_f64(int(out[4].item())))
+    digest = topk_digest(ids_dev, rc_dev, count_dev, min_dev)
+    value = S * D * steps / (ms_total * 1e-3)
+
+    # ---- N-rank result check: gather every rank's LOCAL top-K block with a plain NCCL all-gather, merge on
+    # the host with np.lexsort (independent of sx_exchange_push_ll / the merge kernels) and compare bit for bit
+    merge_check = None
+    if world > 1:
+        local = sp.pricer.block.clone()
+        gathered = torch.empty(world, local.numel(), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gathered.view(-1), local)
+        g = gathered.cpu().numpy()
+        Kp = max(K, 1)
+        g_rc, g_id = g[:, :Kp].reshape(-1).view(np.float64), g[:, Kp:2 * Kp].reshape(-1)
+        real = g_id >= 0
+        o = np.lexsort((g_id[real], g_rc[real]))[:K]
+        ref_ids, ref_rc = g_id[real][o], g_rc[real][o]
+        ref_count = int(g[:, 2 * Kp].sum())
+        ref_min = min(float(lib.sx_key_to_f64(int(v))) for v in g[:, 2 * Kp + 1])
+        ok = (np.array_equal(ref_ids, ids_dev) and ref_rc.tobytes() == rc_dev.tobytes()
+              and ref_count == count_dev and ref_min == min_dev)
+        assert ok, f"rank {rank}: exchanged + merged top-K differs from the host merge of the per-rank blocks"
+        d_all = [None] * world
+        dist.all_gather_object(d_all, digest)
+        assert len(set(d_all)) == 1, f"ranks disagree on the merged result: {d_all}"
+        merge_check = {"ok": True, "against": "np.lexsort over the NCCL-all-gathered per-rank blocks",
+                       "ranks_agree": True, "n_out": n_out}
+
     # where a step's time goes (separate short loop: the extra events are not in the timed region)
     n_st = 5 if world > 1 else 3
     sev = [[torch.cuda.Event(enable_timing=True) for _ in range(n_st)] for _ in range(20)]
     for i in range(20):
         sp.enqueue(y_dev, stage_events=sev[i])
     torch.cuda.synchronize()
-    stage_names = ["begin+pricing", "selection", "exchange", "merge"][:n_st - 1]
+    stage_names = sp.stage_names[:n_st - 1]
     stages = {nm: round(float(np.median([sev[i][q].elapsed_time(sev[i][q + 1]) for i in range(20)])) * 1e3, 1)
               for q, nm in enumerate(stage_names)}
+    stages["step_minus_pricing_kernel"] = round((ms_total / steps - kern_ms) * 1e3, 1)
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = sp.launches - launches0
-    kern_ms = float(np.mean([k0[i].elapsed_time(k1[i]) for i in range(steps)]))
-    per_rank_kern = [kern_ms]
+    per_rank_kern = [round(kern_ms, 4)]
     if world > 1:                                        # the slowest GPU paces a strong-scaled, exchanged step
         t = torch.zeros(world, dtype=torch.float64, device=device)
         t[rank] = kern_ms
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         per_rank_kern = [round(float(v), 4) for v in t.tolist()]
-    count_dev = int(out[3].item())
-    assert int(out[6].item()) == 0, "selection status not clean: the timed pass would have to be repeated"
-    value = S * D * steps / (ms_total * 1e-3)
 
-    # ---- end-to-end arm: duals from pinned host memory, result back to the host every step ---------
-    y_pin = sp.y_pinned                                  # the duals live in pinned host memory (the solver's output buffer)
+    # ---- end-to-end arms --------------------------------------------------------------------------------
+    # e2e: a PAGEABLE dual vector (what the LP solver returns, algorithms.py:96) in, result out, every step.
+    # e2e_pinned: the duals already sit in the pricer's pinned staging buffer (round-1 definition).
+    def timed_price(y_arg):
+        for _ in range(3):
+            r = sp.price(y_arg)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            r = sp.price(y_arg)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), r
+
+    y_pageable = np.array(y_host, copy=True)
+    e2e_ms, res = timed_price(y_pageable)
+    assert res.n_violating == count_dev and topk_digest(res.topk_id, res.topk_rc, res.n_violating, res.min_rc) == digest
+    y_pin = sp.y_pinned
     y_pin[:] = y_host
-    for _ in range(3):
-        res = sp.price(y_pin)
-    barrier()
-    e0.record()
-    for _ in range(steps):
-        res = sp.price(y_pin)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
-    e2e_value = S * D * steps / (e2e_ms * 1e-3)
+    e2e_pin_ms, res = timed_price(y_pin)
     assert res.n_violating == count_dev
+    clocks = sampler.stop() if (sampler is not None and rank == 0) else None
+
+    def e2e_dict(ms, inputs):
+        return {"value": S * D * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sp.h2d_bytes,
+                "d2h_bytes_per_step": sp.d2h_bytes, "ms_per_step": ms / steps, "cuda_graph": sp._graph is not None,
+                "inputs": inputs}
+    e2e = e2e_dict(e2e_ms, "duals y in a pageable NumPy vector every step (copied to pinned staging, this rank's "
+                           "S_loc + D entries uploaded), result block read back to the host; cost matrix resident "
+                           "(uploaded once per problem, see e2e_cold)")
+    e2e_pinned = e2e_dict(e2e_pin_ms, "as e2e, but the duals already sit in the pricer's pinned buffer (y_pinned)")
 
     # ---- cold end-to-end: also upload this rank's slab of M from pinned host memory (once per problem)
     cold = None
-    if rank == 0 or world > 1:
+    if want_cold:
         rows_c = min(S_loc, 4000)                       # bounded pinned sample; scaled to the slab
         h_M = torch.empty(rows_c, D, dtype=torch.float64).pin_memory()
         h_M.copy_(M_loc[:rows_c])
@@ -515,29 +661,8 @@ def main():
                 "h2d_bytes": 8 * S_loc * D, "note": f"upload time scaled from a {rows_c}-row pinned sample"}
         del h_M
 
-    exchange_mode = sp.exchange
-    e2e_h2d, e2e_d2h, e2e_graph = sp.h2d_bytes, sp.d2h_bytes, sp._graph is not None
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    achieved = 8.0 * S_loc * D / (kern_ms * 1e-3) / 1e9
-    traffic = None            # dram read+write bytes per launch from the committed ncu capture, same shape only
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "price_traffic.json")))
-        if (tj["S_loc"], tj["D"]) == (S_loc, D):
-            traffic = tj["traffic_bytes"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "kernel": "price_dense_tma_kernel" if args.variant in (-1, 0) else "price_dense_direct_kernel",
-                "kernel_ms": round(kern_ms, 4), "kernel_ms_per_rank": per_rank_kern, "algorithmic_bytes_per_arc": 8,
-                "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
-
     cpu_baseline = None
-    if not args.no_cpu:
+    if want_cpu and rank == 0:
         rows_h = min(S_loc, 16384)                       # ~5e8-1e9 arcs: a few seconds of single-core NumPy per repetition
         M_h = M_loc[:rows_h].cpu().numpy()
         y_h = np.concatenate([y_host[row0:row0 + rows_h], y_host[S:]])
@@ -547,32 +672,15 @@ def main():
                                   f"oracle NumPy restatement of net_manager.py:474-497, host has {os.cpu_count()} cpus"}
         del M_h
 
-    tree = None
-    if world == 1 and not args.no_tree:
-        del sp, M_loc
-        torch.cuda.empty_cache()
-        tree = [time_tree_build(784, 784, device), time_tree_build(20000, 20000, device, reps=1),
-                time_mcf_path(1_000_000, 10_000_000, device, reps=1)]
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"dense synthetic OT {S}x{D} ({S * D:.3g} arcs, {8 * S * D / 1e9:.1f} GB fp64 cost) "
-                                   f"column-generation pricing pass, row-sharded over {world} GPU(s)",
-                       "S": S, "D": D, "topk": K, "tol": TOL, "violating_arcs": count_dev,
-                       "rows_per_gpu": S_loc, "variant": args.variant, "exchange": exchange_mode,
-                       "l2": f"inputs larger than L2 ({8 * S_loc * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
-                    "d2h_bytes_per_step": e2e_d2h, "ms_per_step": e2e_ms / steps,
-                    "cuda_graph": e2e_graph,
-                    "inputs": "duals y in pinned host memory every step (this rank's S_loc + D entries uploaded), "
-                              "result block read back to the host; cost matrix resident (uploaded once per "
-                              "problem, see e2e_cold)"},
-            "stage_us_rank0": stages, "e2e_cold": cold, "gpu_launches": launches, "clocks": clocks, "tree_build": tree}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leg = {"S": S, "D": D, "S_loc": S_loc, "value": value, "ms_per_step": ms_total / steps, "kernel_ms": kern_ms,
+           "kernel_ms_per_rank": per_rank_kern, "kernel": sp.pricing_kernel_name, "stage_us": stages,
+           "gpu_launches": launches, "violating_arcs": count_dev, "topk_digest": digest, "merge_check": merge_check,
+           "e2e": e2e, "e2e_pinned": e2e_pinned, "e2e_cold": cold, "cpu_baseline": cpu_baseline, "clocks": clocks,
+           "exchange": sp.exchange, "fused": sp.fused}
+    del sp, M_loc, y_dev
+    torch.cuda.empty_cache()
+    barrier()
+    return leg
 
 
 def sweep(args, sp, y_dev, S_loc, D, lib, dev):

@@ -68,6 +68,11 @@ typedef struct sx_price_header {
                                         call sx_topk_select_sorted on the same candidates */
 #define SX_STATUS_K_MISMATCH     4   /* sx_topk_select asked for more arcs than sx_price_pass_begin
                                         announced: the candidates were pruned for the smaller K */
+#define SX_STATUS_NAN_RC         8   /* some reduced cost was NaN.  It is neither counted in n_violating nor
+                                        selected (NumPy: NaN < -tol is False), but the optimality test
+                                        `np.all(rc >= -tol)` (net_manager.py:318,496) is False: callers must
+                                        treat the pass as NOT optimal.  Informational, no repeat needed. */
+#define SX_STATUS_REPEAT_MASK    3   /* bits that ask for the pass / selection to be repeated */
 
 /* Selection state of a pricing pass (opaque device memory, sx_select_state_bytes() bytes, 16 B
  * aligned): candidate counter, pruning bound and the reduced-cost histogram the bound is derived

@@ -22,7 +22,9 @@ inline int cuda_fail(cudaError_t e) {
 
 #define SX_LAUNCH_CHECK() SX_CUDA(cudaPeekAtLastError())
 
-constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+// SM count of the current device (148 on a B200: 2 dies x 74 SMs), queried once per device; grids of the
+// persistent / cooperative kernels are sized from it.  Defined in sx_api.cu.
+int num_sms();
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -385,7 +385,7 @@ constexpr size_t kPfBndFactor = 4;     // boundary list capacity = 4 x T_cap arc
 
 static int pf_grid(long long n, int per_thread) {
     long long g = (n + (long long)kPfThreads * per_thread - 1) / ((long long)kPfThreads * per_thread);
-    if (g > kNumSMs * 4) g = kNumSMs * 4;
+    if (g > num_sms() * 4) g = num_sms() * 4;
     if (g < 1) g = 1;
     return (int)g;
 }
@@ -449,7 +449,7 @@ extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int
     // threshold bin is too crowded for the list, both run over all the weights instead.
     int occ = 1;
     SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pf_split_kernel, kPfThreads, 0));
-    long long fgrid = (long long)kNumSMs * (occ > 0 ? occ : 1);
+    long long fgrid = (long long)num_sms() * (occ > 0 ? occ : 1);
     const long long fneed = (n / 2 + (long long)kPfThreads * kPfBatch - 1) / ((long long)kPfThreads * kPfBatch);
     if (fgrid > fneed) fgrid = fneed > 0 ? fneed : 1;
     const long long bnd_cap = (long long)(kPfBndFactor * (size_t)T_cap);
@@ -459,7 +459,7 @@ extern "C" int sx_kruskal_prefix(const double *weight, int64_t n, int64_t T, int
     SX_CUDA(cudaMemcpyAsync(&n_bnd, &ctl->n_bnd, sizeof(n_bnd), cudaMemcpyDeviceToHost, st));
     SX_CUDA(cudaStreamSynchronize(st));
     SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pf_filter_kernel, kPfThreads, 0));
-    const long long filter_ctas = (long long)kNumSMs * (occ > 0 ? occ : 1);
+    const long long filter_ctas = (long long)num_sms() * (occ > 0 ? occ : 1);
     auto filter_grid = [&](long long cnt) {
         long long need = (cnt / 2 + (long long)kPfThreads * kPfBatch - 1) / ((long long)kPfThreads * kPfBatch);
         if (need < 1) need = 1;

@@ -77,14 +77,16 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
-// acc || (a < b) as ONE predicated compare (setp.lt.or.f64).  Written in PTX because the compiler
-// otherwise rewrites an OR of "x_i < lim" into "min(x_i) < lim", and an fp64 min is ~8 instructions.
+// acc || !(a >= b) as ONE predicated compare (setp.ltu.or.f64: "less than or unordered").  Written in PTX
+// because the compiler otherwise rewrites an OR of "x_i < lim" into "min(x_i) < lim", and an fp64 min is
+// ~8 instructions.  Unordered on purpose: a NaN reduced cost must reach the epilogue, where it raises
+// SX_STATUS_NAN_RC -- the reference's `np.all(rc >= -tol)` (net_manager.py:496) is False for it.
 __device__ __forceinline__ bool lt_or(double a, double b, bool acc) {
     int r;
     asm("{\n"
         ".reg .pred p, q;\n"
         "setp.ne.s32 q, %3, 0;\n"
-        "setp.lt.or.f64 p, %1, %2, q;\n"
+        "setp.ltu.or.f64 p, %1, %2, q;\n"
         "selp.s32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(r)
@@ -214,14 +216,17 @@ __device__ __forceinline__ void tile_epilogue(const DenseParams &p, WarpTally &t
     bool viol = false;
     if (hit) {
         double mn = tmin;
+        bool nan = false;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             mn = rc0[r] < mn ? rc0[r] : mn;
             mn = rc1[r] < mn ? rc1[r] : mn;
             viol = viol || (rc0[r] < p.thr) || (rc1[r] < p.thr);
+            nan = nan || (rc0[r] != rc0[r]) || (rc1[r] != rc1[r]);
         }
         tmin = mn;
         lim = tmin > p.thr ? tmin : p.thr;
+        if (nan) atomicOr(&p.sink.hdr->status, kStatusNanRc);
     }
     if (__any_sync(0xffffffffu, viol))
         emit_violators<2 * RPT>(
@@ -497,12 +502,15 @@ price_arcs_kernel(const double *__restrict__ c, const int32_t *__restrict__ tail
         if (!__any_sync(0xffffffffu, hit)) continue;
         bool viol = false;
         if (hit) {
+            bool nan = false;
 #pragma unroll
             for (int q = 0; q < kArcPerThread; ++q) {
                 tmin = rc[q] < tmin ? rc[q] : tmin;
                 viol = viol || (rc[q] < thr);
+                nan = nan || (rc[q] != rc[q]);
             }
             lim = tmin > thr ? tmin : thr;
+            if (nan) atomicOr(&sink.hdr->status, kStatusNanRc);
         }
         if (!__any_sync(0xffffffffu, viol)) continue;
         const long long k0 = id0 + ch * chunk + threadIdx.x;
@@ -571,7 +579,7 @@ static int launch_tma(const CUtensorMap &map, const DenseParams &p, cudaStream_t
     auto kern = price_dense_tma_kernel<ROWS, STAGES, CWARPS, MINB, WRITE_RC>;
     SX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = p.n_row_tiles * p.n_col_blocks;
-    long long grid = (long long)kNumSMs * MINB;
+    long long grid = (long long)num_sms() * MINB;
     if (grid > total) grid = total;
     if (grid < 1) grid = 1;
     kern<<<(int)grid, (CWARPS + 1) * 32, smem, st>>>(map, p);
@@ -622,7 +630,7 @@ extern "C" size_t sx_select_state_bytes(void) { return sizeof(SelState); }
 extern "C" int sx_price_pass_begin(sx_price_header *header, sx_select_state *sel, int64_t K, void *stream) {
     if (!header || K < 0 || K > 0xffffffffll) return SX_ERR_INVALID;
     if (((uintptr_t)sel & 15) != 0) return SX_ERR_UNALIGNED;
-    pass_begin_kernel<<<sel ? kNumSMs : 1, 256, 0, (cudaStream_t)stream>>>(header, (SelState *)sel, (unsigned)K);
+    pass_begin_kernel<<<sel ? num_sms() : 1, 256, 0, (cudaStream_t)stream>>>(header, (SelState *)sel, (unsigned)K);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }
@@ -669,7 +677,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
     } else {
         p.n_row_tiles = (S_loc + kDirectRows - 1) / kDirectRows;
         const long long total = p.n_row_tiles * p.n_col_blocks;
-        long long grid = (long long)kNumSMs * g_ctas_per_sm_direct;
+        long long grid = (long long)num_sms() * g_ctas_per_sm_direct;
         if (grid > total) grid = total;
         if (variant == 1) {
             if (rc_out) price_dense_direct_kernel<true, true><<<(int)grid, kDirectThreads, 0, st>>>(M, ld, p);
@@ -694,7 +702,7 @@ extern "C" int sx_price_arcs(const double *c, const int32_t *tail, const int32_t
     CandSink sink{header, (SelState *)sel, cand_rc, (int64_t *)cand_id, cand_cap};
     const long long chunk = (long long)kArcThreads * kArcPerThread;
     long long n_chunks = (E + chunk - 1) / chunk;
-    long long grid = (long long)kNumSMs * 8;
+    long long grid = (long long)num_sms() * 8;
     if (grid > n_chunks) grid = n_chunks;
     price_arcs_kernel<<<(int)grid, kArcThreads, 0, st>>>(c, tail, head, vbasis, y, E, id0, -tol, sink, rc_out);
     SX_LAUNCH_CHECK();

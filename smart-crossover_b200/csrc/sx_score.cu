@@ -176,7 +176,7 @@ __global__ void mcf_arc_kernel(const int32_t *__restrict__ tail, const int32_t *
 
 static int grid_for(long long n, int threads) {
     long long g = (n + threads - 1) / threads;
-    const long long cap = (long long)kNumSMs * 16;
+    const long long cap = (long long)num_sms() * 16;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -204,7 +204,7 @@ extern "C" int sx_score_ot(const double *x, const double *s, const double *d, in
     if (vec) {
         const long long col_blocks = (D / 2 + kScThreads * kScCols - 1) / (kScThreads * kScCols);
         const long long tiles = S * col_blocks;
-        const long long grid = tiles < (long long)kNumSMs * 8 ? tiles : (long long)kNumSMs * 8;
+        const long long grid = tiles < (long long)num_sms() * 8 ? tiles : (long long)num_sms() * 8;
         auto launch = [&](auto kern) { kern<<<(int)grid, kScThreads, 0, st>>>(x, s, d, S, D, col_blocks, score_out, hist12_out); };
         if (g_score_min_ctas >= 4) { if (hist12_out) launch(score_ot_vec_kernel<true, 4>); else launch(score_ot_vec_kernel<false, 4>); }
         else { if (hist12_out) launch(score_ot_vec_kernel<true, 3>); else launch(score_ot_vec_kernel<false, 3>); }
@@ -213,7 +213,7 @@ extern "C" int sx_score_ot(const double *x, const double *s, const double *d, in
     }
     const long long col_blocks = (D + kScThreads * kScCols - 1) / (kScThreads * kScCols);
     long long tiles = S * col_blocks;
-    long long grid = tiles < (long long)kNumSMs * 16 ? tiles : (long long)kNumSMs * 16;
+    long long grid = tiles < (long long)num_sms() * 16 ? tiles : (long long)num_sms() * 16;
     score_ot_kernel<<<(int)grid, kScThreads, 0, st>>>(x, s, d, S, D, col_blocks, score_out);
     SX_LAUNCH_CHECK();
     if (hist12_out) return sx_hist12_f64(score_out, S * D, hist12_out, stream);      // unaligned shapes: separate pass

@@ -47,6 +47,7 @@ static_assert(sizeof(SelState) % 16 == 0, "SelState is cleared with 16-byte stor
 constexpr unsigned long long kStatusCandOverflow = 1ull;   // candidate buffer too small: grow and price again
 constexpr unsigned long long kStatusNeedSlowPath = 2ull;   // too many survivors (ties): use sx_topk_select_sorted
 constexpr unsigned long long kStatusKMismatch    = 4ull;   // selection asked for more than the pass pruned for
+constexpr unsigned long long kStatusNanRc        = 8ull;   // a reduced cost was NaN: not optimal (np.all(rc >= -tol) is False)
 
 // Monotone (non-strict) 19-bit image of a reduced cost: a < b  =>  bin(a) <= bin(b).
 // Negative values (every violator when tol >= 0) use the full resolution; anything >= +0 clamps

@@ -148,14 +148,14 @@ extern "C" int sx_sinkhorn_ot(const double *M, int64_t ld, int64_t S, int64_t D,
     const long long n_chunks = (S + kSkRowsPerChunk - 1) / kSkRowsPerChunk;
     double *pm = cv.take<double>((size_t)n_chunks * D), *ps = cv.take<double>((size_t)n_chunks * D);
     double *err2 = cv.take<double>(1);
-    sk_log_kernel<<<kNumSMs, 256, 0, st>>>(a, S, log_a);
-    sk_log_kernel<<<kNumSMs, 256, 0, st>>>(b, D, log_b);
+    sk_log_kernel<<<num_sms(), 256, 0, st>>>(a, S, log_a);
+    sk_log_kernel<<<num_sms(), 256, 0, st>>>(b, D, log_b);
     SX_LAUNCH_CHECK();
     SX_CUDA(cudaMemsetAsync(g, 0, sizeof(double) * (size_t)D, st));
-    sk_fill_kernel<<<kNumSMs, 256, 0, st>>>(f, S, -reg * log((double)S));     // u = 1 / S
+    sk_fill_kernel<<<num_sms(), 256, 0, st>>>(f, S, -reg * log((double)S));     // u = 1 / S
     SX_LAUNCH_CHECK();
     long long row_grid = (S * 32 + 255) / 256;
-    if (row_grid > kNumSMs * 16) row_grid = kNumSMs * 16;
+    if (row_grid > num_sms() * 16) row_grid = num_sms() * 16;
     const dim3 col_grid((unsigned)((D + 255) / 256), (unsigned)n_chunks);
     int64_t it = 0;
     double err = INFINITY;
@@ -179,7 +179,7 @@ extern "C" int sx_sinkhorn_ot(const double *M, int64_t ld, int64_t S, int64_t D,
         SX_LAUNCH_CHECK();
     }
     if (x_out) {
-        sk_plan_kernel<<<kNumSMs * 8, 256, 0, st>>>(M, ld, S, D, f, g, reg, x_out);
+        sk_plan_kernel<<<num_sms() * 8, 256, 0, st>>>(M, ld, S, D, f, g, reg, x_out);
         SX_LAUNCH_CHECK();
     }
     if (iters_h) *iters_h = it;

@@ -11,7 +11,7 @@
 namespace sx {
 
 constexpr int kRsItems   = 8;      // keys per thread in the downsweep; tile = threads * 8
-constexpr int kRsMaxGrid = kNumSMs * 6;
+constexpr int kRsMaxGrid = 148 * 6;   // cap on the upsweep grid (sizes the histogram workspace), not an SM count
 
 enum KeySource { kFromBuffer = 0, kFromF64 = 1, kFromU64 = 2 };
 
@@ -634,7 +634,7 @@ extern "C" int sx_queue_from_order(const uint32_t *order_asc, int64_t n, int64_t
     if (n < 0 || (n > 0 && (!order_asc || !queue_out))) return SX_ERR_INVALID;
     if (n == 0) return SX_OK;
     long long grid = (n + 255) / 256;
-    if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
     queue_from_order_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(order_asc, n, (long long *)queue_out);
     SX_LAUNCH_CHECK();
     return SX_OK;

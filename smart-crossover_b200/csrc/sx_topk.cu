@@ -811,7 +811,7 @@ __global__ void tk_emit_kernel(const double *__restrict__ rc, const long long *_
 
 static int tk_grid(long long n, int threads) {
     long long g = (n + threads - 1) / threads;
-    if (g > kNumSMs * 8) g = kNumSMs * 8;
+    if (g > num_sms() * 8) g = num_sms() * 8;
     if (g < 1) g = 1;
     return (int)g;
 }
@@ -870,7 +870,7 @@ extern "C" int sx_topk_select_sorted(const double *cand_rc, const int64_t *cand_
         topk_prep_kernel<<<1, 1024, 0, st>>>(lists_rc, lists_id, K, L, (int)K, n_cand_dev, cand_cap, plen, poff, out_rc,
                                              (long long *)out_id, (long long *)out_n, nullptr, nullptr);
         SX_LAUNCH_CHECK();
-        topk_rank_kernel<<<kNumSMs * 4, 256, 0, st>>>(lists_rc, lists_id, K, L, (int)K, plen, poff, out_rc,
+        topk_rank_kernel<<<num_sms() * 4, 256, 0, st>>>(lists_rc, lists_id, K, L, (int)K, plen, poff, out_rc,
                                                       (long long *)out_id);
         SX_LAUNCH_CHECK();
         return SX_OK;
@@ -918,7 +918,7 @@ extern "C" int sx_topk_select(const double *cand_rc, const int64_t *cand_id, int
     long long *oid = (long long *)out_id, *on = (long long *)out_n;
     void *args[] = {(void *)&cand_rc, (void *)&cid, (void *)&cand_cap, (void *)&sst, (void *)&header, (void *)&Ki,
                     (void *)&sure, (void *)&listA, (void *)&listB, (void *)&out_rc, (void *)&oid, (void *)&on};
-    SX_CUDA(cudaLaunchCooperativeKernel((void *)topk_select_kernel, dim3(kNumSMs), dim3(kApThreads), args, 0, st));
+    SX_CUDA(cudaLaunchCooperativeKernel((void *)topk_select_kernel, dim3(num_sms()), dim3(kApThreads), args, 0, st));
     return SX_OK;
 }
 
@@ -942,7 +942,7 @@ extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, 
         const int use_smem = stage_bytes <= 200 * 1024;
         const int threads = use_smem ? 1024 : 256;
         long long mg = (G * K + threads - 1) / threads;
-        if (mg > kNumSMs * 4) mg = kNumSMs * 4;
+        if (mg > num_sms() * 4) mg = num_sms() * 4;
         if (use_smem) SX_CUDA(cudaFuncSetAttribute(merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         merge_rank_kernel<<<(int)mg, threads, use_smem ? stage_bytes : 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G,
                                                           (int)K, (const long long *)headers, out_rc,
@@ -958,7 +958,7 @@ extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, 
                                          0, plen, poff, out_rc, (long long *)out_id, (long long *)out_n,
                                          (const long long *)headers, (long long *)out_summary);
     SX_LAUNCH_CHECK();
-    topk_rank_kernel<<<kNumSMs * 2, 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G, (int)K,
+    topk_rank_kernel<<<num_sms() * 2, 256, 0, st>>>(blocks_rc, (const long long *)blocks_id, block_stride, (int)G, (int)K,
                                                   plen, poff, out_rc, (long long *)out_id);
     SX_LAUNCH_CHECK();
     return SX_OK;

@@ -193,7 +193,7 @@ __global__ void flow_finalize_kernel(long long T, const int *__restrict__ rank, 
 
 static int tr_grid(long long n) {
     long long g = (n + kTrThreads - 1) / kTrThreads;
-    if (g > kNumSMs * 8) g = kNumSMs * 8;
+    if (g > num_sms() * 8) g = num_sms() * 8;
     if (g < 1) g = 1;
     return (int)g;
 }

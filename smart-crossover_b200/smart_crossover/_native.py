@@ -20,6 +20,8 @@ SX_TOPK_MAX_K = 1024
 SX_STATUS_CAND_OVERFLOW = 1
 SX_STATUS_NEED_SORTED = 2
 SX_STATUS_K_MISMATCH = 4
+SX_STATUS_NAN_RC = 8
+SX_STATUS_REPEAT_MASK = 3
 SX_ABI_VERSION = 2
 
 

@@ -174,10 +174,16 @@ class PriceResult:
     topk_id: np.ndarray     # int64, ascending (rc, id)
     topk_rc: np.ndarray     # float64
     rc: torch.Tensor | None = None   # full reduced costs if requested (device)
+    status: int = 0                  # SX_STATUS_* bits of the pass (SX_STATUS_NAN_RC: some reduced cost was NaN)
 
     @property
-    def optimal(self) -> bool:       # net_manager.py:318,496
-        return self.n_violating == 0
+    def has_nan(self) -> bool:
+        return bool(self.status & _native.SX_STATUS_NAN_RC)
+
+    @property
+    def optimal(self) -> bool:
+        """`np.all(rc >= -tol)` (net_manager.py:318,496): no violator and no NaN reduced cost."""
+        return self.n_violating == 0 and not self.has_nan
 
 
 class Pricer:
@@ -266,7 +272,7 @@ class Pricer:
         nviol = int(h[2 * Kp]) & 0xFFFFFFFFFFFFFFFF
         min_rc = float(lib.sx_key_to_f64(int(h[2 * Kp + 1])))
         k = int(h[2 * Kp + 4]) if self.K > 0 else 0
-        return PriceResult(nviol, min_rc, h[Kp:Kp + k].copy(), h[:k].view(np.float64).copy())
+        return PriceResult(nviol, min_rc, h[Kp:Kp + k].copy(), h[:k].view(np.float64).copy(), status=self.status)
 
     def overflowed(self, res: PriceResult | None = None) -> bool:
         return self.K > 0 and bool(self.status & _native.SX_STATUS_CAND_OVERFLOW)

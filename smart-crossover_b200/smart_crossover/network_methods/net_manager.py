@@ -58,6 +58,11 @@ def _dev():
     return device
 
 
+def _native_status_nan() -> int:
+    from smart_crossover import _native
+    return _native.SX_STATUS_NAN_RC
+
+
 def _cuda(a, dtype=None):
     import torch
     t = torch.from_numpy(np.ascontiguousarray(a))
@@ -261,8 +266,9 @@ class OTManager:
         all_ids = np.concatenate([ids, b_ids[viol]])
         all_rc = np.concatenate([res.topk_rc, b_rc[viol]])
         o = np.lexsort((all_ids, all_rc))[:K] if K > 0 else np.zeros(0, dtype=np.int64)
-        out = dev.PriceResult(res.n_violating + int(viol.sum()), float(min(res.min_rc, b_rc.min())),
-                              all_ids[o].astype(np.int64), all_rc[o])
+        status = res.status | (_native_status_nan() if np.isnan(b_rc).any() else 0)
+        out = dev.PriceResult(res.n_violating + int(viol.sum()), float(min(res.min_rc, np.nanmin(b_rc))),
+                              all_ids[o].astype(np.int64), all_rc[o], status=status)
         if want_rc:
             full = np.empty((S + 1, D + 1))
             full[:S, :D] = res.rc.cpu().numpy().reshape(S, D)
@@ -279,7 +285,7 @@ class OTManager:
         """All reduced costs >= -1e-6 and no flow left on artificial arcs (reference :485-497)."""
         art_ok = bool(np.all(x[self.artificial_vars][:-1] < TOLERANCE_FOR_ARTIFICIAL_VARS)) \
             if self.artificial_vars.size > 0 else True
-        return bool(art_ok and self.price(y, K=0).n_violating == 0)
+        return bool(art_ok and self.price(y, K=0).optimal)
 
 
 # =================================================================================================
@@ -430,4 +436,4 @@ class MCFManagerStd:
         """Reference :306-319."""
         art_ok = bool(np.all(x[self.artificial_vars] < TOLERANCE_FOR_ARTIFICIAL_VARS)) \
             if self.artificial_vars.size > 0 else True
-        return bool(art_ok and self.price(y, K=0).n_violating == 0)
+        return bool(art_ok and self.price(y, K=0).optimal)

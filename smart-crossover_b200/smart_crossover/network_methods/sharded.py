@@ -44,8 +44,9 @@ class ShardedDensePricer:
     row-major, device resident for the life of the problem, like the reference keeps `ot.M`)."""
 
     def __init__(self, M_loc: torch.Tensor, S: int, row0: int, K: int, tol: float = dev.TOL_RC,
-                 group=None, variant: int = -1, exchange: str = "ll", use_graph: bool = True):
+                 group=None, variant: int = -1, exchange: str = "ll", use_graph: bool = True, fused: bool = False):
         self.M = M_loc
+        self.fused = False
         self.S, self.D = int(S), int(M_loc.shape[1])
         self.S_loc, self.row0 = int(M_loc.shape[0]), int(row0)
         self.K, self.tol, self.variant = int(K), float(tol), variant
@@ -104,6 +105,15 @@ class ShardedDensePricer:
             off = lib.sx_exchange_epoch_offset(blk, self.world) // 8
             self._epoch_ctr = self._symm[off:off + 1]
         dist.barrier(group=self.group)
+
+    @property
+    def stage_names(self):
+        """Names of the intervals between the `stage_events` of `enqueue`."""
+        return ["begin+pricing", "selection", "exchange", "merge"]
+
+    @property
+    def pricing_kernel_name(self):
+        return "price_dense_tma_kernel" if self.variant in (-1, 0) else "price_dense_direct_kernel"
 
     @property
     def launches(self):
@@ -255,7 +265,8 @@ class ShardedDensePricer:
             res, status, cmax = self._read_result()
             # Every rank reads the same folded status, so all ranks repeat the pass together: with a larger
             # candidate buffer after an overflow, with the sorted selection after SX_STATUS_NEED_SORTED.
-            if self.K == 0 or status == 0:
+            res.status = status
+            if self.K == 0 or (status & _native.SX_STATUS_REPEAT_MASK) == 0:
                 return res
             if status & _native.SX_STATUS_CAND_OVERFLOW:
                 self.pricer.grow(cmax)

@@ -388,6 +388,45 @@ def test_price_dense_random_shapes(dev, S, D, K, noise, variant):
         assert res.optimal
 
 
+@pytest.mark.parametrize("variant", [-1, 1, 2])
+@pytest.mark.parametrize("where", ["cost", "source dual", "sink dual"])
+def test_price_nan_reduced_cost_is_not_optimal(dev, variant, where):
+    """A NaN reduced cost: `np.all(rc >= -tol)` (net_manager.py:496) is False, `(rc < -tol).sum()` does not
+    count it and NumPy's argsort puts it last.  The device pass must report the same three things."""
+    S, D = 130, 514
+    s, d, M = cases.ot_points(S, D, 77)
+    y = cases.planted_duals(M, 77, 0.0)
+    y[S:] -= 1e-3                                    # strictly dual feasible: no violator
+    M = M.copy()
+    if where == "cost":
+        M[S - 1, D - 3] = np.nan
+    elif where == "source dual":
+        y[5] = np.nan
+    else:
+        y[S + 511] = np.nan
+    rc_ref = orc.reduced_costs_ot(M, y)
+    assert np.isnan(rc_ref).any() and not np.all(rc_ref >= -1e-6) and (rc_ref < -1e-6).sum() == 0
+    res = dev.price_dense_ot(cu(M), cu(y), K=8, want_rc=True, variant=variant)
+    assert res.rc.cpu().numpy().tobytes() == rc_ref.tobytes()
+    assert res.n_violating == 0 and res.topk_id.size == 0
+    assert res.has_nan and not res.optimal
+    # with violators present the NaN still is not one of them
+    y2 = cases.planted_duals(M, 78, 0.2)
+    if where != "cost":
+        y2[5 if where == "source dual" else S + 511] = np.nan
+    rc2 = orc.reduced_costs_ot(M, y2)
+    cnt, mn, ids, vals = orc.price_summary(rc2, K=64)
+    res = dev.price_dense_ot(cu(M), cu(y2), K=64, variant=variant)
+    assert res.n_violating == cnt and res.min_rc == np.nanmin(rc2) and res.has_nan and not res.optimal
+    assert np.array_equal(res.topk_id, ids) and res.topk_rc.tobytes() == vals.tobytes()
+    # arc-list pricing raises the same flag: rc = c - (y[plus] - y[minus]) with plus = sink, minus = source
+    if variant == -1:
+        minus = np.repeat(np.arange(S), D).astype(np.int32)
+        plus = (S + np.tile(np.arange(D), S)).astype(np.int32)
+        ra = dev.price_arcs(cu(M.ravel()), cu(plus), cu(minus), cu(y2), K=64)
+        assert ra.n_violating == cnt and ra.has_nan and not ra.optimal and np.array_equal(ra.topk_id, ids)
+
+
 def test_price_tied_reduced_costs_and_overflow(dev):
     """Integer costs and duals: massive rc ties (broken by arc id); candidate buffer smaller
     than the violator count forces the exact re-pricing path."""
