@@ -605,6 +605,8 @@ def pricing_leg(args, S, D, ctx, steps, warmup, sampler, want_cpu, want_cold):
     stages = {nm: round(float(np.median([sev[i][q].elapsed_time(sev[i][q + 1]) for i in range(20)])) * 1e3, 1)
               for q, nm in enumerate(stage_names)}
     stages["step_minus_pricing_kernel"] = round((ms_total / steps - kern_ms) * 1e3, 1)
+    if sp.fused:
+        stages["fused_kernel_phases_cta0"] = sp.pricer.fused_phase_us()
     barrier()
     per_rank_kern = [round(kern_ms, 4)]
     if world > 1:                                        # the slowest GPU paces a strong-scaled, exchanged step

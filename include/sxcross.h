@@ -49,7 +49,7 @@ extern "C" {
 #define SX_ERR_PEER_TIMEOUT    -8   /* sx_exchange_blocks: a peer never raised its flag */
 #define SX_ERR_PUSH_ASSERT     -9   /* sx_push_tree_h: the reference's assertions would fire (tree_BI.py:93-94) */
 
-#define SX_ABI_VERSION 2
+#define SX_ABI_VERSION 3
 
 /* Endpoint convention of sx_tree_potentials (which end of an arc carries +1 in A). */
 #define SX_PLUS_IS_HEAD 0   /* OT:  A[S+j,k] = +1, A[i,k] = -1      (formats.py:156-158)     */
@@ -72,7 +72,10 @@ typedef struct sx_price_header {
                                         selected (NumPy: NaN < -tol is False), but the optimality test
                                         `np.all(rc >= -tol)` (net_manager.py:318,496) is False: callers must
                                         treat the pass as NOT optimal.  Informational, no repeat needed. */
-#define SX_STATUS_REPEAT_MASK    3   /* bits that ask for the pass / selection to be repeated */
+#define SX_STATUS_NEED_UNFUSED  16   /* sx_price_dense_ot_fused could not finish its selection (more than 4096
+                                        candidates tie around the K-th value): run the pass again with
+                                        sx_price_pass_begin / sx_price_dense_ot / sx_topk_select */
+#define SX_STATUS_REPEAT_MASK   19   /* bits that ask for the pass / selection to be repeated */
 
 /* Selection state of a pricing pass (opaque device memory, sx_select_state_bytes() bytes, 16 B
  * aligned): candidate counter, pruning bound and the reduced-cost histogram the bound is derived
@@ -252,6 +255,44 @@ SX_API int    sx_price_set_tuning(int tma_shape, int direct_ctas_per_sm);
  * evict_first 1 (default) / 0 = L2 evict-first or normal policy on the loads.  Negative = unchanged. */
 SX_API int    sx_price_set_tma_options(int l2_promotion, int evict_first);
 
+/* ---- K4 fused: one launch per pricing pass -------------------------------------------------
+ * sx_price_dense_ot_fused = sx_price_pass_begin + sx_price_dense_ot (variant 0) + sx_topk_select
+ * (+ sx_exchange_push_ll when peer_bufs_dev != NULL) as ONE cooperative kernel: the state clear of the
+ * next pass is folded into the start of this one (the pricer owns two selection states, used by
+ * alternate passes), the selection runs behind two grid-wide barriers at the end of the pricing
+ * pipeline, and the ranking threads store every selected arc straight into the peers' exchange
+ * buffers.  Same results as the separate calls (net_manager.py:474-497 + top-k).
+ *   state: sx_fused_state_bytes() bytes of device memory, 16 B aligned, initialised ONCE per pricer by
+ *     sx_fused_state_init (and again after any error); K is fixed per state, 1 <= K <= SX_TOPK_MAX_K
+ *     (pass cand_cap = 0 to price for count / min only).
+ *   block (device, block_len >= 2 K + 6 int64): [K rc bits | K ids | n_violating, min_rc_key, n_priced,
+ *     status | n_out | 0], entries past n_out are (+inf, -1).
+ *   peer_bufs_dev / rank / G: as sx_exchange_push_ll (buffers of sx_exchange_ll_buffer_bytes(block_len,
+ *     G) bytes).  NULL: no exchange.
+ *   merged_out (device, 2 K + 5 int64, may be NULL): when given (and sx_fused_merge_fits(K, G)), the last
+ *     CTAs of the same kernel also MERGE the G blocks as they land in the local buffer -- the whole
+ *     multi-GPU pass is one launch per GPU: [K rc bits | K ids | n_out | total n_violating, min key,
+ *     largest single n_violating, OR of the status words]; status_dev receives SX_ERR_PEER_TIMEOUT if
+ *     a peer never shows up.  NULL: follow with sx_topk_merge_ll.
+ *   ws: sx_fused_workspace_bytes() bytes.
+ * status bits SX_STATUS_CAND_OVERFLOW / SX_STATUS_NEED_UNFUSED ask for a repeat with the separate calls
+ * (the block is still well formed and pushed, so no peer waits).  Needs 16 B aligned M and even ld
+ * (SX_ERR_UNALIGNED otherwise: use the separate calls).
+ */
+typedef struct sx_fused_state sx_fused_state;
+SX_API size_t sx_fused_state_bytes(void);
+SX_API size_t sx_fused_workspace_bytes(void);
+/* diagnostics: byte offset inside the state of 8 x uint64 %globaltimer stamps (ns) that CTA 0 of the last
+ * pass took at: start, end of its pricing, after barrier 1, after the filter, after barrier 2, after the rank */
+SX_API size_t sx_fused_state_timestamps_offset(void);
+SX_API int    sx_fused_state_init(sx_fused_state *state, int64_t K, void *stream);
+SX_API int    sx_fused_merge_fits(int64_t K, int G);   /* 1 when the in-kernel merge can stage G blocks of K */
+SX_API int    sx_price_dense_ot_fused(const double *M, int64_t ld, int64_t row0, int64_t S_loc, int64_t D,
+                               const double *y_src, const double *y_dst, double tol, sx_fused_state *state,
+                               double *cand_rc, int64_t *cand_id, int64_t cand_cap, int64_t K, int64_t *block,
+                               int64_t block_len, void *const *peer_bufs_dev, int rank, int G,
+                               int64_t *merged_out, int32_t *status_dev, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- top-k most violating arcs (north_star extension) -------
  * Among the candidates (rc, id) left by a pricing pass select the K smallest by (rc ascending,
  * id ascending).  sel / header are the pass's selection state and header (the candidate count
@@ -309,15 +350,17 @@ SX_API int    sx_exchange_blocks(const int64_t *block, int64_t block_len, void *
  * every 8-byte word of the block travels as one 16-byte slot {lo32, flag, hi32, flag}, flag = epoch --
  * and sx_topk_merge_ll polls the slots of its local buffer while it stages the G blocks in shared
  * memory, then merges them like sx_topk_merge.  No fence, no flag round trip, no separate wait.
- *   Buffer: sx_exchange_ll_buffer_bytes() bytes, zeroed, peer-mapped; the epoch counter sits right
- *   after the 2 * G * block_len slots.  block = [K rc | K ids | 4 header words | ...], block_len >= 2 K + 4.
+ *   Buffer: sx_exchange_ll_buffer_bytes() bytes, zeroed, peer-mapped; the epoch counters (one advanced
+ *   by the pushing side, one by the merge, each once per pass) sit right after the 2 * G * block_len
+ *   slots.  The merge depends on no other kernel of its GPU and is launched with programmatic stream
+ *   serialisation: behind sx_price_dense_ot_fused it becomes resident while that kernel drains.  block = [K rc | K ids | 4 header words | ...], block_len >= 2 K + 4.
  *   G * K * 16 bytes must fit in shared memory (200 KB), else SX_ERR_TOO_LARGE.
  *   out_summary (4 words, may be NULL) as in sx_topk_merge; status_dev as in sx_exchange_blocks.
  */
 SX_API size_t sx_exchange_ll_buffer_bytes(int64_t block_len, int G);
 SX_API int    sx_exchange_push_ll(const int64_t *block, int64_t block_len, void *const *peer_bufs_dev,
                            int rank, int G, void *stream);
-SX_API int    sx_topk_merge_ll(const void *ll_buf_local, int64_t block_len, int64_t G, int64_t K,
+SX_API int    sx_topk_merge_ll(void *ll_buf_local, int64_t block_len, int64_t G, int64_t K,
                         double *out_rc, int64_t *out_id, int64_t *out_n, int64_t *out_summary,
                         int32_t *status_dev, void *stream);
 

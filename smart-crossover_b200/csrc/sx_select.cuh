@@ -11,6 +11,8 @@
 // therefore stays O(K log(n/K)) long however many arcs violate, and the final selection
 // (sx_topk.cu) is a filter by the final b* plus an all-pairs rank of the few survivors.
 #pragma once
+#include <stddef.h>
+
 #include "sx_common.cuh"
 
 namespace sx {
@@ -28,8 +30,10 @@ struct SelState {
     unsigned long long n_cand;       // candidates appended so far (can exceed the buffer capacity)
     unsigned int       bstar;        // only violators with bin <= bstar are appended
     unsigned int       K;            // selection size this pass prunes for
+    // header of the pass when the state is one half of a fused pricer (sx_fused.cu); unused otherwise
+    sx_price_header    hdr;
     // ---- scratch of the selection kernel (sx_topk.cu), zero at the start of a pass ----
-    unsigned int       n_sure;       // elements known to be among the K best
+    unsigned int       n_sure;       // elements known to be among the K best (fused kernel: survivors of the filter)
     unsigned int       pad0[3];
     unsigned int       n_list[kMaxLevels + 4];                // boundary-list length per level
     unsigned long long inv_kmin[kMaxLevels + 2];              // ~min key of the level's boundary list
@@ -43,11 +47,36 @@ struct SelState {
 };
 static_assert(sizeof(SelState) % 16 == 0, "SelState is cleared with 16-byte stores");
 
+// The i-th 16-byte word of a selection state at the start of a pass: everything zero except
+// bstar = last bin (no pruning yet), K, and the embedded header's running minimum (= +max).
+__host__ __device__ inline uint4 sel_clear_word(size_t i, unsigned K) {
+    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    if (i == 0) { z.z = kFineBins - 1u; z.w = K; }                  // n_cand = 0 | bstar | K
+    if (i == 1) { z.z = 0xffffffffu; z.w = 0x7fffffffu; }          // hdr.n_violating = 0 | hdr.min_rc_key = INT64_MAX
+    return z;
+}
+static_assert(offsetof(SelState, hdr) == 16, "sel_clear_word assumes the header follows the first 16 bytes");
+
+// (key, id) image of a candidate: key = f64_to_sort_key(rc); (~0, INT64_MAX) is padding.
+struct KeyId {
+    unsigned long long key;
+    long long          id;
+};
+// L2 load (lists are rewritten by other SMs between grid-wide barriers of one kernel)
+__device__ __forceinline__ KeyId ld_keyid(const KeyId *p) {
+    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
+    return KeyId{v.x, (long long)v.y};
+}
+__device__ __forceinline__ bool keyid_less(const KeyId &a, const KeyId &b) {
+    return a.key < b.key || (a.key == b.key && a.id < b.id);
+}
+
 // bits of sx_price_header.status
 constexpr unsigned long long kStatusCandOverflow = 1ull;   // candidate buffer too small: grow and price again
 constexpr unsigned long long kStatusNeedSlowPath = 2ull;   // too many survivors (ties): use sx_topk_select_sorted
 constexpr unsigned long long kStatusKMismatch    = 4ull;   // selection asked for more than the pass pruned for
-constexpr unsigned long long kStatusNanRc        = 8ull;   // a reduced cost was NaN: not optimal (np.all(rc >= -tol) is False)
+constexpr unsigned long long kStatusNeedUnfused  = 16ull;  // fused pass could not finish its selection: run the separate kernels
+constexpr unsigned long long kStatusNanRc        = 8ull;    // a reduced cost was NaN: not optimal (np.all(rc >= -tol) is False)
 
 // Monotone (non-strict) 19-bit image of a reduced cost: a < b  =>  bin(a) <= bin(b).
 // Negative values (every violator when tol >= 0) use the full resolution; anything >= +0 clamps

@@ -29,6 +29,7 @@
 
 #include "sx_common.cuh"
 #include "sx_select.cuh"
+#include "sx_ll.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -325,19 +326,6 @@ topk_rank_kernel(const double *__restrict__ lists_rc, const long long *__restric
 constexpr int kApThreads = 256;
 constexpr int kApTile    = 2048;
 constexpr int kRankCap   = 4096;   // refine until sure + boundary fit this; the rank itself takes up to kSurvCap
-
-struct KeyId {
-    unsigned long long key;   // f64_to_sort_key(rc); ~0 for padding
-    long long          id;    // arc id; INT64_MAX for padding
-};
-// L2 load (lists are rewritten by other SMs between grid-wide barriers of one kernel)
-__device__ __forceinline__ KeyId ld_keyid(const KeyId *p) {
-    const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
-    return KeyId{v.x, (long long)v.y};
-}
-__device__ __forceinline__ bool keyid_less(const KeyId &a, const KeyId &b) {
-    return a.key < b.key || (a.key == b.key && a.id < b.id);
-}
 
 // All-pairs rank of n elements given by load(e) (padding sorts last).  Every thread of the grid
 // takes part; L = 1..32 lanes share one element and split the comparison range.  emit(e, rank)
@@ -679,21 +667,8 @@ merge_rank_kernel(const double *blocks_rc, const long long *blocks_id, long long
 
 // Merge straight out of the LL exchange buffer (sx_exchange_push_ll): staging a block in shared memory
 // IS the wait for it -- every slot is polled until both of its flags show this epoch.
-__device__ __forceinline__ bool ll_poll(const uint4 *slot, unsigned flag, unsigned long long &v,
-                                        unsigned long long t0, unsigned long long timeout_ns) {
-    for (;;) {
-        uint4 w;
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(slot) : "memory");
-        if (w.y == flag && w.w == flag) { v = (unsigned long long)w.x | ((unsigned long long)w.z << 32); return true; }
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > timeout_ns) { v = 0; return false; }
-    }
-}
-
 __global__ void __launch_bounds__(1024)
-merge_ll_kernel(const char *ll_buf, long long block_len, int G, int K, double *__restrict__ out_rc,
+merge_ll_kernel(char *ll_buf, long long block_len, int G, int K, double *__restrict__ out_rc,
                 long long *__restrict__ out_id, long long *out_n, long long *out_summary, int *status,
                 unsigned long long timeout_ns) {
     extern __shared__ __align__(16) unsigned char mg_raw[];
@@ -701,7 +676,11 @@ merge_ll_kernel(const char *ll_buf, long long block_len, int G, int K, double *_
     __shared__ int s_real;
     __shared__ long long s_hdr[4];
     const size_t slots_bytes = (size_t)2 * G * block_len * 16;
-    const unsigned long long epoch = *reinterpret_cast<const unsigned long long *>(ll_buf + slots_bytes);   // advanced by the push
+    // The merge keeps an epoch counter of its own ([2], [3] = CTAs done), advanced once per launch like the
+    // pushing side's ([0], [1]): it depends on no other kernel of this GPU, so it may be launched with
+    // programmatic stream serialisation and become resident while the pricing kernel is still draining.
+    unsigned long long *mctr = reinterpret_cast<unsigned long long *>(ll_buf + slots_bytes) + 2;
+    const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(mctr) + 1ull;
     const unsigned flag = (unsigned)epoch;
     const uint4 *slots = reinterpret_cast<const uint4 *>(ll_buf) + (size_t)(epoch & 1ull) * G * block_len;
     if (threadIdx.x == 0) { s_real = 0; s_hdr[0] = 0; s_hdr[1] = 0x7fffffffffffffffll; s_hdr[2] = 0; s_hdr[3] = 0; }
@@ -785,6 +764,17 @@ merge_ll_kernel(const char *ll_buf, long long block_len, int G, int K, double *_
             rank += lo;
         }
         if (rank < K) { out_rc[rank] = sort_key_to_f64(mine.key); out_id[rank] = mine.id; }
+    }
+    // not done before the kernel this one was (programmatically) serialised after: what follows in the
+    // stream may rely on both
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {                       // the last CTA to finish advances the merge epoch
+        __threadfence();
+        if (atomicAdd(mctr + 1, 1ull) == (unsigned long long)(gridDim.x - 1)) {
+            mctr[1] = 0ull;
+            *reinterpret_cast<volatile unsigned long long *>(mctr) = epoch;
+        }
     }
 }
 
@@ -964,7 +954,7 @@ extern "C" int sx_topk_merge(const double *blocks_rc, const int64_t *blocks_id, 
     return SX_OK;
 }
 
-extern "C" int sx_topk_merge_ll(const void *ll_buf_local, int64_t block_len, int64_t G, int64_t K, double *out_rc,
+extern "C" int sx_topk_merge_ll(void *ll_buf_local, int64_t block_len, int64_t G, int64_t K, double *out_rc,
                                 int64_t *out_id, int64_t *out_n, int64_t *out_summary, int32_t *status_dev,
                                 void *stream) {
     if (!ll_buf_local || G <= 0 || K <= 0 || block_len < 2 * K + 4 || !out_rc || !out_id || !out_n || !status_dev)
@@ -973,9 +963,18 @@ extern "C" int sx_topk_merge_ll(const void *ll_buf_local, int64_t block_len, int
     if (stage_bytes > 200 * 1024) return SX_ERR_TOO_LARGE;
     SX_CUDA(cudaFuncSetAttribute(merge_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     long long mg = (G * K + 1023) / 1024;
-    merge_ll_kernel<<<(int)mg, 1024, stage_bytes, (cudaStream_t)stream>>>(
-        (const char *)ll_buf_local, block_len, (int)G, (int)K, out_rc, (long long *)out_id, (long long *)out_n,
-        (long long *)out_summary, status_dev, /*timeout_ns=*/10ull * 1000 * 1000 * 1000);
-    SX_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)mg);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = stage_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SX_CUDA(cudaLaunchKernelEx(&cfg, merge_ll_kernel, (char *)ll_buf_local, (long long)block_len, (int)G, (int)K, out_rc,
+                               (long long *)out_id, (long long *)out_n, (long long *)out_summary, (int *)status_dev,
+                               /*timeout_ns=*/10ull * 1000 * 1000 * 1000));
     return SX_OK;
 }

@@ -21,8 +21,9 @@ SX_STATUS_CAND_OVERFLOW = 1
 SX_STATUS_NEED_SORTED = 2
 SX_STATUS_K_MISMATCH = 4
 SX_STATUS_NAN_RC = 8
-SX_STATUS_REPEAT_MASK = 3
-SX_ABI_VERSION = 2
+SX_STATUS_NEED_UNFUSED = 16
+SX_STATUS_REPEAT_MASK = 19
+SX_ABI_VERSION = 3
 
 
 class SxError(RuntimeError):
@@ -85,6 +86,13 @@ SIGNATURES = {
     "sx_price_arcs": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _dbl, _p, _p, _p, _p, _i64, _p, _p]),
     "sx_price_set_tuning": (_int, [_int, _int]),
     "sx_price_set_tma_options": (_int, [_int, _int]),
+    "sx_fused_state_bytes": (_sz, []),
+    "sx_fused_workspace_bytes": (_sz, []),
+    "sx_fused_state_timestamps_offset": (_sz, []),
+    "sx_fused_state_init": (_int, [_p, _i64, _p]),
+    "sx_fused_merge_fits": (_int, [_i64, _int]),
+    "sx_price_dense_ot_fused": (_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _dbl, _p, _p, _p, _i64, _i64, _p, _i64,
+                                       _p, _int, _int, _p, _p, _p, _sz, _p]),
     "sx_topk_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_topk_select": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
     "sx_topk_select_sorted": (_int, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),

@@ -16,6 +16,7 @@ from . import _native
 from ._native import check, lib
 
 TOL_RC = 1e-6   # TOLERANCE_FOR_REDUCED_COSTS, reference parameters.py:8
+FUSED_DEFAULT = True   # dense pricing passes use sx_price_dense_ot_fused when the matrix allows the TMA path
 
 
 def _require_cuda():
@@ -195,7 +196,7 @@ class Pricer:
 
     BLOCK_TAIL = 6      # header (4) + n_out + pad (block length stays even: 16-byte peer stores)
 
-    def __init__(self, device, K: int, cand_cap: int | None = None):
+    def __init__(self, device, K: int, cand_cap: int | None = None, fused: bool | None = None):
         _require_cuda()
         self.device = device
         self.K = int(K)
@@ -214,6 +215,13 @@ class Pricer:
         # pinned staging for the per-pass host round trip
         self.h_block = torch.zeros(2 * Kp + self.BLOCK_TAIL, dtype=torch.int64).pin_memory()
         self.launches = 0
+        # fused pass (sx_price_dense_ot_fused): two selection states used by alternate passes + control block
+        self.fused = bool(FUSED_DEFAULT if fused is None else fused) and Kp <= _native.SX_TOPK_MAX_K
+        self._fused_passes, self._last_fused = 0, False
+        if self.fused:
+            self.fstate = torch.zeros(lib.sx_fused_state_bytes(), dtype=torch.uint8, device=device)
+            self.fws = _ws(lib.sx_fused_workspace_bytes(), device)
+            check(lib.sx_fused_state_init(_ptr(self.fstate), Kp, _stream()), "sx_fused_state_init")
 
     def _alloc(self):
         self.cand_rc = torch.empty(max(self.cap, 1), dtype=torch.float64, device=self.device)
@@ -223,6 +231,7 @@ class Pricer:
     def reset(self):
         check(lib.sx_price_pass_begin(_ptr(self.header), _ptr(self.sel), self.K, _stream()), "sx_price_pass_begin")
         self.launches += 1
+        self._last_fused = False
 
     def price_dense(self, M, ld, row0, S_loc, D, y_src, y_dst, tol=TOL_RC, rc_out=None, variant=-1):
         check(lib.sx_price_dense_ot(_ptr(M), ld, row0, S_loc, D, _ptr(y_src), _ptr(y_dst), float(tol),
@@ -231,6 +240,48 @@ class Pricer:
                                     variant, _stream()),
               "sx_price_dense_ot")
         self.launches += 1
+
+    @staticmethod
+    def fusable(M, ld) -> bool:
+        """The fused pass needs the TMA path: 16-byte aligned base and an even leading dimension."""
+        return M.data_ptr() % 16 == 0 and ld % 2 == 0
+
+    def price_dense_fused(self, M, ld, row0, S_loc, D, y_src, y_dst, tol=TOL_RC, peer_bufs=None, rank=0, G=1,
+                          merged=None, xstatus=None):
+        """begin + pricing + selection (+ push of the block to `peer_bufs`, + merge of the G blocks into
+        `merged`) as one launch."""
+        check(lib.sx_price_dense_ot_fused(_ptr(M), ld, row0, S_loc, D, _ptr(y_src), _ptr(y_dst), float(tol),
+                                          _ptr(self.fstate), _ptr(self.cand_rc), _ptr(self.cand_id),
+                                          self.cap if self.K > 0 else 0, self.Kp, _ptr(self.block),
+                                          self.block.numel(), peer_bufs, rank, G, _ptr(merged), _ptr(xstatus),
+                                          _ptr(self.fws),
+                                          self.fws.numel(), _stream()), "sx_price_dense_ot_fused")
+        self.launches += 1
+        self._fused_passes += 1
+        self._last_fused = True
+
+    def fused_phase_us(self):
+        """Where CTA 0 of the last fused pass spent its time (us): pricing, barrier 1, filter, barrier 2, rank."""
+        off = lib.sx_fused_state_timestamps_offset()
+        t = self.fstate[off:off + 64].view(torch.int64).cpu().numpy()
+        names = ["pricing", "barrier1", "bound+filter", "barrier2", "rank+emit"]
+        out = {n: round(float(t[i + 1] - t[i]) * 1e-3, 2) for i, n in enumerate(names)}
+        out["last_cta_end_minus_cta0_rank_end"] = round(float(t[6] - t[5]) * 1e-3, 2)
+        out["gap_since_previous_pass_end"] = round(float(t[0] - t[7]) * 1e-3, 2)
+        return out
+
+    def note_replayed_fused_passes(self, n: int = 1):
+        """A captured CUDA graph holding a fused pass was replayed n times (keeps `n_candidates` right)."""
+        self._fused_passes += n
+
+    def n_candidates(self) -> int:
+        """Length of the (pruned) candidate list the last pass left (diagnostics / tests); synchronises."""
+        if self.K == 0:
+            return 0
+        if self._last_fused:
+            off = ((self._fused_passes - 1) & 1) * lib.sx_select_state_bytes()
+            return int(self.fstate[off:off + 8].view(torch.int64).item())
+        return int(self.sel[:8].view(torch.int64).item())
 
     def price_arcs(self, c, tail, head, vbasis, y, id0=0, tol=TOL_RC, rc_out=None):
         check(lib.sx_price_arcs(_ptr(c), _ptr(tail), _ptr(head), _ptr(vbasis), _ptr(y), c.numel(), id0,
@@ -291,20 +342,29 @@ class Pricer:
 
 
 def price_dense_ot(M: torch.Tensor, y: torch.Tensor, K: int = 0, tol: float = TOL_RC, want_rc=False,
-                   variant=-1, pricer: Pricer | None = None) -> PriceResult:
+                   variant=-1, pricer: Pricer | None = None, fused: bool | None = None) -> PriceResult:
     """One pricing pass over a device-resident S x D cost matrix with duals y (S + D).
     rc_ij = M_ij - (y[S+j] - y[i]); reference net_manager.py:474-497."""
     S, D = M.shape
-    pr = pricer or Pricer(M.device, K)
+    pr = pricer or Pricer(M.device, K, fused=(FUSED_DEFAULT if fused is None else fused) and not want_rc
+                          and variant in (-1, 0))
     rc = torch.empty(S * D, dtype=torch.float64, device=M.device) if want_rc else None
+    fused = pr.fused and fused is not False and not want_rc and variant in (-1, 0) \
+        and Pricer.fusable(M, M.stride(0)) and S > 0
     while True:
-        pr.reset()
-        pr.price_dense(M, M.stride(0), 0, S, D, y[:S], y[S:S + D], tol, rc, variant)
-        pr.select()
+        if fused:
+            pr.price_dense_fused(M, M.stride(0), 0, S, D, y[:S], y[S:S + D], tol)
+        else:
+            pr.reset()
+            pr.price_dense(M, M.stride(0), 0, S, D, y[:S], y[S:S + D], tol, rc, variant)
+            pr.select()
         res = pr.fetch()
-        if not pr.overflowed(res):
+        if pr.overflowed(res):
+            pr.grow(res.n_violating)   # more violators than candidate slots: size exactly, price again
+        elif fused and (pr.status & _native.SX_STATUS_NEED_UNFUSED):
+            fused = False              # too many ties for the in-kernel selection: separate kernels
+        else:
             break
-        pr.grow(res.n_violating)   # more violators than candidate slots: size exactly, price again
     res.rc = rc
     return res
 

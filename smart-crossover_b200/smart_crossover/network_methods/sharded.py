@@ -44,16 +44,19 @@ class ShardedDensePricer:
     row-major, device resident for the life of the problem, like the reference keeps `ot.M`)."""
 
     def __init__(self, M_loc: torch.Tensor, S: int, row0: int, K: int, tol: float = dev.TOL_RC,
-                 group=None, variant: int = -1, exchange: str = "ll", use_graph: bool = True, fused: bool = False):
+                 group=None, variant: int = -1, exchange: str = "ll", use_graph: bool = True, fused: bool | None = None,
+                 fused_merge: bool = True):
         self.M = M_loc
-        self.fused = False
         self.S, self.D = int(S), int(M_loc.shape[1])
         self.S_loc, self.row0 = int(M_loc.shape[0]), int(row0)
         self.K, self.tol, self.variant = int(K), float(tol), variant
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.pricer = dev.Pricer(M_loc.device, self.K)
+        self.fused = bool(dev.FUSED_DEFAULT if fused is None else fused) and variant in (-1, 0) and dev.Pricer.fusable(M_loc, M_loc.stride(0)) \
+            and max(self.K, 1) <= _native.SX_TOPK_MAX_K and self.S_loc > 0
+        self.pricer = dev.Pricer(M_loc.device, self.K, fused=self.fused)
         self._merge_launches = 0
+        self._dead = False
         self.use_graph = bool(use_graph)
         self._graph, self._capture_tried, self._graph_launches, self._replayed_launches = None, False, 0, 0
         self._capture_overcount = 0
@@ -82,12 +85,25 @@ class ShardedDensePricer:
         if self.exchange == "ll" and 16 * self.world * Kp > 200 * 1024:
             self.exchange = "p2p"                       # blocks do not fit the merge kernel's shared memory
         if self.exchange in ("ll", "p2p"):
+            err = None
             try:
                 self._setup_p2p(Kp)
-            except Exception as e:                      # no peer access on this box: say so, use NCCL
+            except Exception as e:                      # no peer access on this box
+                err = e
+            # every rank must use the same exchange: one rank falling back alone would leave the others
+            # spinning on its slots (all_reduce MIN of the success flags)
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=M_loc.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # also the barrier after the zero-fill
+            if int(ok.item()) == 0:
                 import warnings
-                warnings.warn(f"NVLink peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+                warnings.warn("NVLink peer exchange unavailable on at least one rank"
+                              + (f" ({type(err).__name__}: {err})" if err is not None else "")
+                              + "; every rank uses the NCCL all-gather")
                 self.exchange = "nccl"
+
+        # fused pass + "ll" exchange: the merge of the G blocks runs inside the same kernel when they fit
+        self.fused_merge = bool(fused_merge) and self.fused and self.exchange == "ll" \
+            and bool(lib.sx_fused_merge_fits(Kp, self.world))
 
     def _setup_p2p(self, Kp: int):
         import torch.distributed._symmetric_memory as symm
@@ -104,15 +120,19 @@ class ShardedDensePricer:
         if self.exchange == "p2p":
             off = lib.sx_exchange_epoch_offset(blk, self.world) // 8
             self._epoch_ctr = self._symm[off:off + 1]
-        dist.barrier(group=self.group)
 
     @property
     def stage_names(self):
         """Names of the intervals between the `stage_events` of `enqueue`."""
+        if self.fused:
+            return ["fused begin+pricing+selection" + ("+push" if self.exchange == "ll" else "")
+                    + ("+merge" if self.fused_merge else ""), "selection", "exchange", "merge"]
         return ["begin+pricing", "selection", "exchange", "merge"]
 
     @property
     def pricing_kernel_name(self):
+        if self.fused:
+            return "price_fused_kernel"
         return "price_dense_tma_kernel" if self.variant in (-1, 0) else "price_dense_direct_kernel"
 
     @property
@@ -122,7 +142,7 @@ class ShardedDensePricer:
 
     # -- device-only step: everything stays on the GPU(s) --------------------------------------
     def enqueue(self, y_dev: torch.Tensor, kernel_events=None, sorted_path: bool = False, stage_events=None,
-                y_parts=None):
+                y_parts=None, unfused: bool = False):
         """Enqueue one pricing pass; returns device tensors
         (rc[K], id[K], n_out, count, min key, largest per-rank count, status).  A non-zero status
         (SX_STATUS_*) means the pass must be repeated (`price` does that).  `kernel_events` =
@@ -134,29 +154,53 @@ class ShardedDensePricer:
         y_src, y_dst = y_parts if y_parts is not None else (y_dev[self.row0:self.row0 + self.S_loc],
                                                               y_dev[self.S:self.S + self.D])
         mark = (lambda i: stage_events[i].record()) if stage_events is not None else (lambda i: None)
+        fused = self.fused and not sorted_path and not unfused
         mark(0)
-        p.reset()
-        if kernel_events is not None:
-            kernel_events[0].record()
-        p.price_dense(self.M, self.M.stride(0), self.row0, self.S_loc, self.D, y_src, y_dst,
-                      self.tol, None, self.variant)
-        if kernel_events is not None:
-            kernel_events[1].record()
-        mark(1)
-        p.select(sorted_path=sorted_path)
+        if fused:
+            # ONE launch: state clear of the next pass, pricing, selection and (exchange "ll") the push of the
+            # selected arcs into every peer's buffer
+            if kernel_events is not None:
+                kernel_events[0].record()
+            if self.exchange == "ll":
+                p.price_dense_fused(self.M, self.M.stride(0), self.row0, self.S_loc, self.D, y_src, y_dst, self.tol,
+                                    self._hdl.buffer_ptrs_dev, self._rank, self.world,
+                                    merged=self.d_out if self.fused_merge else None,
+                                    xstatus=self._xstatus if self.fused_merge else None)
+            else:
+                p.price_dense_fused(self.M, self.M.stride(0), self.row0, self.S_loc, self.D, y_src, y_dst, self.tol)
+            if kernel_events is not None:
+                kernel_events[1].record()
+            mark(1)
+        else:
+            p.reset()
+            if kernel_events is not None:
+                kernel_events[0].record()
+            p.price_dense(self.M, self.M.stride(0), self.row0, self.S_loc, self.D, y_src, y_dst,
+                          self.tol, None, self.variant)
+            if kernel_events is not None:
+                kernel_events[1].record()
+            mark(1)
+            p.select(sorted_path=sorted_path)
         mark(2)
         Kp = max(self.K, 1)
         if self.world == 1:
             return p.out_rc, p.out_id, p.out_n[0], p.header[0], p.header[1], p.header[0], p.header[3]
         # one exchange: every rank's block (top-K + header) lands in `gathered`, consumed in place
         if self.exchange == "ll":
-            check(lib.sx_exchange_push_ll(dev._ptr(p.block), self.blk, self._hdl.buffer_ptrs_dev, self._rank,
-                                          self.world, dev._stream()), "sx_exchange_push_ll")
+            if fused and self.fused_merge:                 # the merge ran inside the pricing kernel too
+                mark(3)
+                mark(4)
+                return (self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2],
+                        self._m_sum[3])
+            if not fused:
+                check(lib.sx_exchange_push_ll(dev._ptr(p.block), self.blk, self._hdl.buffer_ptrs_dev, self._rank,
+                                              self.world, dev._stream()), "sx_exchange_push_ll")
+                self._merge_launches += 1
             mark(3)
             check(lib.sx_topk_merge_ll(dev._ptr(self._symm), self.blk, self.world, Kp, dev._ptr(self._m_rc),
                                        dev._ptr(self._m_id), dev._ptr(self._m_n), dev._ptr(self._m_sum),
                                        dev._ptr(self._xstatus), dev._stream()), "sx_topk_merge_ll")
-            self._merge_launches += 2
+            self._merge_launches += 1
             mark(4)
             return (self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2],
                     self._m_sum[3])
@@ -182,12 +226,13 @@ class ShardedDensePricer:
         return self._m_rc, self._m_id, self._m_n[0], self._m_sum[0], self._m_sum[1], self._m_sum[2], self._m_sum[3]
 
     # -- host-facing call: duals in, (count, min, top-K) out --------------------------------------
-    def _step(self, sorted_path: bool = False):
+    def _step(self, sorted_path: bool = False, unfused: bool = False):
         """H2D of the duals this rank needs (its rows + every sink), one pass, D2H of the result."""
         r0 = self.row0                                             # y_loc = [this rank's S_loc source duals | D sink duals]
         self.y_loc[:self.S_loc].copy_(self.h_y[r0:r0 + self.S_loc], non_blocking=True)
         self.y_loc[self.S_loc:].copy_(self.h_y[self.S:], non_blocking=True)
-        self.enqueue(None, sorted_path=sorted_path, y_parts=(self.y_loc[:self.S_loc], self.y_loc[self.S_loc:]))
+        self.enqueue(None, sorted_path=sorted_path, y_parts=(self.y_loc[:self.S_loc], self.y_loc[self.S_loc:]),
+                     unfused=unfused)
         if self.world == 1:
             self.pricer.h_block.copy_(self.pricer.block, non_blocking=True)
         else:
@@ -222,6 +267,8 @@ class ShardedDensePricer:
             return
         self._graph_launches = self.launches - launches
         self._capture_overcount += self._graph_launches       # recorded, not executed
+        if self.fused:
+            self.pricer._fused_passes -= 1
         self._graph = g
 
     def _read_result(self):
@@ -236,6 +283,7 @@ class ShardedDensePricer:
         h = self.h_out.numpy()
         xs = int(h[2 * K + 5]) & 0xFFFFFFFF                    # int32 status word of the exchange / merge kernels
         if self.exchange in ("ll", "p2p") and xs:
+            self._dead = True                                   # epochs may be out of step now
             check(xs - (1 << 32) if xs >= (1 << 31) else xs, "peer exchange")
         n_out = int(h[2 * K]) if self.K > 0 else 0
         res = dev.PriceResult(int(h[2 * K + 1]), float(lib.sx_key_to_f64(int(h[2 * K + 2]))),
@@ -252,14 +300,19 @@ class ShardedDensePricer:
         if self._graph is None and self.use_graph and not self._capture_tried:
             self._capture_tried = True
             self._capture()
-        sorted_path = False
+        if self._dead:
+            raise RuntimeError("this pricer saw a peer-exchange timeout; its epoch counters may be out of step with "
+                               "the peers': build a new one")
+        sorted_path, unfused = False, False
         first = True
         while True:
             if first and self._graph is not None:
                 self._graph.replay()
                 self._replayed_launches += self._graph_launches
+                if self.fused:
+                    self.pricer.note_replayed_fused_passes(1)
             else:
-                self._step(sorted_path=sorted_path)
+                self._step(sorted_path=sorted_path, unfused=unfused)
             first = False
             torch.cuda.current_stream().synchronize()
             res, status, cmax = self._read_result()
@@ -271,8 +324,10 @@ class ShardedDensePricer:
             if status & _native.SX_STATUS_CAND_OVERFLOW:
                 self.pricer.grow(cmax)
                 self._graph, self._capture_tried = None, False      # buffers moved: record again next time
-            else:
+            elif status & _native.SX_STATUS_NEED_SORTED:
                 sorted_path = True
+            else:                                                   # SX_STATUS_NEED_UNFUSED: the separate kernels refine
+                unfused = True
 
     @property
     def y_pinned(self) -> np.ndarray:

@@ -43,7 +43,7 @@ def _passes(S, D):
     return M, ys
 
 
-def _worker(rank, world, port, exchange, S, D, K, fused):
+def _worker(rank, world, port, exchange, S, D, K, kw):
     import torch
     import torch.distributed as dist
     from oracle import network_oracle as orc
@@ -57,9 +57,10 @@ def _worker(rank, world, port, exchange, S, D, K, fused):
         M, ys = _passes(S, D)
         row0, S_loc = row_partition(S, world, rank)
         M_loc = torch.from_numpy(np.ascontiguousarray(M[row0:row0 + S_loc])).to(device)
-        kw = {} if fused is None else {"fused": fused}
         sp = ShardedDensePricer(M_loc, S, row0, K, exchange=exchange, **kw)
         assert sp.exchange == exchange, f"exchange fell back to {sp.exchange}"
+        assert sp.fused == (kw.get("fused") is not False and D % 2 == 0), "fused pass not in the expected state"
+        assert sp.fused_merge == (sp.fused and exchange == "ll" and kw.get("fused_merge", True)), "in-kernel merge?"
         for rep in range(2):                       # second sweep replays the captured CUDA graph
             for name, y in ys:
                 res = sp.price(y)
@@ -84,16 +85,32 @@ def _worker(rank, world, port, exchange, S, D, K, fused):
         dist.destroy_process_group()
 
 
-def _spawn(world, exchange, S, D, K, fused=None):
+def _spawn(world, exchange, S, D, K, **kw):
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), exchange, S, D, K, fused), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), exchange, S, D, K, kw), nprocs=world, join=True)
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
 @pytest.mark.parametrize("exchange", ["ll", "p2p", "nccl"])
 @pytest.mark.parametrize("K", [64, 1024])
 def test_sharded_pricer_on_real_ranks_matches_oracle(exchange, K):
-    _spawn(2, exchange, 301, 517, K)
+    _spawn(2, exchange, 301, 518, K)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("exchange", ["ll", "nccl"])
+def test_sharded_pricer_separate_kernels_on_real_ranks(exchange):
+    """The round-1 path (pass begin, pricing, selection, push and merge as separate launches), which the
+    fused pass falls back to, on real ranks."""
+    _spawn(2, exchange, 301, 517, 256, fused=False)
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("K", [64, 1024])
+def test_sharded_pricer_fused_push_with_separate_merge_kernel(K):
+    """Fused price + select + push, merge as a kernel of its own (programmatic stream serialisation):
+    the path taken when G blocks of K do not fit the in-kernel merge."""
+    _spawn(2, "ll", 301, 518, K, fused_merge=False)
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
@@ -101,6 +118,7 @@ def test_sharded_pricer_uneven_rows_and_more_ranks_than_rows_allow():
     """S not divisible by G, and (with every GPU of the box) slabs of a handful of rows."""
     G = min(_n_gpus(), 8)
     _spawn(G, "ll", 8 * G + 3, 700, 256)
+    _spawn(2, "ll", 301, 517, 64)                  # odd D: no TMA path, so no fused pass either
 
 
 @pytest.mark.skipif(_n_gpus() < 4, reason="needs at least 4 GPUs")

@@ -25,6 +25,15 @@ def dev():
     return device
 
 
+@pytest.fixture(params=["fused", "separate"])
+def fused_mode(request, dev):
+    """Dense pricing passes through the fused kernel (price + select in one launch) or the separate ones."""
+    old = dev.FUSED_DEFAULT
+    dev.FUSED_DEFAULT = request.param == "fused"
+    yield request.param
+    dev.FUSED_DEFAULT = old
+
+
 def cu(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
@@ -372,7 +381,7 @@ def test_price_dense_golden(dev, name, variant):
                                          (1000, 1002, 5000, 0.05), (2049, 4100, 100, 0.01),
                                          (4096, 4096, 1024, 0.0)])
 @pytest.mark.parametrize("variant", [-1, 1, 2])
-def test_price_dense_random_shapes(dev, S, D, K, noise, variant):
+def test_price_dense_random_shapes(dev, fused_mode, S, D, K, noise, variant):
     if variant == 1 and D % 2:
         pytest.skip("vector loads need an even leading dimension")
     s, d, M = cases.ot_points(S, D, 1000 + S)
@@ -390,7 +399,7 @@ def test_price_dense_random_shapes(dev, S, D, K, noise, variant):
 
 @pytest.mark.parametrize("variant", [-1, 1, 2])
 @pytest.mark.parametrize("where", ["cost", "source dual", "sink dual"])
-def test_price_nan_reduced_cost_is_not_optimal(dev, variant, where):
+def test_price_nan_reduced_cost_is_not_optimal(dev, fused_mode, variant, where):
     """A NaN reduced cost: `np.all(rc >= -tol)` (net_manager.py:496) is False, `(rc < -tol).sum()` does not
     count it and NumPy's argsort puts it last.  The device pass must report the same three things."""
     S, D = 130, 514
@@ -427,7 +436,7 @@ def test_price_nan_reduced_cost_is_not_optimal(dev, variant, where):
         assert ra.n_violating == cnt and ra.has_nan and not ra.optimal and np.array_equal(ra.topk_id, ids)
 
 
-def test_price_tied_reduced_costs_and_overflow(dev):
+def test_price_tied_reduced_costs_and_overflow(dev, fused_mode):
     """Integer costs and duals: massive rc ties (broken by arc id); candidate buffer smaller
     than the violator count forces the exact re-pricing path."""
     s, d, M = cases.ot_grid(12, 5)          # 144 x 144, integer costs
@@ -443,7 +452,7 @@ def test_price_tied_reduced_costs_and_overflow(dev):
 
 
 @pytest.mark.parametrize("frac,K", [(0.5, 64), (0.5, 1024), (0.9, 1), (0.02, 1024), (0.3, 4000)])
-def test_price_many_violators_are_pruned(dev, frac, K):
+def test_price_many_violators_are_pruned(dev, fused_mode, frac, K):
     """A far-from-optimal y (10 % - 90 % of all arcs violate): the count stays exact, the candidate
     list stays short (running histogram bound) and the top-K is still exact."""
     S, D = 6000, 4096
@@ -457,12 +466,12 @@ def test_price_many_violators_are_pruned(dev, frac, K):
     res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
     assert res.n_violating == cnt and res.min_rc == mn and cnt > 0.9 * frac * S * D
     assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
-    n_cand = int(pr.sel[:8].view(torch.int64).item())
-    assert n_cand < cnt // 4, f"pruning kept {n_cand} of {cnt} violators"
+    n_cand = pr.n_candidates()
+    assert 0 < n_cand < cnt // 4, f"pruning kept {n_cand} of {cnt} violators"
     assert pr.status == 0
 
 
-def test_price_all_equal_reduced_costs(dev):
+def test_price_all_equal_reduced_costs(dev, fused_mode):
     """Every arc has the same reduced cost: no bound can prune and 60 000 candidates tie at the K-th
     value; the selection refines on the arc id (ids win ties).  The sorted path gives the same."""
     S, D, K = 300, 200, 100
@@ -480,7 +489,7 @@ def test_price_all_equal_reduced_costs(dev):
     assert np.array_equal(alt.topk_id, np.arange(K)) and alt.n_violating == S * D
 
 
-def test_price_near_ties_at_the_kth_value(dev):
+def test_price_near_ties_at_the_kth_value(dev, fused_mode):
     """One tight arc per column shifted by the same delta (bench.py's planted duals): D reduced costs
     that differ only in their last bits sit at the top, far more than 8192 of them."""
     S, D, K = 700, 20000, 1024
@@ -498,7 +507,7 @@ def test_price_near_ties_at_the_kth_value(dev):
     assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
 
 
-def test_price_bins_are_monotone_over_magnitudes(dev):
+def test_price_bins_are_monotone_over_magnitudes(dev, fused_mode):
     """Violations spread over 12 orders of magnitude, both signs of the exponent, with K landing
     inside a dense cluster: exercises the two-level histogram scan."""
     S, D = 512, 1024
@@ -515,7 +524,7 @@ def test_price_bins_are_monotone_over_magnitudes(dev):
         assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
 
 
-def test_price_tma_stage_release_under_atomic_pressure(dev):
+def test_price_tma_stage_release_under_atomic_pressure(dev, fused_mode):
     """Every arc violates and all reduced costs fall into one histogram bin, so nothing is pruned and
     every warp-tile appends ~500 candidates (global atomics + stores saturate the load/store queue).
     The TMA pipeline must still hand out intact tiles: a stage may only be released once its data has
@@ -543,6 +552,14 @@ def test_price_tma_stage_release_under_atomic_pressure(dev):
         pr.select()
         res = pr.fetch()
         assert res.n_violating == cnt and np.array_equal(res.topk_id, ids)
+    if fused_mode == "fused":
+        # the same pressure inside the fused kernel: 8 M survivors are too many for its in-kernel rank, so
+        # every pass raises SX_STATUS_NEED_UNFUSED and is repeated by the separate kernels
+        assert pr.fused
+        for _ in range(3):
+            res = dev.price_dense_ot(cu(M), cu(y), K=K, pricer=pr)
+            assert pr.status == 0 and res.n_violating == cnt and res.min_rc == mn
+            assert np.array_equal(res.topk_id, ids) and np.array_equal(res.topk_rc, vals)
 
 
 def test_price_row_slabs_and_merge(dev):
@@ -617,6 +634,108 @@ def test_ll_exchange_and_merge_with_emulated_ranks(dev, G, K):
         assert int(o_n.item()) == k and np.array_equal(o_id[:k].cpu().numpy(), whole.topk_id)
 
 
+@pytest.mark.parametrize("G,K", [(2, 128), (8, 1024), (5, 33), (3, 1)])
+def test_fused_pass_pushes_to_emulated_ranks(dev, G, K):
+    """sx_price_dense_ot_fused with G emulated ranks on one GPU: every "rank" prices its row slab, selects and
+    stores its block straight into all G exchange buffers from inside the pricing kernel; every rank's merge
+    then finds all G blocks in its own buffer.  Five passes on the same pricers (both selection states, both
+    buffer halves, a converged pass with only padding, a pass where most arcs violate)."""
+    from smart_crossover._native import check, lib
+    S, D = 64 * G + 3, 700
+    s, d, M = cases.ot_points(S, D, 50 + G)
+    Mt = cu(M)
+    blk = 2 * K + dev.Pricer.BLOCK_TAIL
+    nbytes = lib.sx_exchange_ll_buffer_bytes(blk, G)
+    bufs = [torch.zeros(nbytes // 8, dtype=torch.int64, device="cuda") for _ in range(G)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    bounds = [S * g // G for g in range(G + 1)]
+    pricers = [dev.Pricer(torch.device("cuda"), K, fused=True) for _ in range(G)]
+    ys = [cases.planted_duals(M, 7, 0.05), cases.planted_duals(M, 8, 0.3),
+          cases.planted_duals(M, 9, 0.0) - np.concatenate([np.zeros(S), np.full(D, 1e-3)]),
+          np.concatenate([np.zeros(S), np.full(D, 1.0)]), cases.planted_duals(M, 10, 0.01)]
+    for y in ys:
+        yt = cu(y)
+        cnt, mn, ids, vals = orc.price_summary(orc.reduced_costs_ot(M, y), K)
+        for g in range(G):
+            r0, r1 = bounds[g], bounds[g + 1]
+            pricers[g].price_dense_fused(Mt[r0:r1], D, r0, r1 - r0, D, yt[r0:r1], yt[S:], peer_bufs=dev._ptr(ptrs),
+                                         rank=g, G=G)
+        for g in range(G):
+            out = torch.zeros(2 * K + 6, dtype=torch.int64, device="cuda")
+            check(lib.sx_topk_merge_ll(dev._ptr(bufs[g]), blk, G, K, dev._ptr(out[:K]), dev._ptr(out[K:2 * K]),
+                                       dev._ptr(out[2 * K:]), dev._ptr(out[2 * K + 1:]), dev._ptr(status),
+                                       dev._stream()), "merge_ll")
+            h = out.cpu().numpy()
+            k = int(h[2 * K])
+            assert int(status.item()) == 0 and k == ids.size
+            assert np.array_equal(h[K:K + k], ids) and h[:k].view(np.float64).tobytes() == vals.tobytes()
+            assert int(h[2 * K + 1]) == cnt and lib.sx_key_to_f64(int(h[2 * K + 2])) == mn
+            assert int(h[2 * K + 4]) == 0 and np.all(h[K + k:2 * K] == -1)
+        # the local blocks hold each slab's own top-K
+        for g in range(G):
+            r0, r1 = bounds[g], bounds[g + 1]
+            c_g, m_g, i_g, v_g = orc.price_summary(orc.reduced_costs_ot(M[r0:r1], np.concatenate([y[r0:r1], y[S:]])), K)
+            res = pricers[g].fetch()
+            assert res.n_violating == c_g and res.min_rc == m_g and pricers[g].status == 0
+            assert np.array_equal(res.topk_id, i_g + r0 * D) and res.topk_rc.tobytes() == v_g.tobytes()
+
+
+@pytest.mark.parametrize("K", [1, 64, 1024])
+def test_fused_pass_in_kernel_merge_of_one_block(dev, K):
+    """The in-kernel merge with G = 1 (the only form one GPU can run: with G > 1 every rank's kernel waits
+    for the others' pushes; tests/test_gpu_multirank.py covers that on real ranks): the block pushed into
+    the rank's own exchange buffer comes back merged, over several epochs."""
+    from smart_crossover._native import lib
+    S, D = 300, 1024
+    s, d, M = cases.ot_points(S, D, 91)
+    Mt = cu(M)
+    blk = 2 * K + dev.Pricer.BLOCK_TAIL
+    buf = torch.zeros(lib.sx_exchange_ll_buffer_bytes(blk, 1) // 8, dtype=torch.int64, device="cuda")
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
+    merged = torch.zeros(2 * K + 6, dtype=torch.int64, device="cuda")
+    xstatus = merged[2 * K + 5:].view(torch.int32)[:1]
+    pr = dev.Pricer(torch.device("cuda"), K, fused=True)
+    assert lib.sx_fused_merge_fits(K, 1)
+    for it, noise in enumerate([0.05, 0.3, 0.0, 0.01, 0.3]):
+        y = cases.planted_duals(M, 20 + it, noise)
+        if noise == 0.0:
+            y[S:] -= 1e-3
+        yt = cu(y)
+        cnt, mn, ids, vals = orc.price_summary(orc.reduced_costs_ot(M, y), K)
+        pr.price_dense_fused(Mt, D, 0, S, D, yt[:S], yt[S:], peer_bufs=dev._ptr(ptrs), rank=0, G=1, merged=merged,
+                             xstatus=xstatus)
+        h = merged.cpu().numpy()
+        k = int(h[2 * K])
+        assert k == ids.size and int(h[2 * K + 5]) == 0 and int(h[2 * K + 4]) == 0
+        assert np.array_equal(h[K:K + k], ids) and h[:k].view(np.float64).tobytes() == vals.tobytes()
+        assert int(h[2 * K + 1]) == cnt and lib.sx_key_to_f64(int(h[2 * K + 2])) == mn and int(h[2 * K + 3]) == cnt
+        assert np.all(h[K + k:2 * K] == -1)
+
+
+@pytest.mark.parametrize("K", [0, 1, 100, 1024])
+def test_fused_pass_sequence_on_one_pricer(dev, K):
+    """Passes alternate between the pricer's two selection states; each pass clears the other one.  A long
+    sequence of very different duals on ONE pricer must give the oracle's answer every time (a stale
+    histogram bin or counter would prune real candidates)."""
+    S, D = 1500, 2048
+    rng = np.random.default_rng(K)
+    M = rng.random((S, D))
+    Mt = cu(M)
+    pr = dev.Pricer(torch.device("cuda"), K, fused=True)
+    assert pr.fused
+    fracs = [0.5, 1e-4, 0.0, 0.9, 0.02, 0.0, 1e-5, 0.3, 0.3, 1.0]
+    for it, frac in enumerate(fracs):
+        y = np.concatenate([rng.normal(0, 1e-3, S), np.full(D, frac - 1e-4)])      # rc ~ M - frac
+        res = dev.price_dense_ot(Mt, cu(y), K=K, pricer=pr)
+        cnt, mn, ids, vals = orc.price_summary(orc.reduced_costs_ot(M, y), K)
+        # dense violations put more than 4096 candidates into the K-th value's histogram bin: those passes are
+        # repeated by the separate kernels (and the fused state must survive that); the others stay fused
+        assert pr.status == 0 and (pr._last_fused or frac > 0.02), f"pass {it} fell back"
+        assert res.n_violating == cnt and res.min_rc == mn, f"pass {it}"
+        assert np.array_equal(res.topk_id, ids) and res.topk_rc.tobytes() == vals.tobytes(), f"pass {it}"
+
+
 @pytest.mark.parametrize("name", MCF_FULL)
 def test_mcf_scores_queue_and_arc_pricing_golden(dev, name):
     import scipy.sparse as sp
@@ -660,7 +779,7 @@ def test_mcf_mid_digests(dev):
 
 
 # ---- full-size property tests (BASELINE.json configs[3]: 20 000 x 20 000, 3.2 GB) -------------------
-def test_c4_full_size_planted_violators(dev):
+def test_c4_full_size_planted_violators(dev, fused_mode):
     """No oracle pass at this size: plant a known set of violators into a dual-feasible instance
     and require the pricing pass to return exactly that set, in order."""
     S = D = 20000
