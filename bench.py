@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-fused", action="store_true",
                     help="price / select / push as separate launches (round-1 path) instead of the fused kernel")
     ap.add_argument("--no-c4", action="store_true", help="skip the second leg (dense OT 20 000 x 20 000)")
+    ap.add_argument("--no-manager", action="store_true", help="skip the OTManager end-to-end leg")
     ap.add_argument("--c4-size", type=int, default=20000)
     ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
     ap.add_argument("--sweep-ab", default="", metavar="I,J,..",
@@ -401,9 +402,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+        host_group = dist.new_group(backend="gloo")          # CPU-side waits (no kernel spinning on an idle GPU)
 
     def barrier():
         torch.cuda.synchronize()
@@ -430,7 +433,13 @@ def main():
         print(json.dumps(time_tree_build(args.tree_only, args.tree_only, device, reps=2)), flush=True)
         return
 
-    ctx = {"world": world, "rank": rank, "device": device, "barrier": barrier, "max_over_ranks": max_over_ranks}
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
+
+    ctx = {"world": world, "rank": rank, "device": device, "barrier": barrier, "max_over_ranks": max_over_ranks,
+           "host_barrier": host_barrier, "local": local}
     S = D = args.size
     if args.rows:
         S = args.rows
@@ -447,11 +456,13 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
     sampler = ClockSampler(local)
     main_leg = pricing_leg(args, S, D, ctx, steps, warmup, sampler=sampler, want_cpu=not args.no_cpu, want_cold=True)
+    main_mgr = manager_leg(args, S, D, ctx, steps, main_leg)
     # second, shorter leg: BASELINE.json configs[3] (dense OT 20 000 x 20 000, "pricing at 1/2/4/8 B200")
-    c4_leg = None
+    c4_leg, c4_mgr = None, None
     if not args.no_c4 and (S, D) != (args.c4_size, args.c4_size):
         c4_leg = pricing_leg(args, args.c4_size, args.c4_size, ctx, steps, warmup, sampler=None, want_cpu=False,
                              want_cold=False)
+        c4_mgr = manager_leg(args, args.c4_size, args.c4_size, ctx, steps, c4_leg)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -486,7 +497,8 @@ def main():
                        "fused": L["fused"],
                        "l2": f"inputs larger than L2 ({8 * L['S_loc'] * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
             "roofline": roofline_of(L), "cpu_baseline": L["cpu_baseline"],
-            "e2e": L["e2e"], "e2e_pinned": L["e2e_pinned"],
+            "e2e": main_mgr if main_mgr is not None else L["e2e"],
+            "e2e_one_process_per_gpu": L["e2e"], "e2e_pinned": L["e2e_pinned"],
             "topk_digest": L["topk_digest"], "merge_check": L["merge_check"],
             "stage_us_rank0": L["stage_us"], "e2e_cold": L["e2e_cold"], "gpu_launches": L["gpu_launches"],
             "clocks": L["clocks"], "tree_build": tree}
@@ -494,12 +506,72 @@ def main():
         C = c4_leg
         line["c4"] = {"workload": workload_of(C), "value": C["value"], "unit": UNIT, "ms_per_step": C["ms_per_step"],
                       "steps": steps, "rows_per_gpu": C["S_loc"], "violating_arcs": C["violating_arcs"],
-                      "roofline": roofline_of(C), "stage_us_rank0": C["stage_us"], "e2e": C["e2e"],
+                      "roofline": roofline_of(C), "stage_us_rank0": C["stage_us"],
+                      "e2e": c4_mgr if c4_mgr is not None else C["e2e"], "e2e_one_process_per_gpu": C["e2e"],
                       "e2e_pinned": C["e2e_pinned"], "topk_digest": C["topk_digest"],
                       "merge_check": C["merge_check"], "gpu_launches": C["gpu_launches"]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def manager_leg(args, S, D, ctx, steps, leg):
+    """End to end through the reference's call surface: `OTManager.price(y, K)` /
+    `OTManager.check_optimality_condition(x, y)` (net_manager.py:485-497) with a PAGEABLE dual vector, as
+    `column_generation` calls it with the LP solver's output (algorithms.py:132).  ONE process: rank 0 drives
+    all N GPUs of the job through the manager's persistent pricer (sx_ot_pricer: one worker thread, one
+    stream and one fused kernel per GPU); the other ranks of a torchrun job idle on a CPU barrier meanwhile.
+    Timed with the host clock around the blocking calls (what the caller sees)."""
+    import torch
+    world, rank = ctx["world"], ctx["rank"]
+    out = None
+    ctx["host_barrier"]()
+    if rank == 0 and not args.no_manager:
+        from smart_crossover import device as dev
+        from smart_crossover.network_methods.net_manager import OTManager
+        K = args.topk
+        devices = [(ctx["local"] + i) % torch.cuda.device_count() for i in range(world)]
+        slabs = dev.CostSlabs(S, D, devices)
+        for g, d in enumerate(devices):
+            with torch.cuda.device(d):
+                P, Q, a = make_points(S, D, torch.device("cuda", d))
+                make_slab(P, Q, slabs.row0[g], slabs.rows[g], out=slabs.view(g))
+                del P, Q, a
+        slabs.sync()
+        mgr = OTManager.from_device_cost(np.full(S, 1.0 / S), np.full(D, 1.0 / D), slabs)
+        y = np.array(leg["y_host"], copy=True)               # pageable, as a solver hands it over
+        for _ in range(3):
+            res = mgr.price(y, K=K)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = mgr.price(y, K=K)
+        dt = time.perf_counter() - t0
+        assert topk_digest(res.topk_id, res.topk_rc, res.n_violating, res.min_rc) == leg["topk_digest"], \
+            "OTManager.price disagrees with the device-timed arm"
+        for _ in range(3):
+            opt = mgr.check_optimality_condition(None, y)
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            opt = mgr.check_optimality_condition(None, y)
+        dt0 = time.perf_counter() - t1
+        assert opt == (leg["violating_arcs"] == 0)
+        st = mgr._pricer(K).stats()
+        G = len(devices)
+        blk = 2 * max(K, 1) + 6
+        out = {"value": S * D * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps,
+               "h2d_bytes_per_step": 8 * (S + G * D), "d2h_bytes_per_step": 8 * blk * G,
+               "call": "OTManager.price(y, K) -- one process drives all GPUs (sx_ot_pricer)",
+               "check_optimality_condition_ms": 1e3 * dt0 / steps,
+               "devices": devices, "fused": st["fused"], "merge_in_kernel": st["merge_in_kernel"],
+               "repeated_passes": st["repeated_passes"], "timer": "host wall clock around the blocking calls",
+               "inputs": "duals y in a pageable NumPy vector every step; each GPU's worker thread stages its "
+                         "S_loc + D entries in pinned memory and uploads them; merged result read back; cost "
+                         "matrix resident (uploaded / generated once per problem)"}
+        mgr._drop_device_state()
+        del mgr, slabs
+        torch.cuda.empty_cache()
+    ctx["host_barrier"]()
+    return out
 
 
 def committed_traffic(S_loc, D):
@@ -678,7 +750,7 @@ def pricing_leg(args, S, D, ctx, steps, warmup, sampler, want_cpu, want_cold):
            "kernel_ms_per_rank": per_rank_kern, "kernel": sp.pricing_kernel_name, "stage_us": stages,
            "gpu_launches": launches, "violating_arcs": count_dev, "topk_digest": digest, "merge_check": merge_check,
            "e2e": e2e, "e2e_pinned": e2e_pinned, "e2e_cold": cold, "cpu_baseline": cpu_baseline, "clocks": clocks,
-           "exchange": sp.exchange, "fused": sp.fused}
+           "exchange": sp.exchange, "fused": sp.fused, "y_host": y_host}
     del sp, M_loc, y_dev
     torch.cuda.empty_cache()
     barrier()

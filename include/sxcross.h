@@ -379,11 +379,41 @@ SX_API int    sx_sinkhorn_ot(const double *M, int64_t ld, int64_t S, int64_t D, 
                       int64_t check_every, double *f, double *g, double *x_out, int64_t *iters_h,
                       double *err_h, void *ws, size_t ws_bytes, void *stream);
 
-/* ---- host-buffer entry point (what a reference-side binding calls with NumPy arrays) ----
- * One pricing pass with HOST buffers: uploads y (and M if M_dev == NULL), prices, selects
- * the top K, and returns count / min / top-k on the host.  Synchronises before returning.
+/* ---- host-buffer entry points (what a reference-side binding calls with NumPy arrays) ----
+ * sx_ot_pricer: persistent pricer of one dense OT problem for `OTManager.check_optimality_condition`
+ * (net_manager.py:485-497, called once per column-generation round from algorithms.py:132).  It owns every
+ * buffer a pass needs (nothing is allocated per pass), one stream and one host worker thread per GPU, and
+ * row-shards the cost matrix over the ndev GPUs it is given: device g prices rows [S g / ndev, S (g+1) / ndev)
+ * with ONE kernel per pass (sx_price_dense_ot_fused: price + select + NVLink push + merge).  Single process,
+ * plain function calls; not thread-safe (one caller at a time), like the reference's managers.
+ *   slabs[g]: DEVICE pointer (on device devs[g], caller-owned, resident for the life of the pricer) to that
+ *     row range of M, row-major with leading dimension ld (even ld and 16-byte aligned slabs select the
+ *     TMA / fused path; anything else is priced by the scalar-load kernels).
+ *   K: top-K size (0: count / min only).  ndev > 1 needs K <= SX_TOPK_MAX_K and peer access between the
+ *     devices (SX_ERR_NO_DEVICE otherwise).
+ * sx_ot_pricer_price_h: y_src_h (S source duals) and y_dst_h (D sink duals) are HOST vectors (pageable is
+ *   fine: each worker copies its slice into pinned staging); returns count / min / top-K on the host and
+ *   (status_h, may be NULL) the SX_STATUS_* bits that survived (SX_STATUS_NAN_RC).  Repeats the pass
+ *   internally when the fused kernel asks for it (candidate overflow, ties).
+ * sx_ot_pricer_info: device / row range of shard g.  sx_ot_pricer_stats: passes, repeated passes, whether the
+ *   fused kernel and the in-kernel merge are in use.
+ */
+typedef struct sx_ot_pricer sx_ot_pricer;
+SX_API int    sx_ot_pricer_create(int ndev, const int *devs, const double *const *slabs, int64_t ld, int64_t S,
+                           int64_t D, int64_t K, double tol, sx_ot_pricer **out);
+SX_API int    sx_ot_pricer_destroy(sx_ot_pricer *p);
+SX_API int    sx_ot_pricer_info(const sx_ot_pricer *p, int g, int *dev, int64_t *row0, int64_t *S_loc);
+SX_API int    sx_ot_pricer_price_h(sx_ot_pricer *p, const double *y_src_h, const double *y_dst_h,
+                            unsigned long long *n_violating_h, double *min_rc_h, double *topk_rc_h,
+                            int64_t *topk_id_h, int64_t *topk_n_h, unsigned long long *status_h);
+SX_API int    sx_ot_pricer_stats(const sx_ot_pricer *p, unsigned long long *passes, unsigned long long *repeats,
+                          int *fused, int *merge_in_kernel);
+
+/* One-shot form: uploads y (and M if M_dev == NULL), prices on the current device, returns count / min /
+ * top-k on the host.  Creates and destroys an sx_ot_pricer inside: for a single pass only -- a
+ * column-generation loop holds an sx_ot_pricer.
  *   M_h: host S x D cost matrix (row-major, contiguous) or NULL when M_dev is given.
- *   M_dev: device-resident copy from a previous call (managers upload M once), or NULL.
+ *   M_dev: device-resident copy (leading dimension D), or NULL.
  */
 SX_API int    sx_price_dense_ot_h(const double *M_h, const double *M_dev, int64_t S, int64_t D,
                            const double *y_h, double tol, int64_t K,

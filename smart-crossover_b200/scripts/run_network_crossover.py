@@ -48,6 +48,9 @@ def main(problem: str, folder: str, test_object: str = "crossover", solver: str 
     if problem in ("mcf", "goto"):
         for mcf in load_min_cost_flow_instances(folder):
             bar = solve_mcf(mcf, method="barrier", solver=solver, settings=SolverSettings(crossover="off"))
+            if bar.status != "OPTIMAL" or bar.x_bar is None:
+                print(f"{mcf.name}: barrier run ended with status {bar.status}; skipped")
+                continue
             out = network_crossover(x=bar.x_bar, mcf=mcf, method="cnet_mcf", solver=solver,
                                     solver_settings=SolverSettings(presolve="on"))
             results[mcf.name] = {"cnet": (out.runtime, out.iter_count), "obj": out.obj_val}
@@ -58,8 +61,11 @@ def main(problem: str, folder: str, test_object: str = "crossover", solver: str 
                 x = sinkhorn(ot.s, ot.d, ot.M, reg=10, numItermax=1000).flatten()
                 warm = datetime.now() - start
             else:
-                x = solve_ot(ot, method="barrier", solver=solver, settings=SolverSettings(crossover="off")).x_bar
-                warm = None
+                bar = solve_ot(ot, method="barrier", solver=solver, settings=SolverSettings(crossover="off"))
+                if bar.status != "OPTIMAL" or bar.x_bar is None:
+                    print(f"{ot.name}: barrier run ended with status {bar.status}; skipped")
+                    continue
+                x, warm = bar.x_bar, None
             tnet = network_crossover(x=x, ot=ot, method="tnet", solver=solver, solver_settings=SolverSettings(presolve="on"))
             cnet = network_crossover(x=x, ot=ot, method="cnet_ot", solver=solver, solver_settings=SolverSettings(presolve="on"))
             results[ot.name] = {"sinkhorn": warm, "tnet": (tnet.runtime, tnet.iter_count),

@@ -107,6 +107,11 @@ SIGNATURES = {
     "sx_sinkhorn_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_sinkhorn_ot": (_int, [_p, _i64, _i64, _i64, _p, _p, _dbl, _i64, _dbl, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sx_price_dense_ot_h": (_int, [_p, _p, _i64, _i64, _p, _dbl, _i64, _p, _p, _p, _p, _p]),
+    "sx_ot_pricer_create": (_int, [_int, _p, _p, _i64, _i64, _i64, _i64, _dbl, _p]),
+    "sx_ot_pricer_destroy": (_int, [_p]),
+    "sx_ot_pricer_info": (_int, [_p, _int, _p, _p, _p]),
+    "sx_ot_pricer_price_h": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "sx_ot_pricer_stats": (_int, [_p, _p, _p, _p, _p]),
     "sx_push_tree_h": (_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _p, _p]),
 }
 

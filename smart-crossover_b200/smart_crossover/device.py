@@ -410,3 +410,123 @@ def topk_merge(blocks_rc: torch.Tensor, blocks_id: torch.Tensor, headers: torch.
     if headers is not None:
         return out_rc, out_id, out_n, summary
     return out_rc, out_id, out_n
+
+
+# ---- persistent, row-sharded pricer behind the managers (sx_ot_pricer) --------------------------------
+MIN_ARCS_PER_DEVICE = 1 << 25      # below ~3e7 arcs (270 MB) per GPU another device only adds latency
+
+
+def pricing_devices(n_arcs: int, S: int) -> list:
+    """Devices a dense OT problem of n_arcs is priced on: `SX_DEVICES` ("all", a count or a comma list) or
+    as many visible GPUs as give each at least MIN_ARCS_PER_DEVICE arcs, starting at the current device."""
+    import os
+    _require_cuda()
+    n_vis, cur = torch.cuda.device_count(), torch.cuda.current_device()
+    spec = os.environ.get("SX_DEVICES", "").strip()
+    if spec and spec != "all" and "," in spec:
+        devs = [int(v) for v in spec.split(",")]
+    else:
+        want = n_vis if spec == "all" else (int(spec) if spec else max(1, n_arcs // MIN_ARCS_PER_DEVICE))
+        devs = [(cur + i) % n_vis for i in range(max(1, min(want, n_vis)))]
+    devs = devs[:max(1, min(len(devs), S))]
+    if len(devs) > 1 and not all(torch.cuda.can_device_access_peer(a, b) for a in devs for b in devs if a != b):
+        devs = devs[:1]
+    return devs
+
+
+class CostSlabs:
+    """Row shards of a dense S x D cost matrix, one per device, resident for the life of the problem (as the
+    reference keeps `ot.M` in its manager).  Leading dimension rounded up to even (TMA path)."""
+
+    def __init__(self, S: int, D: int, devices):
+        _require_cuda()
+        self.S, self.D, self.devices = int(S), int(D), list(devices)
+        self.ld = self.D + (self.D & 1)
+        G = len(self.devices)
+        self.row0 = [self.S * g // G for g in range(G)]
+        self.rows = [self.S * (g + 1) // G - self.row0[g] for g in range(G)]
+        self.t = [torch.empty(self.rows[g], self.ld, dtype=torch.float64, device=torch.device("cuda", d))
+                  for g, d in enumerate(self.devices)]
+
+    def view(self, g: int) -> torch.Tensor:
+        """(rows_g, D) view of shard g."""
+        return self.t[g][:, :self.D]
+
+    @classmethod
+    def from_host(cls, M, devices, border=None):
+        """Upload a host matrix.  `border` = (bigM, corner): the device matrix is the (S+1) x (D+1) big-M
+        extension of M (net_manager.py:390-393) -- last row / column = bigM, corner = `corner` -- built on the
+        device, so the extended matrix never exists on the host."""
+        M = np.asarray(M, dtype=np.float64)
+        S0, D0 = M.shape
+        S, D = (S0 + 1, D0 + 1) if border is not None else (S0, D0)
+        self = cls(S, D, devices)
+        for g in range(len(self.devices)):
+            r0, r1 = self.row0[g], self.row0[g] + self.rows[g]
+            h1 = min(r1, S0)
+            if h1 > r0:
+                self.t[g][:h1 - r0, :D0].copy_(torch.from_numpy(np.ascontiguousarray(M[r0:h1])))
+            if border is not None:
+                self.t[g][:, D0] = float(border[0])
+                if r1 == S:                                    # the artificial source is the last row
+                    self.t[g][-1, :D0] = float(border[0])
+                    self.t[g][-1, D0] = float(border[1])
+        self.sync()
+        return self
+
+    def sync(self):
+        for d in self.devices:
+            torch.cuda.synchronize(d)
+
+
+class OTPricer:
+    """`sx_ot_pricer`: persistent pricer of one dense OT problem over the devices of its `CostSlabs`.
+    `price(y_src, y_dst)` takes HOST vectors (the LP solver's duals) and returns a PriceResult; nothing is
+    allocated per pass.  One kernel per GPU and pass (price + select + NVLink push + merge)."""
+
+    def __init__(self, slabs: CostSlabs, K: int, tol: float = TOL_RC):
+        _require_cuda()
+        self.slabs, self.K = slabs, int(K)
+        G = len(slabs.devices)
+        devs = (ctypes.c_int * G)(*slabs.devices)
+        ptrs = (ctypes.c_void_p * G)(*[t.data_ptr() for t in slabs.t])
+        self._h = ctypes.c_void_p()
+        slabs.sync()
+        check(lib.sx_ot_pricer_create(G, devs, ptrs, slabs.ld, slabs.S, slabs.D, self.K, float(tol),
+                                      ctypes.byref(self._h)), "sx_ot_pricer_create")
+        Kp = max(self.K, 1)
+        self._rc = np.empty(Kp, dtype=np.float64)
+        self._id = np.empty(Kp, dtype=np.int64)
+        self._cnt, self._min = ctypes.c_ulonglong(0), ctypes.c_double(0.0)
+        self._n, self._status = ctypes.c_int64(0), ctypes.c_ulonglong(0)
+
+    def price(self, y_src: np.ndarray, y_dst: np.ndarray) -> PriceResult:
+        y_src = np.ascontiguousarray(y_src, dtype=np.float64)
+        y_dst = np.ascontiguousarray(y_dst, dtype=np.float64)
+        if y_src.size != self.slabs.S or y_dst.size != self.slabs.D:
+            raise ValueError("dual vectors do not match the cost matrix")
+        check(lib.sx_ot_pricer_price_h(self._h, y_src.ctypes.data, y_dst.ctypes.data, ctypes.byref(self._cnt),
+                                       ctypes.byref(self._min), self._rc.ctypes.data, self._id.ctypes.data,
+                                       ctypes.byref(self._n), ctypes.byref(self._status)), "sx_ot_pricer_price_h")
+        k = int(self._n.value) if self.K > 0 else 0
+        return PriceResult(int(self._cnt.value), float(self._min.value), self._id[:k].copy(), self._rc[:k].copy(),
+                           status=int(self._status.value))
+
+    def stats(self) -> dict:
+        a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        f, m = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib.sx_ot_pricer_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(f), ctypes.byref(m)),
+              "sx_ot_pricer_stats")
+        return {"passes": a.value, "repeated_passes": b.value, "fused": bool(f.value), "merge_in_kernel": bool(m.value),
+                "devices": list(self.slabs.devices)}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.sx_ot_pricer_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

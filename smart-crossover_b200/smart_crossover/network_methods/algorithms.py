@@ -15,6 +15,7 @@ from smart_crossover.network_methods.tree_BI import tree_basis_identify
 from smart_crossover.output import Output
 from smart_crossover.parameters import COLUMN_GENERATION_RATIO
 from smart_crossover.solver_caller.caller import SolverSettings
+from smart_crossover.solver_caller.solving import generate_solver_caller
 from smart_crossover.timer import Timer
 
 _METHODS = ("tnet", "cnet_ot", "cnet_mcf")
@@ -36,6 +37,11 @@ def network_crossover(x: np.ndarray,
     print(f"*** Running {method} algorithm. ***")
     if method not in _METHODS:
         raise ValueError("Invalid method specified. Choose from 'tnet', 'cnet_ot', or 'cnet_mcf'.")
+    # fail before any GPU work: an unavailable solver backend (the default "GRB" is kept from the reference;
+    # only "HGS" ships here) or a barrier run that returned no interior point
+    generate_solver_caller(solver, solver_settings)
+    if x is None:
+        raise ValueError("x is None: the interior-point run returned no solution (check its status)")
     timer = Timer()
     timer.start_timer()
     push_iter = 0

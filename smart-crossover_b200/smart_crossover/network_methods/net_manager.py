@@ -58,17 +58,97 @@ def _dev():
     return device
 
 
-def _native_status_nan() -> int:
-    from smart_crossover import _native
-    return _native.SX_STATUS_NAN_RC
-
-
 def _cuda(a, dtype=None):
     import torch
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
     return t.cuda()
+
+
+class BigMExtendedCost:
+    """(S+1) x (D+1) cost matrix of the big-M extension (reference `net_manager.py:390-393`: last column and
+    last row = bigM, corner = 0) as a VIEW of the original matrix: nothing is copied until somebody asks for
+    the dense array (`np.asarray`), which the managers never do -- the sub-problem takes single entries
+    (`take_flat`) and the device builds its own extended copy (`CostSlabs.from_host(border=...)`)."""
+
+    ndim = 2
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, base: np.ndarray, bigM: float) -> None:
+        self.base = np.asarray(base)
+        self.bigM = float(bigM)
+        self.shape = (self.base.shape[0] + 1, self.base.shape[1] + 1)
+        self.size = self.shape[0] * self.shape[1]
+
+    def take_flat(self, ids: np.ndarray) -> np.ndarray:
+        """Entries at row-major indices `ids` of the extended matrix."""
+        S, D = self.base.shape
+        i, j = np.divmod(np.asarray(ids, dtype=np.int64), D + 1)
+        inner = (i < S) & (j < D)
+        out = np.full(i.shape, self.bigM)
+        out[inner] = self.base[i[inner], j[inner]]
+        out[(i == S) & (j == D)] = 0.0
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        S, D = self.base.shape
+        M = np.full(self.shape, self.bigM)
+        M[:S, :D] = self.base
+        M[S, D] = 0.0
+        return M if dtype is None else M.astype(dtype, copy=False)
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) == 2 and all(isinstance(k, (int, np.integer)) for k in key):
+            i, j = (int(k) % n for k, n in zip(key, self.shape))
+            return float(self.take_flat(np.array([i * self.shape[1] + j]))[0])
+        return np.asarray(self)[key]
+
+    def ravel(self):
+        return np.asarray(self).ravel()
+
+    flatten = ravel
+
+    def max(self):
+        return max(float(self.base.max()), self.bigM, 0.0)
+
+
+class DeviceResidentCost:
+    """Stand-in for `ot.M` when the cost matrix only exists on the device(s) (`OTManager.from_device_cost`:
+    a 60 000 x 60 000 matrix generated shard by shard in HBM has no host copy).  Knows its shape; any attempt
+    to read it on the host raises."""
+
+    ndim = 2
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, slabs) -> None:
+        self.slabs = slabs
+        self.shape = (slabs.S, slabs.D)
+        self.size = slabs.S * slabs.D
+
+    def take_flat(self, ids: np.ndarray) -> np.ndarray:
+        """Entries at row-major arc ids, gathered from the device shards (the restricted master's costs)."""
+        import torch
+        ids = np.asarray(ids, dtype=np.int64)
+        out = np.empty(ids.size)
+        i, j = np.divmod(ids, self.slabs.D)
+        for g, d in enumerate(self.slabs.devices):
+            r0, rows = self.slabs.row0[g], self.slabs.rows[g]
+            m = (i >= r0) & (i < r0 + rows)
+            if m.any():
+                ii = torch.from_numpy(i[m] - r0).to(torch.device("cuda", d))
+                jj = torch.from_numpy(j[m]).to(torch.device("cuda", d))
+                out[m] = self.slabs.t[g][ii, jj].cpu().numpy()
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        raise TypeError("this cost matrix is device resident; it has no host copy")
+
+
+def _take_flat(M, ids: np.ndarray) -> np.ndarray:
+    if isinstance(M, DeviceResidentCost):
+        return M.take_flat(ids)
+    return M.take_flat(ids) if isinstance(M, BigMExtendedCost) else np.asarray(M).ravel()[ids]
 
 
 class _SortedFlows:
@@ -92,17 +172,21 @@ class _SortedFlows:
         return _dev().kruskal_order_head(self.sorted_key, self.order, T)
 
     def matches(self, weights: np.ndarray) -> bool:
-        return weights is self.scores_np or (weights.shape == self.scores_np.shape
-                                             and np.array_equal(weights, self.scores_np, equal_nan=True))
+        """Whether `weights` are the scores this sort was made from: the very array `get_sorted_flows`
+        returned, or a view of it.  (No O(n) host comparison: at 3.6e9 arcs that would cost more than the
+        tree build; a caller that passes a modified copy simply gets a fresh sort.)"""
+        return weights is self.scores_np or (isinstance(weights, np.ndarray) and weights.size == self.scores_np.size
+                                             and np.shares_memory(weights, self.scores_np))
 
 
 # =================================================================================================
 class OTManager:
     """Optimal-transport manager (reference `net_manager.py:322-509`).
 
-    After `extend_by_bigM` the host-side `ot` is the (S+1) x (D+1) extended problem exactly as in
-    the reference, but the device keeps the original S x D cost matrix: the S + D + 1 artificial
-    arcs are priced on the host from their closed form (bigM on the border, 0 in the corner).
+    After `extend_by_bigM` the host-side `ot` is the (S+1) x (D+1) extended problem as in the reference,
+    but its cost matrix is a view (`BigMExtendedCost`), not a copy; the device builds the extended matrix
+    itself from the original block, so the S + D + 1 artificial arcs are priced by the same kernel as
+    everything else and arc ids come back in the extended numbering.
     """
 
     def __init__(self, ot: OptTransport) -> None:
@@ -111,11 +195,21 @@ class OTManager:
         self.n = ot.s.size * ot.d.size
         self.mask_sub_ot = np.zeros(self.n, dtype=bool)
         self.artificial_vars = np.array([])
-        self._S0, self._D0 = ot.s.size, ot.d.size       # shape of the device-resident block
-        self._M_dev = None
+        self._slabs = None              # device-resident row shards of the CURRENT cost matrix (built on first pricing)
+        self._pricers = {}              # K -> persistent OTPricer over those shards
         self._mcf = None
         self._sorted = None
         self._bigM = None
+
+    @classmethod
+    def from_device_cost(cls, s: np.ndarray, d: np.ndarray, slabs) -> "OTManager":
+        """Manager over a cost matrix that already sits on the device(s) as `device.CostSlabs` (generated or
+        uploaded there by the caller).  Scoring, the tree build, pricing and the restricted master work as
+        usual; `to_MCF` / `get_mcf` / `extend_by_bigM` need the host matrix and are not available."""
+        mgr = cls(OptTransport(np.asarray(s, dtype=np.float64), np.asarray(d, dtype=np.float64),
+                               DeviceResidentCost(slabs)))
+        mgr._slabs = slabs
+        return mgr
 
     # ---- lazily built host / device state ---------------------------------------------------------
     @property
@@ -132,11 +226,36 @@ class OTManager:
     def get_mcf(self) -> None:
         self._mcf = self.ot.to_MCF()
 
-    def _device_cost(self):
-        if self._M_dev is None:
-            M = np.asarray(self.ot.M, dtype=np.float64)
-            self._M_dev = _cuda(M[:self._S0, :self._D0])
-        return self._M_dev
+    def _device_slabs(self):
+        """The cost matrix on the device(s), uploaded once per problem: row-sharded over the GPUs
+        `device.pricing_devices` picks (one below ~3e7 arcs per extra GPU).  After `extend_by_bigM` the
+        device matrix is the extended one, built on the device from the original block."""
+        if self._slabs is None:
+            dev = _dev()
+            S, D = self.ot.s.size, self.ot.d.size
+            devices = dev.pricing_devices(S * D, S)
+            if isinstance(self.ot.M, BigMExtendedCost):
+                self._slabs = dev.CostSlabs.from_host(self.ot.M.base, devices, border=(self.ot.M.bigM, 0.0))
+            else:
+                self._slabs = dev.CostSlabs.from_host(self.ot.M, devices)
+        return self._slabs
+
+    def _pricer(self, K: int):
+        """One persistent pricer per top-K size (buffers, streams and worker threads live as long as the
+        manager: a column-generation round allocates nothing)."""
+        pr = self._pricers.get(K)
+        if pr is None:
+            pr = self._pricers[K] = _dev().OTPricer(self._device_slabs(), K, tol=TOLERANCE_FOR_REDUCED_COSTS)
+        return pr
+
+    def _drop_device_state(self):
+        for pr in self._pricers.values():
+            pr.close()
+        self._pricers, self._slabs = {}, None
+
+    def pricing_devices(self):
+        """Devices the cost matrix is sharded over (diagnostics)."""
+        return list(self._device_slabs().devices)
 
     def get_X(self, x: np.ndarray) -> np.ndarray:
         return x.reshape((self.ot.s.size, self.ot.d.size))
@@ -157,18 +276,18 @@ class OTManager:
     def extend_by_bigM(self, bigM: float) -> None:
         """Artificial source and sink joined to everything at cost bigM (reference :381-400)."""
         S, D = self.ot.s.size, self.ot.d.size
-        M_ext = np.full((S + 1, D + 1), float(bigM))
-        M_ext[:S, :D] = self.ot.M
-        M_ext[S, D] = 0.0
         mask = np.zeros((S + 1, D + 1), dtype=np.bool_)
         mask[S, :] = True
         mask[:, D] = True
         self.mask_sub_ot = mask
-        self.artificial_vars = np.where(mask.ravel())[0]
-        self._device_cost()                                   # keep the S x D block resident
+        # row-major ids of the border, ascending (= np.where(mask.ravel())[0] without scanning n booleans)
+        self.artificial_vars = np.concatenate([np.arange(S, dtype=np.int64) * (D + 1) + D,
+                                               S * (D + 1) + np.arange(D + 1, dtype=np.int64)])
         self._bigM = float(bigM)
+        # `ot.M` becomes a view of the extended matrix: neither the host nor the PCIe link ever sees a copy
         self.ot = OptTransport(np.append(self.ot.s, np.sum(self.ot.d)),
-                               np.append(self.ot.d, np.sum(self.ot.s)), M_ext)
+                               np.append(self.ot.d, np.sum(self.ot.s)), BigMExtendedCost(self.ot.M, bigM))
+        self._drop_device_state()
         self._mcf = None
         self._sorted = None
 
@@ -211,7 +330,7 @@ class OTManager:
         vals[1::2] = 1.0
         A = sp.csc_matrix((vals, rows, np.arange(0, 2 * k + 1, 2)), shape=(S + D, k))
         return MinCostFlow(A=A, b=np.hstack([-self.ot.s, self.ot.d]),
-                           c=np.asarray(self.ot.M).ravel()[ids], u=np.full(k, np.inf))
+                           c=_take_flat(self.ot.M, ids), u=np.full(k, np.inf))
 
     def solve_subproblem(self, solver: str, solver_settings: SolverSettings) -> Output:
         method = "network_simplex" if solver == "CPL" else "default"
@@ -231,55 +350,31 @@ class OTManager:
         self.basis = Basis(vbasis, np.concatenate([-np.ones(self.m + 1), np.zeros(1)]))
 
     # ---- K4: pricing ---------------------------------------------------------------------------------------------
-    def _split_duals(self, y: np.ndarray):
-        """(source duals, sink duals) of the device block inside the current node numbering."""
-        y = np.asarray(y, dtype=np.float64)
-        S_cur = self.ot.s.size
-        return y[:self._S0], y[S_cur:S_cur + self._D0]
-
-    def _border_reduced_costs(self, y: np.ndarray):
-        """Reduced costs of the artificial arcs (last row and last column of the extended matrix)."""
-        S, D = self._S0, self._D0
-        y = np.asarray(y, dtype=np.float64)
-        row = np.append(np.full(D, self._bigM), 0.0) - (y[S + 1:S + D + 2] - y[S])      # arcs (S, j), j = 0..D
-        col = np.full(S, self._bigM) - (y[S + 1 + D] - y[:S])                            # arcs (i, D), i < S
-        return row, col
-
     def price(self, y: np.ndarray, K: int = 0, want_rc: bool = False):
-        """One pricing pass: violator count, min reduced cost and the K most violating arcs
-        (ids in the current arc numbering).  north_star extension; see `device.PriceResult`."""
-        dev = _dev()
-        import torch
-        M = self._device_cost()
-        u, v = self._split_duals(y)
-        y_dev = _cuda(np.concatenate([u, v]))
-        res = dev.price_dense_ot(M, y_dev, K=K, tol=TOLERANCE_FOR_REDUCED_COSTS, want_rc=want_rc)
-        if self._bigM is None:
-            return res
-        # extended problem: re-index the block's arcs into (S+1) x (D+1) and add the border arcs
-        S, D = self._S0, self._D0
-        row, col = self._border_reduced_costs(y)
-        ids = res.topk_id // D * (D + 1) + res.topk_id % D
-        b_ids = np.concatenate([S * (D + 1) + np.arange(D + 1), np.arange(S) * (D + 1) + D])
-        b_rc = np.concatenate([row, col])
-        viol = b_rc < -TOLERANCE_FOR_REDUCED_COSTS
-        all_ids = np.concatenate([ids, b_ids[viol]])
-        all_rc = np.concatenate([res.topk_rc, b_rc[viol]])
-        o = np.lexsort((all_ids, all_rc))[:K] if K > 0 else np.zeros(0, dtype=np.int64)
-        status = res.status | (_native_status_nan() if np.isnan(b_rc).any() else 0)
-        out = dev.PriceResult(res.n_violating + int(viol.sum()), float(min(res.min_rc, np.nanmin(b_rc))),
-                              all_ids[o].astype(np.int64), all_rc[o], status=status)
+        """One pricing pass over every arc of the current OT (after `extend_by_bigM`: the extended one):
+        violator count, min reduced cost and the K most violating arcs (north_star extension; see
+        `device.PriceResult`).  Goes through the manager's persistent, row-sharded pricer: the duals are the
+        only upload.  `want_rc` also returns the full reduced-cost vector (host), shard by shard."""
+        y = np.asarray(y, dtype=np.float64)
+        S, D = self.ot.s.size, self.ot.d.size
+        res = self._pricer(int(K)).price(y[:S], y[S:S + D])
         if want_rc:
-            full = np.empty((S + 1, D + 1))
-            full[:S, :D] = res.rc.cpu().numpy().reshape(S, D)
-            full[S, :] = row
-            full[:S, D] = col
-            out.rc = torch.from_numpy(full.ravel())
-        return out
+            import torch
+            dev = _dev()
+            slabs = self._device_slabs()
+            rc = np.empty((S, D))
+            for g, d in enumerate(slabs.devices):
+                with torch.cuda.device(d):
+                    r0, rows = slabs.row0[g], slabs.rows[g]
+                    y_g = torch.from_numpy(np.concatenate([y[r0:r0 + rows], y[S:S + D]])).cuda()
+                    part = dev.price_dense_ot(slabs.view(g), y_g, K=0, tol=TOLERANCE_FOR_REDUCED_COSTS, want_rc=True)
+                    rc[r0:r0 + rows] = part.rc.cpu().numpy().reshape(rows, D)
+            res.rc = rc.ravel()
+        return res
 
     def get_reduced_cost_for_original_OT(self, y: np.ndarray) -> np.ndarray:
         """rc = c - A^T y over every arc of the current OT (reference :474-483)."""
-        return self.price(y, K=0, want_rc=True).rc.cpu().numpy()
+        return self.price(y, K=0, want_rc=True).rc
 
     def check_optimality_condition(self, x: np.ndarray, y: np.ndarray) -> bool:
         """All reduced costs >= -1e-6 and no flow left on artificial arcs (reference :485-497)."""
@@ -301,6 +396,8 @@ class MCFManagerStd:
         self.c_rescaling_factor = None
         self._arcs_dev = None
         self._sorted = None
+        self._arc_pricers = {}          # K -> reusable pricing buffers
+        self._vb_src, self._vb_dev = None, None
 
     # ---- arc list of the current incidence matrix (host scan once per matrix, then device resident) ------
     @staticmethod
@@ -420,13 +517,24 @@ class MCFManagerStd:
 
     # ---- K4 ------------------------------------------------------------------------------------------------------
     def price(self, y: np.ndarray, K: int = 0, want_rc: bool = False):
-        """Arc-list pricing: rc_k = c_k - (y_tail - y_head), negated for arcs at their upper bound."""
+        """Arc-list pricing: rc_k = c_k - (y_tail - y_head), negated for arcs at their upper bound.
+        The arc list, the costs, the basis statuses and the pricing buffers stay on the device between
+        calls: a pass uploads the duals, and the statuses only when `set_basis` changed them."""
         import torch
         dev = _dev()
         arcs = self._device_arcs()
-        vb = _cuda(np.asarray(self.basis.vbasis).astype(np.int8)) if getattr(self, "basis", None) is not None else None
+        vb = None
+        basis = getattr(self, "basis", None)
+        if basis is not None:
+            if self._vb_src is not basis.vbasis:
+                self._vb_dev = _cuda(np.asarray(basis.vbasis).astype(np.int8))
+                self._vb_src = basis.vbasis
+            vb = self._vb_dev
+        pr = self._arc_pricers.get(K)
+        if pr is None:
+            pr = self._arc_pricers[K] = dev.Pricer(arcs["c"].device, K, fused=False)
         return dev.price_arcs(arcs["c"], arcs["tail"], arcs["head"], _cuda(np.asarray(y, dtype=np.float64)), vbasis=vb,
-                              K=K, tol=TOLERANCE_FOR_REDUCED_COSTS, want_rc=want_rc)
+                              K=K, tol=TOLERANCE_FOR_REDUCED_COSTS, want_rc=want_rc, pricer=pr)
 
     def get_reduced_cost_for_original_mcf(self, y: np.ndarray) -> np.ndarray:
         """Reference :293-304."""

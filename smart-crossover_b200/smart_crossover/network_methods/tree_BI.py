@@ -26,7 +26,12 @@ def tree_basis_identify(ot_manager: OTManager, flow_weights: np.ndarray) -> Tupl
     """Max-weight spanning tree of the flow weights, pushed to a basic feasible solution.
     Returns the basis (last node's row is the redundant one: cbasis = [-1]*(m-1) + [0]) and the
     number of push iterations.  Reference `tree_BI.py:12-29`."""
-    tree = max_weight_spanning_tree(ot_manager.ot, flow_weights, _sorted=ot_manager._sorted)
+    # The FULL spanning tree goes to the push phase.  `max_weight_spanning_tree` (like the reference,
+    # tree_BI.py:56) drops tree arcs whose weight is exactly zero, after which the reference's square solve
+    # (:74-76) fails; the device already has the complete tree, and a zero-weight tree arc is a legitimate
+    # (degenerate) basic arc.  Identical to the reference whenever the reference succeeds.
+    tree_t, nt = _device_tree(ot_manager.ot, flow_weights, ot_manager._sorted)
+    tree = tree_t[:nt].cpu().numpy()
     vbasis, push_iter = push_tree_to_bfs(ot_manager, tree)
     cbasis = np.concatenate([-np.ones(ot_manager.m - 1), np.array([0])])
     return Basis(vbasis, cbasis), push_iter
@@ -55,10 +60,15 @@ def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlo
     N, n = S + D, S * D
     flow_weights = np.asarray(flow_weights, dtype=np.float64)
     have_sort = _sorted is not None and _sorted.matches(flow_weights)
-    if np.isnan(flow_weights).any():
-        raise ValueError("flow weights contain NaN (a zero marginal?): the spanning tree is undefined")
+    nan_msg = "flow weights contain NaN (a zero marginal?): the spanning tree is undefined"
+    if have_sort:
+        # NaN keys sort last (NumPy order): one device read instead of an O(n) host scan
+        if bool(_sorted.sorted_key[-1:].isnan().item()):
+            raise ValueError(nan_msg)
     if not have_sort and use_prefix_path(n, N):
         w_t = _cuda(flow_weights.ravel())
+        if bool(w_t.isnan().any().item()):
+            raise ValueError(nan_msg)
         head = dev.kruskal_prefix(w_t, PREFIX_FACTOR * N)
         if head is not None:
             tree_t, n_t = dev.kruskal(head, N, S=S, D=D)
@@ -67,6 +77,8 @@ def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlo
         _sorted = _SortedFlows(w_t, flow_weights)
     elif not have_sort:
         _sorted = _SortedFlows(_cuda(flow_weights), flow_weights)
+        if bool(_sorted.sorted_key[-1:].isnan().item()):
+            raise ValueError(nan_msg)
     if n > 4 * PREFIX_FACTOR * N:
         # the sort exists: only its heaviest 16 N arcs are put into Kruskal order first
         head = _sorted.kruskal_order_head(PREFIX_FACTOR * N)

@@ -21,6 +21,7 @@ import scipy.sparse as sp
 import scipy.optimize._highspy._core as _hc
 
 from smart_crossover.output import Basis, Output
+from smart_crossover.solver_caller.caller import SolverCaller
 
 _TO_HIGHS = {0: _hc.HighsBasisStatus.kBasic, -1: _hc.HighsBasisStatus.kLower,
              -2: _hc.HighsBasisStatus.kUpper, -3: _hc.HighsBasisStatus.kZero}
@@ -29,7 +30,7 @@ _FROM_HIGHS = {_hc.HighsBasisStatus.kBasic: 0, _hc.HighsBasisStatus.kLower: -1,
                _hc.HighsBasisStatus.kNonbasic: -1}
 
 
-class HgsCaller:
+class HgsCaller(SolverCaller):
     """HiGHS adapter with the method names of the reference's `SolverCaller`."""
 
     solver_name = "HGS"
