@@ -398,6 +398,8 @@ class MCFManagerStd:
         self._sorted = None
         self._arc_pricers = {}          # K -> reusable pricing buffers
         self._vb_src, self._vb_dev = None, None
+        self._host_arcs_of, self._host_tail, self._host_head = None, None, None
+        self._freed = None              # bool over the arcs: opened by add_free_variables so far
 
     # ---- arc list of the current incidence matrix (host scan once per matrix, then device resident) ------
     @staticmethod
@@ -413,12 +415,20 @@ class MCFManagerStd:
         head[cols[A.data < 0]] = A.indices[A.data < 0]
         return tail, head
 
-    def _device_arcs(self):
-        import torch
-        if self._arcs_dev is None or self._arcs_dev["A"] is not self.mcf.A:
+    def _host_arcs(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(tail, head) of every column of the current `mcf.A`: one host scan per matrix (the big-M extension
+        appends its arcs without a scan)."""
+        if self._host_arcs_of is not self.mcf.A:
             tail, head = self._endpoints(self.mcf.A)
             if (tail < 0).any() or (head < 0).any():
                 raise ValueError("every column of A must have one +1 and one -1 entry")
+            self._host_arcs_of, self._host_tail, self._host_head = self.mcf.A, tail, head
+        return self._host_tail, self._host_head
+
+    def _device_arcs(self):
+        import torch
+        if self._arcs_dev is None or self._arcs_dev["A"] is not self.mcf.A:
+            tail, head = self._host_arcs()
             self._arcs_dev = {"A": self.mcf.A, "tail": _cuda(tail, torch.int32), "head": _cuda(head, torch.int32),
                               "c": None, "c_src": None}
         d = self._arcs_dev
@@ -454,12 +464,18 @@ class MCFManagerStd:
         b_true = self.mcf.b - self.mcf.A.multiply(at_up) @ (self.mcf.u * at_up)
         sign = np.sign(b_true)
         sign[sign == 0] = 1
+        tail, head = self._host_arcs()
         A_ext = sp.vstack((sp.hstack((self.mcf.A, sp.diags(sign))),
                            sp.csr_matrix(np.concatenate([np.zeros(self.n), -sign]))))
         # the reference sizes the artificial capacities with n instead of m (:148, harmless); m is used here
         self.mcf = MinCostFlow(A_ext, np.append(self.mcf.b, 0.0),
                                np.concatenate([self.mcf.c, bigM * np.ones(self.m)]),
                                np.concatenate([self.mcf.u, np.inf * np.ones(self.m)]))
+        # end points of the artificial arcs are known: node i -> artificial node m where sign = +1, else m -> i
+        node = np.arange(self.m, dtype=np.int64)
+        self._host_arcs_of = self.mcf.A
+        self._host_tail = np.concatenate([tail, np.where(sign > 0, node, self.m)])
+        self._host_head = np.concatenate([head, np.where(sign > 0, self.m, node)])
         new_ids = np.arange(self.n, self.n + self.m, dtype=np.int64)
         self.artificial_vars = new_ids.astype(int)
         self.var_info["non_fix"] = np.append(self.var_info["non_fix"], new_ids)
@@ -473,17 +489,30 @@ class MCFManagerStd:
         return obj_val * self.c_rescaling_factor
 
     def fix_variables(self, ind_fix_to_low: np.ndarray, ind_fix_to_up: np.ndarray) -> None:
-        everything = np.arange(len(self.mcf.c))
+        """Reference :224-234; `non_fix` / `fix` are the sorted complements (what `np.setdiff1d` returns there),
+        taken with a mask instead of two sorts of n ids."""
+        n = len(self.mcf.c)
+        fixed = np.zeros(n, dtype=bool)
+        fixed[np.asarray(ind_fix_to_low, dtype=np.int64)] = True
+        fixed[np.asarray(ind_fix_to_up, dtype=np.int64)] = True
         self.var_info["fix_low"] = ind_fix_to_low
         self.var_info["fix_up"] = ind_fix_to_up
-        self.var_info["non_fix"] = np.setdiff1d(everything, np.append(ind_fix_to_low, ind_fix_to_up))
-        self.var_info["fix"] = np.setdiff1d(everything, self.var_info["non_fix"])
+        self.var_info["non_fix"] = np.flatnonzero(~fixed)
+        self.var_info["fix"] = np.flatnonzero(fixed)
+        self._freed = None
 
     def add_free_variables(self, ind_free_new: np.ndarray) -> None:
-        """Append the new columns in queue order and drop them from the fixed sets (reference :236-245)."""
+        """Append the new columns in queue order and drop them from the fixed sets (reference :236-245).  The
+        reference does three `np.setdiff1d` (sorts of the remaining fixed ids) per round; the fixed sets are
+        sorted and duplicate free, so a mask of the freed arcs gives the same arrays in O(|set|)."""
+        new = np.asarray(ind_free_new, dtype=np.int64)
         self.var_info["non_fix"] = np.append(self.var_info["non_fix"], ind_free_new)
+        if self._freed is None or self._freed.size != self.mcf.c.size:
+            self._freed = np.zeros(self.mcf.c.size, dtype=bool)
+        self._freed[new] = True
         for key in ("fix", "fix_low", "fix_up"):
-            self.var_info[key] = np.setdiff1d(self.var_info[key], ind_free_new)
+            arr = np.asarray(self.var_info[key])
+            self.var_info[key] = arr[~self._freed[arr]] if arr.size else arr
 
     def set_initial_basis(self) -> None:
         vbasis = np.concatenate((-np.ones(self.n), np.zeros(self.m)))
@@ -494,9 +523,30 @@ class MCFManagerStd:
         self.basis = basis
 
     def update_subproblem(self) -> None:
-        nf, up = self.var_info["non_fix"], self.var_info["fix_up"]
-        self.mcf_sub = MinCostFlow(A=self.mcf.A[:, nf], b=self.mcf.b - self.mcf.A[:, up] @ self.mcf.u[up],
-                                   c=self.mcf.c[nf], u=self.mcf.u[nf])
+        """Restricted master over the open columns, in `non_fix` order (reference :202-209), assembled from
+        the arcs' end points instead of slicing the full incidence matrix: column k has +1 at tail_k and -1
+        at head_k (rows ascending inside a column, the canonical form `A[:, non_fix]` has too), and the flow
+        of the arcs fixed at their upper bound is moved to the right-hand side by one signed accumulation in
+        ascending arc order -- the order SciPy's `A[:, up] @ u[up]` adds in, so b is bit-identical."""
+        tail, head = self._host_arcs()
+        nf = np.asarray(self.var_info["non_fix"], dtype=np.int64)
+        up = np.asarray(self.var_info["fix_up"], dtype=np.int64)
+        N, k = self.mcf.b.size, nf.size
+        t, h = tail[nf], head[nf]
+        rows = np.empty(2 * k, dtype=np.int64)
+        vals = np.empty(2 * k)
+        first = t < h
+        rows[0::2] = np.where(first, t, h)
+        rows[1::2] = np.where(first, h, t)
+        vals[0::2] = np.where(first, 1.0, -1.0)
+        vals[1::2] = -vals[0::2]
+        A_sub = sp.csc_matrix((vals, rows, np.arange(0, 2 * k + 1, 2, dtype=np.int64)), shape=(N, k))
+        idx = np.empty(2 * up.size, dtype=np.int64)
+        w = np.empty(2 * up.size)
+        idx[0::2], idx[1::2] = tail[up], head[up]
+        w[0::2], w[1::2] = self.mcf.u[up], -self.mcf.u[up]
+        moved = np.bincount(idx, weights=w, minlength=N) if up.size else np.zeros(N)
+        self.mcf_sub = MinCostFlow(A=A_sub, b=self.mcf.b - moved, c=self.mcf.c[nf], u=self.mcf.u[nf])
 
     def solve_subproblem(self, solver: str, solver_settings: SolverSettings) -> Output:
         method = "network_simplex" if solver == "CPL" else "default"

@@ -119,3 +119,63 @@ def test_mcf_manager_calls_match_the_reference(name):
     mgr.set_basis(Basis(fx.out["vbasis"], -np.ones(N)))
     assert mgr.get_reduced_cost_for_original_mcf(fx.out["y"]).tobytes() == fx.out["rc"].tobytes()
     assert mgr.check_optimality_condition(x, fx.out["y"]) == bool(fx.out["optimal"])
+
+
+# ---- BASELINE.json configs[1] (784 x 784) and the 20 000-node MCF: goldens from make_golden_e2e.py ---------
+def test_c2_device_tree_flows_through_the_push_phase():
+    """784 x 784: tree flows computed on the DEVICE (Euler tour, double-double subtree sums) feed the native
+    push loop; the reference gets them from SuperLU (tree_BI.py:74-76).  A rounding difference that flips a
+    `< 0` or `== 0` test would change the push count (934) or the basis."""
+    from golden_util import c2_inputs
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.net_manager import OTManager
+    from smart_crossover.network_methods.tree_BI import push_tree_to_bfs, tree_basis_identify, tree_flows
+    s, d, M, x = c2_inputs()
+    small = Fixture("ot_c2_784_small")
+    ot = OptTransport(s, d, M)
+    mgr = OTManager(ot)
+    tree = small.out["tree"]
+    vbasis, push_iter = push_tree_to_bfs(mgr, tree)                 # device flows -> native push
+    assert push_iter == int(small.out["push_iter"]) == 934
+    assert np.array_equal(np.flatnonzero(vbasis == 0), small.out["basic_tree"])
+    # the same through the public entry: scores -> device tree -> flows -> push
+    queue, scores = mgr.get_sorted_flows(x)
+    basis, it = tree_basis_identify(mgr, scores)
+    assert it == 934 and np.array_equal(np.flatnonzero(basis.vbasis == 0), small.out["basic_tree"])
+    flows = tree_flows(ot, tree)
+    assert flows.shape == (784 + 784 - 1,) and (flows < 0).sum() > 0      # the push had something to do
+
+
+@pytest.mark.parametrize("method", ["tnet", "cnet_ot"])
+def test_network_crossover_c2_784(method):
+    from golden_util import c2_inputs
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.algorithms import network_crossover
+    s, d, M, x = c2_inputs()
+    fx = Fixture("e2e_c2_784")
+    out = network_crossover(x=x.copy(), ot=OptTransport(s.copy(), d.copy(), M.copy()), method=method, solver="HGS",
+                            solver_settings=_quiet())
+    ref = float(fx.out[f"{method}_obj"])
+    assert abs(out.obj_val - ref) <= 1e-9 * abs(ref)
+    assert abs(out.obj_val - float(fx.out["direct_obj"])) <= 1e-9 * abs(ref)
+    # same restricted masters, same warm-start bases, same solver => same simplex path as the reference run
+    assert out.iter_count == int(fx.out[f"{method}_iters"])
+    assert np.array_equal(np.flatnonzero(out.basis.vbasis == 0), fx.out[f"{method}_basic"])
+
+
+def test_network_crossover_mcf_20k():
+    """cnet_mcf on 20 000 nodes / 200 000 arcs (the reference needs 87 s here, nearly all of it in HiGHS)."""
+    from golden_util import mcf_mid_inputs
+    from smart_crossover.formats import MinCostFlow
+    from smart_crossover.network_methods.algorithms import network_crossover
+    tail, head, b, c, u, x = mcf_mid_inputs()
+    E, N = c.size, b.size
+    A = sp.csr_matrix((np.concatenate([np.ones(E, dtype=int), -np.ones(E, dtype=int)]),
+                       (np.concatenate([tail, head]), np.concatenate([np.arange(E)] * 2))), shape=(N, E))
+    fx = Fixture("e2e_mcf_20k")
+    out = network_crossover(x=x.copy(), mcf=MinCostFlow(A=A, b=b.copy(), c=c.copy(), u=u.copy()), method="cnet_mcf",
+                            solver="HGS", solver_settings=_quiet())
+    ref = float(fx.out["cnet_mcf_obj"])
+    assert abs(out.obj_val - ref) <= 1e-9 * abs(ref) and abs(out.obj_val - float(fx.out["direct_obj"])) <= 1e-9 * abs(ref)
+    assert out.iter_count == int(fx.out["cnet_mcf_iters"])
+    assert np.array_equal(np.flatnonzero(out.basis.vbasis == 0), fx.out["cnet_mcf_basic"])

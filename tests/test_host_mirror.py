@@ -123,6 +123,49 @@ def test_sub_problem_assembly_equals_slicing_the_full_matrix(name):
     assert mgr2.basis.cbasis.size == S + D + 2 and (mgr2.basis.vbasis[mgr2.artificial_vars] == 0).all()
 
 
+@pytest.mark.parametrize("name", ["mcf_small_200", "mcf_ties_60"])
+def test_mcf_restricted_master_equals_the_reference_formulas(name):
+    """`MCFManagerStd.update_subproblem` / `add_free_variables` / `fix_variables` build the restricted master
+    from the arcs' end points and a mask of freed arcs; the reference slices `A[:, non_fix]`, multiplies
+    `A[:, fix_up] @ u[fix_up]` and calls `np.setdiff1d` three times per round (net_manager.py:202-209,
+    224-245).  Same matrices (canonical CSC arrays), bit-identical right-hand side, same index sets."""
+    import scipy.sparse as sp
+    from smart_crossover.formats import MinCostFlow
+    from smart_crossover.network_methods.net_manager import MCFManagerStd
+    fx = Fixture(name)
+    tail, head, b, c, u, x = (fx.inp[k] for k in ("tail", "head", "b", "c", "u", "x"))
+    E, N = c.size, b.size
+    A = sp.lil_matrix((N, E), dtype=int)
+    A[head, np.arange(E)] = -1
+    A[tail, np.arange(E)] = 1
+    mgr = MCFManagerStd(MinCostFlow(A=A.tocsr(), b=b.copy(), c=c.copy(), u=u * 1.37))      # non-integer capacities
+    x = np.clip(x, 0, mgr.mcf.u)
+    mgr.rescale_cost(np.max(np.abs(c)))
+    low, up = np.where(x < mgr.mcf.u / 2)[0], np.where(x >= mgr.mcf.u / 2)[0]
+    mgr.fix_variables(ind_fix_to_low=low, ind_fix_to_up=up)
+    ref = {"fix_low": low, "fix_up": up, "non_fix": np.setdiff1d(range(E), np.append(low, up))}
+    ref["fix"] = np.setdiff1d(range(E), ref["non_fix"])
+    mgr.extend_by_bigM(mgr.m * np.max(mgr.mcf.c))
+    ref["non_fix"] = np.append(ref["non_fix"], np.arange(E, E + N))
+    queue = np.random.default_rng(0).permutation(E)
+    for lo, hi in ((0, 50), (50, 150), (150, 400)):
+        mgr.add_free_variables(queue[lo:hi])
+        ref["non_fix"] = np.append(ref["non_fix"], queue[lo:hi])
+        for key in ("fix", "fix_low", "fix_up"):
+            ref[key] = np.setdiff1d(ref[key], queue[lo:hi])
+        for key in ref:
+            assert np.array_equal(mgr.var_info[key], ref[key]), key
+        mgr.update_subproblem()
+        A_ref = sp.csc_matrix(mgr.mcf.A[:, ref["non_fix"]])
+        b_ref = mgr.mcf.b - mgr.mcf.A[:, ref["fix_up"]] @ mgr.mcf.u[ref["fix_up"]]
+        A_sub = sp.csc_matrix(mgr.mcf_sub.A)
+        assert np.array_equal(A_sub.indptr, A_ref.indptr) and np.array_equal(A_sub.indices, A_ref.indices)
+        assert np.array_equal(A_sub.data, A_ref.data)
+        assert mgr.mcf_sub.b.tobytes() == b_ref.tobytes()
+        assert np.array_equal(mgr.mcf_sub.c, mgr.mcf.c[ref["non_fix"]])
+        assert np.array_equal(mgr.mcf_sub.u, mgr.mcf.u[ref["non_fix"]])
+
+
 def test_highs_backend_solves_and_reports_like_a_solver_caller():
     fx = Fixture("ot_c1_40x40")
     ot = OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"])

@@ -101,6 +101,26 @@ def test_c2_784_digests():
     assert np.array_equal(ids, small["topk_ids_pert"])
 
 
+def test_c2_784_push_phase():
+    """784 x 784: the oracle's tree flows through the oracle's push loop and through the product's native
+    push loop (sx_push_tree_h, host code): the reference's push count (934) and basis."""
+    import ctypes
+    from smart_crossover import _native
+    s, d, M, x = c2_inputs()
+    small = Fixture("ot_c2_784_small").out
+    tree = small["tree"]
+    flows = orc.ot_tree_flows(tree, s, d)
+    vbasis, it = orc.push_tree_to_bfs(tree, flows, *M.shape)
+    assert it == int(small["push_iter"]) == 934
+    assert np.array_equal(np.flatnonzero(vbasis == 0), small["basic_tree"])
+    pos = np.empty(4 * tree.size, dtype=np.int64)
+    n_pos, n_it = ctypes.c_int64(0), ctypes.c_int64(0)
+    tree64, flows64 = np.ascontiguousarray(tree, dtype=np.int64), np.ascontiguousarray(flows)
+    assert _native.lib.sx_push_tree_h(tree64.ctypes.data, flows64.ctypes.data, tree.size, *M.shape, pos.ctypes.data,
+                                      pos.size, ctypes.byref(n_pos), ctypes.byref(n_it)) == 0
+    assert n_it.value == 934 and np.array_equal(np.sort(pos[:n_pos.value]), small["basic_tree"])
+
+
 def test_mcf_mid_digests():
     tail, head, b, c, u, x = mcf_mid_inputs()
     dg = digests()["mcf_mid_20k"]["digests"]
