@@ -27,6 +27,7 @@
 // sx_topk_merge_ll), which own the refinement levels and the sorted fallback.
 #include <stdlib.h>
 
+#include "sx_gridbar.cuh"
 #include "sx_ll.cuh"
 #include "sx_price_tma.cuh"
 
@@ -39,8 +40,7 @@ constexpr int kMergeCtas      = 64;     // CTAs (from the end of the grid) that 
 
 struct FusedCtl {
     unsigned long long pass;      // passes completed; parity selects the selection state in use
-    unsigned int       bar_cnt;   // grid barrier: arrivals of the current phase
-    unsigned int       bar_gen;   // grid barrier: generation
+    GridBarrier        bar;       // grid-wide barrier (sx_gridbar.cuh)
     unsigned int       pad[4];
     unsigned long long ts[8];     // diagnostics: %globaltimer of CTA 0 at the phase boundaries of the last pass
 };
@@ -67,43 +67,13 @@ struct FusedParams {
     unsigned long long timeout_ns;
 };
 
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void stamp(FusedCtl *ctl, int i) {
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ts[i] = global_timer_ns();
-}
-
-// Reusable grid-wide barrier (all CTAs resident: cooperative launch).  The last CTA to arrive resets the
-// arrival count and bumps the generation the others spin on, so nothing depends on the grid size of
-// earlier launches.
-__device__ __forceinline__ void grid_barrier(FusedCtl *ctl) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned gen = ld_volatile_u32(&ctl->bar_gen);      // read before arriving
-        __threadfence();
-        if (atomicAdd(&ctl->bar_cnt, 1u) == gridDim.x - 1u) {
-            *reinterpret_cast<volatile unsigned *>(&ctl->bar_cnt) = 0u;
-            __threadfence();
-            atomicAdd(&ctl->bar_gen, 1u);
-        } else {
-            while (ld_acquire_u32(&ctl->bar_gen) == gen) {}
-        }
-        __threadfence();
-    }
-    __syncthreads();
 }
 
 // slot `idx` of rank r's block, parity half of `epoch`, in the exchange buffer `buf`
@@ -150,7 +120,7 @@ price_fused_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p
     price_tiles<ROWS, STAGES, CWARPS, false>(tmap, p, smem_raw);
     stamp(ctl, 1);
 
-    grid_barrier(ctl);      // header, histogram and candidate list of this pass are complete
+    grid_barrier(&ctl->bar);      // header, histogram and candidate list of this pass are complete
     stamp(ctl, 2);
     if (blockIdx.x == 0 && tid == 0) {
         // every CTA has read `pass` and the exchange epoch: advance them for the next launch (the merge
@@ -195,7 +165,7 @@ price_fused_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p
             }
         }
         stamp(ctl, 3);
-        grid_barrier(ctl);      // survivor list complete
+        grid_barrier(&ctl->bar);      // survivor list complete
         const unsigned n_s_raw = __ldcg(&sel->n_sure);
         incomplete = n_s_raw > (unsigned)kFusedSurvCap;
         n_s = incomplete ? 0 : (int)n_s_raw;

@@ -15,11 +15,8 @@
 //            on the contracted graph); hook that root under the other (smaller id wins when
 //            both picked the same arc) and record the arc;
 // and repeats until the chunk has no survivor.  Work is atomics / L2 bound, not HBM bound.
-#include <cooperative_groups.h>
-
 #include "sx_common.cuh"
-
-namespace cg = cooperative_groups;
+#include "sx_gridbar.cuh"
 
 namespace sx {
 
@@ -41,11 +38,14 @@ struct KrParams {
     unsigned long long *ctr;              // [0] tree count, [1],[2] survivor counts of list 0/1
 };
 
+// SINGLE: the whole forest lives in the shared memory of one CTA (plain loads); otherwise in global memory,
+// read through L2 because other SMs rewrite it.
+template <bool SINGLE>
 __device__ __forceinline__ int kr_find(int *parent, int x) {
     for (;;) {
-        const int p = __ldcg(parent + x);
+        const int p = SINGLE ? parent[x] : __ldcg(parent + x);
         if (p == x) return x;
-        const int gp = __ldcg(parent + p);
+        const int gp = SINGLE ? parent[p] : __ldcg(parent + p);
         if (gp == p) return p;
         parent[x] = gp;   // path halving; racing writers only ever store an ancestor
         x = gp;
@@ -57,12 +57,28 @@ __device__ __forceinline__ void kr_endpoints(const KrParams &p, uint32_t e, int 
     else { const long long i = (long long)e / p.D; u = (int)i; v = (int)(p.S + ((long long)e - i * p.D)); }
 }
 
-__global__ void __launch_bounds__(kKrThreads) kruskal_kernel(KrParams p) {
-    cg::grid_group grid = cg::this_grid();
+template <bool SINGLE>
+__device__ __forceinline__ void kr_sync(GridBarrier *bar) {
+    if (SINGLE) __syncthreads(); else grid_barrier(bar);
+}
+
+// The whole algorithm; `parent` / `best` are the forest and the per-root proposals (global memory, or the
+// shared memory of the only CTA when SINGLE: every barrier is then a __syncthreads and every find a few
+// shared-memory reads -- the 784 x 784 tree drops from 0.18 ms of grid-wide barriers to a few tens of us).
+template <bool SINGLE>
+__device__ __forceinline__ unsigned long long kr_ld(const unsigned long long *q) {
+    return SINGLE ? *reinterpret_cast<const volatile unsigned long long *>(q) : __ldcg(q);
+}
+
+// `ctr`: [0] tree count, [1], [2] survivor counts of the two lists (shared memory when SINGLE).
+template <bool SINGLE>
+__device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, unsigned long long *best,
+                                             unsigned long long *ctr) {
+    GridBarrier *bar = reinterpret_cast<GridBarrier *>(p.ctr + 4);
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gsz  = (long long)gridDim.x * blockDim.x;
-    for (long long v = gtid; v < p.N; v += gsz) { p.parent[v] = (int)v; p.best[v] = ~0ull; }
-    grid.sync();
+    for (long long v = gtid; v < p.N; v += gsz) { parent[v] = (int)v; best[v] = ~0ull; }
+    kr_sync<SINGLE>(bar);
 
     long long pos = 0;
     long long csize = p.first_chunk;
@@ -80,7 +96,7 @@ __global__ void __launch_bounds__(kKrThreads) kruskal_kernel(KrParams p) {
             ++epoch;
             const unsigned long long tag = (kEpochMax - epoch) << 40;
             const int nxt = cur ^ 1;
-            const long long cnt_in = first ? (cend - pos) : (long long)__ldcg(&p.ctr[1 + cur]);
+            const long long cnt_in = first ? (cend - pos) : (long long)kr_ld<SINGLE>(&ctr[1 + cur]);
             // ---- phase A: filter + propose ----
             for (long long base = (long long)blockIdx.x * blockDim.x; base < cnt_in; base += gsz) {
                 const long long idx = base + threadIdx.x;
@@ -88,71 +104,87 @@ __global__ void __launch_bounds__(kKrThreads) kruskal_kernel(KrParams p) {
                 uint32_t q = 0;
                 int ru = 0, rv = 0;
                 if (idx < cnt_in) {
-                    q = first ? (uint32_t)(pos + idx) : p.list[cur][idx];
+                    q = first ? (uint32_t)(pos + idx) : __ldcg(&p.list[cur][idx]);
                     int u, v;
                     kr_endpoints(p, p.korder[q], u, v);
-                    ru = kr_find(p.parent, u);
-                    rv = kr_find(p.parent, v);
+                    ru = kr_find<SINGLE>(parent, u);
+                    rv = kr_find<SINGLE>(parent, v);
                     alive = ru != rv;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, alive);
                 if (m) {
                     unsigned long long slot0 = 0;
                     if (lane_id() == (unsigned)(__ffs(m) - 1))
-                        slot0 = atomicAdd(&p.ctr[1 + nxt], (unsigned long long)__popc(m));
+                        slot0 = atomicAdd(&ctr[1 + nxt], (unsigned long long)__popc(m));
                     slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(m) - 1);
                     if (alive) {
                         const long long slot = (long long)slot0 + __popc(m & ((1u << lane_id()) - 1u));
                         p.list[nxt][slot]  = q;
                         p.roots[nxt][slot] = make_int2(ru, rv);
-                        atomicMin(&p.best[ru], tag | q);
-                        atomicMin(&p.best[rv], tag | q);
+                        atomicMin(&best[ru], tag | q);
+                        atomicMin(&best[rv], tag | q);
                     }
                 }
             }
-            grid.sync();
-            const long long alive_n = (long long)__ldcg(&p.ctr[1 + nxt]);
+            kr_sync<SINGLE>(bar);
+            const long long alive_n = (long long)kr_ld<SINGLE>(&ctr[1 + nxt]);
             if (alive_n == 0) break;
             // ---- phase B: hook the winners ----
-            if (gtid == 0) p.ctr[1 + cur] = 0;   // becomes the append counter of the next round
+            if (gtid == 0) ctr[1 + cur] = 0;   // becomes the append counter of the next round
             for (long long idx = gtid; idx < alive_n; idx += gsz) {
-                const uint32_t q = p.list[nxt][idx];
-                const int2 r = p.roots[nxt][idx];
+                const uint32_t q = __ldcg(&p.list[nxt][idx]);
+                const int2 r = __ldcg(&p.roots[nxt][idx]);
                 const unsigned long long key = tag | q;
-                const bool su = __ldcg(&p.best[r.x]) == key;
-                const bool sv = __ldcg(&p.best[r.y]) == key;
+                const bool su = (SINGLE ? best[r.x] : __ldcg(&best[r.x])) == key;
+                const bool sv = (SINGLE ? best[r.y] : __ldcg(&best[r.y])) == key;
                 if (su || sv) {
-                    const unsigned long long t = atomicAdd(&p.ctr[0], 1ull);
+                    const unsigned long long t = atomicAdd(&ctr[0], 1ull);
                     if (t < want) p.tree_out[t] = (long long)p.korder[q];
                     if (su && sv) {
                         const int hi = r.x > r.y ? r.x : r.y, lo = r.x > r.y ? r.y : r.x;
-                        p.parent[hi] = lo;
+                        parent[hi] = lo;
                     } else if (su) {
-                        p.parent[r.x] = r.y;
+                        parent[r.x] = r.y;
                     } else {
-                        p.parent[r.y] = r.x;
+                        parent[r.y] = r.x;
                     }
                 }
             }
-            grid.sync();
-            if (__ldcg(&p.ctr[0]) >= want) { done = true; break; }
+            kr_sync<SINGLE>(bar);
+            if (kr_ld<SINGLE>(&ctr[0]) >= want) { done = true; break; }
             first = false;
             cur = nxt;
         }
         // the break on alive_n == 0 leaves ctr[1+nxt] == 0 and ctr[1+cur] possibly stale: clear both
-        grid.sync();
-        if (gtid == 0) { p.ctr[1] = 0; p.ctr[2] = 0; }
-        grid.sync();
+        kr_sync<SINGLE>(bar);
+        if (gtid == 0) { ctr[1] = 0; ctr[2] = 0; }
+        kr_sync<SINGLE>(bar);
         pos = cend;
         csize *= 2;
         if (csize > p.list_cap) csize = p.list_cap;
     }
 }
 
+__global__ void __launch_bounds__(kKrThreads) kruskal_kernel(KrParams p) { kruskal_body<false>(p, p.parent, p.best, p.ctr); }
+
+constexpr int kKrSmallThreads = 1024;
+constexpr long long kKrSmallN = 16000;      // 12 bytes of shared memory per node
+__global__ void __launch_bounds__(kKrSmallThreads) kruskal_small_kernel(KrParams p) {
+    extern __shared__ __align__(16) unsigned char kr_raw[];
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(kr_raw);
+    int *parent = reinterpret_cast<int *>(kr_raw + (size_t)p.N * sizeof(unsigned long long));
+    __shared__ unsigned long long s_ctr[4];
+    if (threadIdx.x < 4) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
+    kruskal_body<true>(p, parent, best, s_ctr);
+    __syncthreads();
+    if (threadIdx.x == 0) p.ctr[0] = s_ctr[0];          // read by kr_count_kernel
+}
+
 __global__ void kr_fill_kernel(long long *tree_out, long long cap, unsigned long long *ctr) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cap) tree_out[i] = 0x7fffffffffffffffll;
-    if (i < 4) ctr[i] = 0;
+    if (i < 8) ctr[i] = 0;                     // [0..2] counters, [4] grid barrier
 }
 __global__ void kr_count_kernel(const unsigned long long *ctr, long long cap, long long *n_tree_out) {
     const unsigned long long c = ctr[0];
@@ -224,9 +256,14 @@ extern "C" int sx_kruskal(const uint32_t *korder, int64_t n, const int32_t *tail
     const size_t sort_ws_bytes = ws_bytes - cv.off;
     p.tree_out = raw_tree;
 
-    kr_fill_kernel<<<(int)((tcap + 4 + 255) / 256), 256, 0, st>>>(raw_tree, tcap, p.ctr);
+    kr_fill_kernel<<<(int)((tcap + 8 + 255) / 256), 256, 0, st>>>(raw_tree, tcap, p.ctr);
     SX_LAUNCH_CHECK();
-    if (n > 0 && tcap > 0) {
+    if (n > 0 && tcap > 0 && N <= kKrSmallN) {
+        const size_t smem = (size_t)N * 12 + 16;
+        SX_CUDA(cudaFuncSetAttribute(kruskal_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kKrSmallN * 12 + 16)));
+        kruskal_small_kernel<<<1, kKrSmallThreads, smem, st>>>(p);
+        SX_LAUNCH_CHECK();
+    } else if (n > 0 && tcap > 0) {
         int dev = 0, sms = 0, per_sm = 0;
         SX_CUDA(cudaGetDevice(&dev));
         SX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

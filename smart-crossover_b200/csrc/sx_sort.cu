@@ -7,6 +7,7 @@
 // a single-block scan, and a downsweep (stable in-tile ranking with warp match + shuffles,
 // shared-memory exchange, coalesced run-wise scatter; 12 B read + 12 B written per key).
 #include "sx_common.cuh"
+#include "sx_gridbar.cuh"
 
 namespace sx {
 
@@ -207,6 +208,91 @@ struct RsSmem {
     uint32_t           warp_tot[8];
 };
 
+// Stable in-tile ranking of the tile's keys by their digit: on return rank[r] is the key's position among the
+// keys of its warp with the same digit, sm.cnt[w][d] the number of such keys in earlier warps, sm.tile_cnt[d] the
+// tile's digit histogram and sm.tile_start[d] its exclusive scan.  sm.cnt must be zero and visible on entry.
+template <int THREADS>
+__device__ __forceinline__ void rs_rank_tile(RsSmem<THREADS> &sm, const unsigned long long (&key)[kRsItems], int shift,
+                                             uint32_t (&rank)[kRsItems]) {
+    constexpr int kWarps = THREADS / 32;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const unsigned d = (unsigned)((key[r] >> shift) & 0xff);
+        const unsigned peers = match_digit(d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = sm.cnt[warp][d];
+            sm.cnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per-digit exclusive scan over warps, and the tile's digit totals
+    if (threadIdx.x < 256) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            uint32_t t = sm.cnt[w][threadIdx.x];
+            sm.cnt[w][threadIdx.x] = s;
+            s += t;
+        }
+        sm.tile_cnt[threadIdx.x] = s;
+        // exclusive scan over the 256 digits (8 warps x 32)
+        uint32_t incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) sm.warp_tot[warp] = incl;
+        sm.tile_start[threadIdx.x] = incl - s;   // warp-local exclusive
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        uint32_t add = 0;
+        for (int w = 0; w < warp; ++w) add += sm.warp_tot[w];
+        sm.tile_start[threadIdx.x] += add;
+    }
+    __syncthreads();
+}
+
+// Exchange through shared memory (keys grouped by digit, stable) and run-coalesced scatter to the tile's
+// global positions sm.digit_base[d] + (index within the tile's digit run).
+template <int THREADS, bool LAST_F64>
+__device__ __forceinline__ void rs_scatter_tile(RsSmem<THREADS> &sm, const unsigned long long (&key)[kRsItems],
+                                                const uint32_t (&val)[kRsItems], const uint32_t (&rank)[kRsItems],
+                                                int shift, long long valid, const RsDst &dst) {
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const unsigned d = (unsigned)((key[r] >> shift) & 0xff);
+        const uint32_t pos = sm.tile_start[d] + sm.cnt[warp][d] + rank[r];
+        sm.keys[pos] = key[r];
+        sm.vals[pos] = val[r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRsItems; ++k) {
+        const int i = threadIdx.x + k * THREADS;
+        if (i < valid) {
+            const unsigned long long kk = sm.keys[i];
+            const unsigned d = (unsigned)((kk >> shift) & 0xff);
+            const size_t g = (size_t)sm.digit_base[d] + (uint32_t)(i - sm.tile_start[d]);
+            if (LAST_F64) {
+                if (dst.f64) dst.f64[g] = sort_key_to_f64(kk);
+            } else if (dst.keys) {
+                dst.keys[g] = kk;
+            }
+            dst.vals[g] = sm.vals[i];
+        }
+    }
+}
+
 template <int THREADS, int SRC, bool LAST_F64>
 __global__ void __launch_bounds__(THREADS)
 rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tiles_per_block,
@@ -215,7 +301,6 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
     constexpr int kTile = THREADS * kRsItems, kWarps = THREADS / 32;
     RsSmem<THREADS> &sm = *reinterpret_cast<RsSmem<THREADS> *>(rs_raw);
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    const unsigned lt = (1u << lane) - 1u;
     if (threadIdx.x < 256) sm.digit_base[threadIdx.x] = hist[(size_t)threadIdx.x * grid + blockIdx.x];
 
     const long long tile0 = (long long)blockIdx.x * tiles_per_block;
@@ -251,48 +336,44 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
         }
         __syncthreads();
         uint32_t rank[kRsItems];
-#pragma unroll
-        for (int r = 0; r < kRsItems; ++r) {
-            const unsigned d = (unsigned)((key[r] >> shift) & 0xff);
-            const unsigned peers = match_digit(d);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader) {
-                old = sm.cnt[warp][d];
-                sm.cnt[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[r] = old + __popc(peers & lt);
-            __syncwarp();
-        }
+        rs_rank_tile<THREADS>(sm, key, shift, rank);
+        rs_scatter_tile<THREADS, LAST_F64>(sm, key, val, rank, shift, valid, dst);
         __syncthreads();
-        // per-digit exclusive scan over warps, and the tile's digit totals
-        if (threadIdx.x < 256) {
-            uint32_t s = 0;
+        if (threadIdx.x < 256) sm.digit_base[threadIdx.x] += sm.tile_cnt[threadIdx.x];
+    }
+}
+
+// ---- small inputs: one CTA, every pass in shared memory ------------------------------------------------------
+// Up to 8192 keys (the half-edges and tree arcs of a 784 x 784 instance, all of a 40 x 40 one): one tile of
+// 1024 threads x 8 keys, ranked per 8-bit digit exactly like a downsweep tile and exchanged through shared
+// memory; nothing touches global memory between the load and the final store.  ~3 us per pass instead of
+// three launches.
+constexpr int kSmallSortMax = 8192;
+constexpr int kSmallThreads = 1024;
+
+template <int SRC>
+__global__ void __launch_bounds__(kSmallThreads)
+rs_small_sort_kernel(RsSrc src, int n, int passes, uint32_t *order_out, double *sorted_f64,
+                     unsigned long long *sorted_u64) {
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    RsSmem<kSmallThreads> &sm = *reinterpret_cast<RsSmem<kSmallThreads> *>(rs_raw);
+    constexpr int kWarps = kSmallThreads / 32;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int li0 = warp * (32 * kRsItems) + lane;
+    unsigned long long key[kRsItems];
+    uint32_t           val[kRsItems];
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                uint32_t t = sm.cnt[w][threadIdx.x];
-                sm.cnt[w][threadIdx.x] = s;
-                s += t;
-            }
-            sm.tile_cnt[threadIdx.x] = s;
-            // exclusive scan over the 256 digits (8 warps x 32)
-            uint32_t incl = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (lane == 31) sm.warp_tot[warp] = incl;
-            sm.tile_start[threadIdx.x] = incl - s;   // warp-local exclusive
-        }
+    for (int r = 0; r < kRsItems; ++r) {
+        const int li = li0 + r * 32;
+        key[r] = li < n ? rs_load_key<SRC>(src, li) : ~0ull;      // padding: all-ones, last by stability
+        val[r] = li < n ? (uint32_t)li : 0xffffffffu;
+    }
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = 8 * ps;
+        for (int i = threadIdx.x; i < kWarps * 256; i += kSmallThreads) (&sm.cnt[0][0])[i] = 0;
         __syncthreads();
-        if (threadIdx.x < 256) {
-            uint32_t add = 0;
-            for (int w = 0; w < warp; ++w) add += sm.warp_tot[w];
-            sm.tile_start[threadIdx.x] += add;
-        }
-        __syncthreads();
+        uint32_t rank[kRsItems];
+        rs_rank_tile<kSmallThreads>(sm, key, shift, rank);
 #pragma unroll
         for (int r = 0; r < kRsItems; ++r) {
             const unsigned d = (unsigned)((key[r] >> shift) & 0xff);
@@ -302,22 +383,137 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kRsItems; ++k) {
-            const int i = threadIdx.x + k * THREADS;
-            if (i < valid) {
-                const unsigned long long kk = sm.keys[i];
-                const unsigned d = (unsigned)((kk >> shift) & 0xff);
-                const size_t g = (size_t)sm.digit_base[d] + (uint32_t)(i - sm.tile_start[d]);
-                if (LAST_F64) {
-                    if (dst.f64) dst.f64[g] = sort_key_to_f64(kk);
-                } else if (dst.keys) {
-                    dst.keys[g] = kk;
+        for (int r = 0; r < kRsItems; ++r) {
+            key[r] = sm.keys[li0 + r * 32];
+            val[r] = sm.vals[li0 + r * 32];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < kRsItems; ++r) {
+        const int li = li0 + r * 32;
+        if (li < n) {
+            order_out[li] = val[r];
+            if (sorted_f64) sorted_f64[li] = sort_key_to_f64(key[r]);
+            if (sorted_u64) sorted_u64[li] = key[r];
+        }
+    }
+}
+
+// ---- mid-size inputs: every pass of the sort in ONE cooperative launch ---------------------------------------
+// One tile of 4096 keys per CTA, all CTAs resident (up to ~1.2 M keys).  Per 8-bit pass: rank the tile in shared
+// memory, publish its digit histogram, grid barrier, every CTA reads the (256 x tiles) table through L2 and
+// derives its own digit bases (digits before mine over all tiles + my digit over earlier tiles), scatter, grid
+// barrier.  16 barriers instead of 24 launches: the 614 656 keys of a 784 x 784 instance are launch-latency
+// bound (0.25 ms for ~2 us of memory traffic per pass).
+constexpr int kCoopThreads = 512;
+constexpr int kCoopTile = kCoopThreads * kRsItems;
+
+struct RsCoop {
+    const double *key_f64;                 // first pass source (one of the two)
+    const unsigned long long *key_u64;
+    unsigned long long *kbuf[2];
+    uint32_t *vbuf[2];
+    uint32_t *hist;                        // 256 x gridDim.x, digit-major
+    GridBarrier *bar;
+    long long n;
+    int passes;
+    uint32_t *order_out;
+    double *sorted_f64;
+    unsigned long long *sorted_u64;
+};
+
+template <bool F64>
+__global__ void __launch_bounds__(kCoopThreads, 2) rs_coop_sort_kernel(RsCoop c) {
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    RsSmem<kCoopThreads> &sm = *reinterpret_cast<RsSmem<kCoopThreads> *>(rs_raw);
+    constexpr int kWarps = kCoopThreads / 32;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int grid = gridDim.x;
+    const long long tbase = (long long)blockIdx.x * kCoopTile;
+    const long long valid = (c.n - tbase < kCoopTile) ? (c.n - tbase) : kCoopTile;
+    const int li0 = warp * (32 * kRsItems) + lane;
+    for (int ps = 0; ps < c.passes; ++ps) {
+        const int shift = 8 * ps;
+        const bool last = ps == c.passes - 1;
+        // ping-pong buffers selected without indexing the parameter arrays (keeps them out of local memory)
+        const unsigned long long *src_k = (ps & 1) ? c.kbuf[0] : c.kbuf[1];
+        const uint32_t *src_v = (ps & 1) ? c.vbuf[0] : c.vbuf[1];
+        unsigned long long *dst_k = (ps & 1) ? c.kbuf[1] : c.kbuf[0];
+        uint32_t *dst_v = (ps & 1) ? c.vbuf[1] : c.vbuf[0];
+        for (int i = threadIdx.x; i < kWarps * 256; i += kCoopThreads) (&sm.cnt[0][0])[i] = 0;
+        unsigned long long key[kRsItems];
+        uint32_t           val[kRsItems];
+#pragma unroll
+        for (int r = 0; r < kRsItems; ++r) {
+            const int li = li0 + r * 32;
+            const long long gi = tbase + li;
+            key[r] = ~0ull;
+            val[r] = 0xffffffffu;
+            if (li < valid) {
+                if (ps == 0) {
+                    key[r] = F64 ? f64_to_sort_key(c.key_f64[gi]) : c.key_u64[gi];
+                    val[r] = (uint32_t)gi;
+                } else {
+                    key[r] = __ldcg(src_k + gi);
+                    val[r] = __ldcg(src_v + gi);
                 }
-                dst.vals[g] = sm.vals[i];
             }
         }
         __syncthreads();
-        if (threadIdx.x < 256) sm.digit_base[threadIdx.x] += sm.tile_cnt[threadIdx.x];
+        uint32_t rank[kRsItems];
+        rs_rank_tile<kCoopThreads>(sm, key, shift, rank);
+        // the padding of the last tile sits in digit 0xff (all-ones keys): it is not part of the histogram
+        if (threadIdx.x < 256) {
+            uint32_t cnt = sm.tile_cnt[threadIdx.x];
+            if (threadIdx.x == 255) cnt -= (uint32_t)(kCoopTile - valid);
+            c.hist[(size_t)blockIdx.x * 256 + threadIdx.x] = cnt;               // tile-major: a row is 1 KB
+        }
+        grid_barrier(c.bar);
+        // Every CTA reads the whole (tiles x 256) table: 64 threads cover a row with 128-bit loads, the 8
+        // thread groups take rows t = g, g + 8, ... (all loads independent, several rows in flight per thread).
+        // tot[d] = sum over all tiles, pre[d] = sum over the tiles before this one.
+        {
+            const int q = threadIdx.x & 63, g = threadIdx.x >> 6;                 // digits 4q..4q+3, row group g
+            uint4 tot = make_uint4(0, 0, 0, 0), pre = make_uint4(0, 0, 0, 0);
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(c.hist);
+#pragma unroll 4
+            for (int t = g; t < grid; t += kCoopThreads / 64) {
+                const uint4 v = __ldcg(h4 + (size_t)t * 64 + q);
+                tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+                if (t < (int)blockIdx.x) { pre.x += v.x; pre.y += v.y; pre.z += v.z; pre.w += v.w; }
+            }
+            // partial sums of the 8 groups: sm.keys (free until the scatter) as 2 x 8 x 256 uint32
+            uint32_t *part = reinterpret_cast<uint32_t *>(sm.keys);
+            reinterpret_cast<uint4 *>(part + g * 256)[q] = tot;
+            reinterpret_cast<uint4 *>(part + 2048 + g * 256)[q] = pre;
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            const uint32_t *part = reinterpret_cast<const uint32_t *>(sm.keys);
+            uint32_t tot = 0, pre = 0;
+#pragma unroll
+            for (int g = 0; g < kCoopThreads / 64; ++g) { tot += part[g * 256 + threadIdx.x]; pre += part[2048 + g * 256 + threadIdx.x]; }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) sm.warp_tot[warp] = incl;
+            sm.digit_base[threadIdx.x] = incl - tot + pre;                     // warp-local exclusive + earlier tiles
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            uint32_t add = 0;
+            for (int w = 0; w < warp; ++w) add += sm.warp_tot[w];
+            sm.digit_base[threadIdx.x] += add;
+        }
+        __syncthreads();
+        RsDst dst{last ? c.sorted_u64 : dst_k, last ? c.sorted_f64 : nullptr, last ? c.order_out : dst_v};
+        if (last && F64) rs_scatter_tile<kCoopThreads, true>(sm, key, val, rank, shift, valid, dst);
+        else             rs_scatter_tile<kCoopThreads, false>(sm, key, val, rank, shift, valid, dst);
+        if (!last) grid_barrier(c.bar);
     }
 }
 
@@ -326,13 +522,18 @@ struct RsPlan {
     int       grid, threads;
 };
 static int g_rs_threads = 512;
+static int g_rs_coop = 1;      // mid-size inputs take the single cooperative launch (sx_sort_set_tuning(0 / 1) switches it)
 static RsPlan rs_plan(long long n) {
     RsPlan p;
     p.threads = g_rs_threads;
     const long long tile = (long long)p.threads * kRsItems;
     p.tiles = (n + tile - 1) / tile;
     if (p.tiles < 1) p.tiles = 1;
-    p.tiles_per_block = (p.tiles + kRsMaxGrid - 1) / kRsMaxGrid;
+    // One wave of downsweep CTAs (2 per SM) is enough up to ~64 M keys and keeps the (256 x grid) counter table --
+    // which a single CTA scans between the sweeps -- small: 31 -> ~10 us per pass at 10 M keys.
+    long long max_grid = n < (1ll << 26) ? 2ll * num_sms() : kRsMaxGrid;
+    if (max_grid > kRsMaxGrid) max_grid = kRsMaxGrid;
+    p.tiles_per_block = (p.tiles + max_grid - 1) / max_grid;
     p.grid = (int)((p.tiles + p.tiles_per_block - 1) / p.tiles_per_block);
     return p;
 }
@@ -370,12 +571,50 @@ static int rs_sort(const double *key_f64, const unsigned long long *key_u64, lon
     if (n >= (1ll << 32)) return SX_ERR_TOO_LARGE;
     if (ws_bytes < sx_argsort_workspace_bytes(n) || !ws) return SX_ERR_WORKSPACE;
     if (n == 0) return SX_OK;
+    if (n <= kSmallSortMax) {
+        const size_t smem = sizeof(RsSmem<kSmallThreads>);
+        RsSrc src{key_u64, key_f64, nullptr};
+        if (key_f64) {
+            SX_CUDA(cudaFuncSetAttribute(rs_small_sort_kernel<kFromF64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rs_small_sort_kernel<kFromF64><<<1, kSmallThreads, smem, st>>>(src, (int)n, passes, order_out, sorted_f64, sorted_u64);
+        } else {
+            SX_CUDA(cudaFuncSetAttribute(rs_small_sort_kernel<kFromU64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rs_small_sort_kernel<kFromU64><<<1, kSmallThreads, smem, st>>>(src, (int)n, passes, order_out, sorted_f64, sorted_u64);
+        }
+        SX_LAUNCH_CHECK();
+        return SX_OK;
+    }
     const RsPlan pl = rs_plan(n);
     Carver cv(ws);
     unsigned long long *kbuf[2] = {cv.take<unsigned long long>(n), cv.take<unsigned long long>(n)};
     uint32_t *vbuf[2] = {cv.take<uint32_t>(n), cv.take<uint32_t>(n)};
     uint32_t *hist = cv.take<uint32_t>((size_t)256 * kRsMaxGrid);
+    GridBarrier *bar = cv.take<GridBarrier>(1);
     const bool f64 = key_f64 != nullptr;
+    {
+        // mid-size: one tile per CTA, all passes in one cooperative launch, if every tile can be resident
+        const long long tiles = (n + kCoopTile - 1) / kCoopTile;
+        static int coop_max[64] = {0};
+        int dev = 0;
+        SX_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && coop_max[dev] == 0) {
+            int occ_a = 0, occ_b = 0;
+            SX_CUDA(cudaFuncSetAttribute(rs_coop_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<kCoopThreads>)));
+            SX_CUDA(cudaFuncSetAttribute(rs_coop_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<kCoopThreads>)));
+            SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, rs_coop_sort_kernel<true>, kCoopThreads, sizeof(RsSmem<kCoopThreads>)));
+            SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, rs_coop_sort_kernel<false>, kCoopThreads, sizeof(RsSmem<kCoopThreads>)));
+            const int occ = occ_a < occ_b ? occ_a : occ_b;
+            coop_max[dev] = occ > 0 ? occ * num_sms() : -1;
+        }
+        if (dev >= 0 && dev < 64 && g_rs_coop && tiles <= coop_max[dev] && tiles <= kRsMaxGrid) {
+            RsCoop c{key_f64, key_u64, {kbuf[0], kbuf[1]}, {vbuf[0], vbuf[1]}, hist, bar, n, passes, order_out, sorted_f64, sorted_u64};
+            SX_CUDA(cudaMemsetAsync(bar, 0, sizeof(GridBarrier), st));
+            void *args[] = {(void *)&c};
+            void *kern = f64 ? (void *)rs_coop_sort_kernel<true> : (void *)rs_coop_sort_kernel<false>;
+            SX_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)tiles), dim3(kCoopThreads), args, sizeof(RsSmem<kCoopThreads>), st));
+            return SX_OK;
+        }
+    }
     for (int ps = 0; ps < passes; ++ps) {
         const bool first = ps == 0, last = ps == passes - 1;
         RsSrc src{first ? key_u64 : kbuf[(ps - 1) & 1], key_f64, first ? nullptr : vbuf[(ps - 1) & 1]};
@@ -604,6 +843,7 @@ __global__ void ko_run_start_kernel(const double *__restrict__ key, long long po
 using namespace sx;
 
 extern "C" int sx_sort_set_tuning(int downsweep_threads) {
+    if (downsweep_threads == 0 || downsweep_threads == 1) { g_rs_coop = downsweep_threads; return SX_OK; }
     if (downsweep_threads != 256 && downsweep_threads != 512 && downsweep_threads != 1024) return SX_ERR_INVALID;
     g_rs_threads = downsweep_threads;
     return SX_OK;
@@ -612,7 +852,7 @@ extern "C" int sx_sort_set_tuning(int downsweep_threads) {
 extern "C" size_t sx_argsort_workspace_bytes(int64_t n) {
     if (n < 0) return 0;
     return 2 * carve_bytes((size_t)n, 8) + 2 * carve_bytes((size_t)n, 4) +
-           carve_bytes((size_t)256 * kRsMaxGrid, 4) + 256;
+           carve_bytes((size_t)256 * kRsMaxGrid, 4) + 512;
 }
 
 extern "C" int sx_argsort_f64(const double *key, int64_t n, uint32_t *order_asc_out, double *sorted_key_out,

@@ -20,10 +20,21 @@
 // prefix sums are carried in double-double (error-free TwoSum), so each flow is the correctly
 // rounded-to-1-ulp subtree sum no matter how large the running total is.
 #include "sx_common.cuh"
+#include "sx_gridbar.cuh"
 
 namespace sx {
 
 constexpr int kTrThreads = 256;
+constexpr int kTourThreads = 1024;     // the cooperative tour kernel: few, fat CTAs make the grid barrier cheap
+constexpr long long kTourSmallH = 4096; // up to here one CTA ranks the whole tour in shared memory (128 KB)
+
+// Ranking state of a half-edge: inclusive prefix of the weights, tour position, predecessor still to jump over.
+// One 16-byte record: a pointer-jumping round is two 128-bit gathers per element instead of six loads.
+struct __align__(16) TourNode {
+    double sum;
+    int    rank;
+    int    pred;
+};
 
 struct TreeArrays {
     unsigned long long *origin;   // H sort keys: origin node of each half-edge
@@ -32,9 +43,7 @@ struct TreeArrays {
     int      *dest;               // H
     int      *pos;                // H position of a half-edge in `ho`
     int      *first;              // N first position of a node's run in `ho`, -1 if none
-    double   *sum[2];             // H
-    int      *rank[2];            // H
-    int      *pred[2];            // H
+    TourNode *node[2];            // H, ping-pong of the pointer jumping
 };
 
 __global__ void tree_halfedges_kernel(const long long *__restrict__ tree, long long T,
@@ -55,65 +64,98 @@ __global__ void tree_halfedges_kernel(const long long *__restrict__ tree, long l
             minus = plus_is_tail ? head[e] : tail[e];
             c = cost ? cost[e] : 0.0;
         }
-        a.origin[2 * t] = (unsigned long long)minus; a.dest[2 * t] = plus;      a.sum[0][2 * t] = c;
-        a.origin[2 * t + 1] = (unsigned long long)plus; a.dest[2 * t + 1] = minus; a.sum[0][2 * t + 1] = -c;
+        a.origin[2 * t] = (unsigned long long)minus; a.dest[2 * t] = plus;      a.node[0][2 * t].sum = c;
+        a.origin[2 * t + 1] = (unsigned long long)plus; a.dest[2 * t + 1] = minus; a.node[0][2 * t + 1].sum = -c;
     }
 }
 
-__global__ void tree_first_kernel(long long H, TreeArrays a) {
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < H;
-         p += (long long)gridDim.x * blockDim.x) {
+__device__ __forceinline__ TourNode ld_node(const TourNode *p) {
+    const int4 v = __ldcg(reinterpret_cast<const int4 *>(p));
+    TourNode n;
+    n.sum = __hiloint2double(v.y, v.x); n.rank = v.z; n.pred = v.w;
+    return n;
+}
+
+// Everything between the half-edge sort and the read-out in ONE launch: adjacency (first / pos), Euler
+// successor, cut at the root, and the ceil(log2 H) pointer-jumping rounds, separated by barriers instead of
+// kernel boundaries -- 17-21 launches of ~5 us each used to be most of the potentials' time.  Large tours run
+// cooperatively (grid-wide barriers, sx_gridbar.cuh; the grid is sized to the work); a tour of up to
+// kTourSmallH half-edges is ranked by ONE CTA with the ping-pong records in shared memory and __syncthreads
+// as the barrier.  Leaves the result in node[rounds & 1].
+__global__ void __launch_bounds__(kTourThreads)
+tree_tour_kernel(long long H, long long N, long long root, int rounds, TreeArrays a, GridBarrier *bar, int32_t *status) {
+    extern __shared__ __align__(16) unsigned char tour_raw[];
+    const bool single = gridDim.x == 1;
+    auto sync_all = [&]() { if (single) __syncthreads(); else grid_barrier(bar); };
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gsz = (long long)gridDim.x * blockDim.x;
+    for (long long v = gtid; v <= N; v += gsz) a.first[v] = -1;
+    sync_all();
+    for (long long p = gtid; p < H; p += gsz) {
         const unsigned long long v = a.sorted_origin[p];
         if (p == 0 || a.sorted_origin[p - 1] != v) a.first[v] = (int)p;
         a.pos[a.ho[p]] = (int)p;
     }
-}
-
-__global__ void tree_succ_kernel(long long H, TreeArrays a) {
-    for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < H;
-         h += (long long)gridDim.x * blockDim.x) {
+    sync_all();
+    for (long long h = gtid; h < H; h += gsz) {
         const long long twin = h ^ 1;
         const unsigned long long v = (unsigned long long)a.dest[h];
-        long long p2 = (long long)a.pos[twin] + 1;
-        if (p2 >= H || a.sorted_origin[p2] != v) p2 = a.first[v];
+        long long p2 = (long long)__ldcg(a.pos + twin) + 1;
+        if (p2 >= H || a.sorted_origin[p2] != v) p2 = __ldcg(a.first + v);
         const uint32_t succ = a.ho[p2];
-        a.pred[0][succ] = (int)h;
-        a.rank[0][h] = 1;
+        a.node[0][succ].pred = (int)h;
+        a.node[0][h].rank = 1;
     }
-}
-
-__global__ void tree_cut_kernel(long long root, TreeArrays a, int32_t *status) {
-    const int f = a.first[root];
-    if (f < 0) { *status = SX_ERR_NOT_SPANNING; return; }
-    a.pred[0][a.ho[f]] = -1;
-}
-
-__global__ void tree_jump_kernel(long long H, const double *__restrict__ sum_in, const int *__restrict__ rank_in,
-                                 const int *__restrict__ pred_in, double *__restrict__ sum_out,
-                                 int *__restrict__ rank_out, int *__restrict__ pred_out) {
-    for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < H;
-         h += (long long)gridDim.x * blockDim.x) {
-        const int p = pred_in[h];
-        double s = sum_in[h];
-        int r = rank_in[h], np = p;
-        if (p >= 0) {
-            s = sum_in[p] + s;
-            r += rank_in[p];
-            np = pred_in[p];
+    sync_all();
+    if (gtid == 0) {
+        const int f = __ldcg(a.first + root);
+        if (f < 0) *status = SX_ERR_NOT_SPANNING; else a.node[0][a.ho[f]].pred = -1;
+    }
+    sync_all();
+    if (single && H <= kTourSmallH) {
+        TourNode *in = reinterpret_cast<TourNode *>(tour_raw), *out = in + H;
+        for (long long h = threadIdx.x; h < H; h += blockDim.x) in[h] = ld_node(a.node[0] + h);
+        __syncthreads();
+        for (int r = 0; r < rounds; ++r) {
+            for (long long h = threadIdx.x; h < H; h += blockDim.x) {
+                TourNode me = in[h];
+                if (me.pred >= 0) {
+                    const TourNode pr = in[me.pred];
+                    me.sum = pr.sum + me.sum; me.rank += pr.rank; me.pred = pr.pred;
+                }
+                out[h] = me;
+            }
+            __syncthreads();
+            TourNode *t = in; in = out; out = t;
         }
-        sum_out[h] = s; rank_out[h] = r; pred_out[h] = np;
+        TourNode *res = (rounds & 1) ? a.node[1] : a.node[0];
+        for (long long h = threadIdx.x; h < H; h += blockDim.x) res[h] = in[h];
+        return;
+    }
+    const TourNode *in = a.node[0];
+    TourNode *out = a.node[1];
+    for (int r = 0; r < rounds; ++r) {
+        for (long long h = gtid; h < H; h += gsz) {
+            TourNode me = ld_node(in + h);
+            if (me.pred >= 0) {
+                const TourNode pr = ld_node(in + me.pred);
+                me.sum = pr.sum + me.sum; me.rank += pr.rank; me.pred = pr.pred;
+            }
+            out[h] = me;
+        }
+        sync_all();
+        TourNode *t = const_cast<TourNode *>(in); in = out; out = t;
     }
 }
 
-__global__ void tree_finalize_kernel(long long T, long long root, const double *__restrict__ sum,
-                                     const int *__restrict__ rank, const int *__restrict__ pred,
+__global__ void tree_finalize_kernel(long long T, long long root, const TourNode *__restrict__ node,
                                      const int *__restrict__ dest, double *__restrict__ y, int32_t *status) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
          t += (long long)gridDim.x * blockDim.x) {
         const long long ha = 2 * t, hb = 2 * t + 1;
-        if (pred[ha] != -1 || pred[hb] != -1) { *status = SX_ERR_NOT_SPANNING; continue; }
-        const long long down = rank[ha] < rank[hb] ? ha : hb;
-        y[dest[down]] = sum[down];
+        const TourNode na = node[ha], nb = node[hb];
+        if (na.pred != -1 || nb.pred != -1) { *status = SX_ERR_NOT_SPANNING; continue; }
+        y[dest[na.rank < nb.rank ? ha : hb]] = na.rank < nb.rank ? na.sum : nb.sum;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) y[root] = 0.0;
 }
@@ -133,17 +175,18 @@ __device__ __forceinline__ dd dd_add(dd a, double b) {           // error-free a
 __device__ __forceinline__ dd dd_add(dd a, dd b) { return dd_add(dd_add(a, b.hi), b.lo); }
 
 // w[pos] = supply of the node entered at tour position pos (down half-edges), 0 for up half-edges.
-__global__ void flow_scatter_kernel(long long T, const int *__restrict__ rank, const int *__restrict__ pred,
+__global__ void flow_scatter_kernel(long long T, const TourNode *__restrict__ node,
                                     const int *__restrict__ dest, const double *__restrict__ b, double *__restrict__ w,
                                     int32_t *status) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
          t += (long long)gridDim.x * blockDim.x) {
         const long long ha = 2 * t, hb = 2 * t + 1;
-        if (pred[ha] != -1 || pred[hb] != -1) { *status = SX_ERR_NOT_SPANNING; continue; }
-        const bool a_down = rank[ha] < rank[hb];
-        const long long down = a_down ? ha : hb, up = a_down ? hb : ha;
-        w[rank[down] - 1] = b[dest[down]];
-        w[rank[up] - 1] = 0.0;
+        const TourNode na = node[ha], nb = node[hb];
+        if (na.pred != -1 || nb.pred != -1) { *status = SX_ERR_NOT_SPANNING; continue; }
+        const bool a_down = na.rank < nb.rank;
+        const long long down = a_down ? ha : hb;
+        w[(a_down ? na.rank : nb.rank) - 1] = b[dest[down]];
+        w[(a_down ? nb.rank : na.rank) - 1] = 0.0;
     }
 }
 
@@ -174,15 +217,15 @@ __global__ void __launch_bounds__(1024) flow_scan_kernel(long long H, const doub
 }
 
 // flow(t) = +/- (P[rank(up) - 1] - P[rank(down) - 2]): supplies of the subtree below arc t.
-__global__ void flow_finalize_kernel(long long T, const int *__restrict__ rank, const int *__restrict__ dest,
+__global__ void flow_finalize_kernel(long long T, const TourNode *__restrict__ node,
                                      const double *__restrict__ phi, const double *__restrict__ plo,
                                      double *__restrict__ flow) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < T;
          t += (long long)gridDim.x * blockDim.x) {
         const long long ha = 2 * t, hb = 2 * t + 1;            // ha: minus -> plus, hb: plus -> minus
-        const bool a_down = rank[ha] < rank[hb];
-        const long long down = a_down ? ha : hb, up = a_down ? hb : ha;
-        const long long r1 = rank[down] - 1, r2 = rank[up] - 1;  // tour positions, r1 < r2
+        const int ra = node[ha].rank, rb = node[hb].rank;
+        const bool a_down = ra < rb;
+        const long long r1 = (a_down ? ra : rb) - 1, r2 = (a_down ? rb : ra) - 1;  // tour positions (down, up), r1 < r2
         dd top{phi[r2], plo[r2]};
         if (r1 > 0) top = dd_add(top, dd{-phi[r1 - 1], -plo[r1 - 1]});
         const double subtree = top.hi + top.lo;
@@ -206,7 +249,7 @@ extern "C" size_t sx_tree_potentials_workspace_bytes(int64_t N) {
     if (N < 0) return 0;
     const size_t H = 2 * (size_t)(N > 0 ? N : 1);
     return 2 * carve_bytes(H, 8) + carve_bytes(H, 4) * 3 + carve_bytes((size_t)N + 1, 4) +
-           2 * carve_bytes(H, 8) + 4 * carve_bytes(H, 4) + sx_argsort_workspace_bytes((int64_t)H) + 512;
+           2 * carve_bytes(H, 16) + sx_argsort_workspace_bytes((int64_t)H) + 1024;
 }
 
 // Shared by potentials and flows: half-edges, Euler tour cut at the root, pointer jumping.
@@ -223,9 +266,8 @@ static int tree_tour(const int64_t *tree, int64_t n_tree, const int32_t *tail, c
     a.dest = cv.take<int>(H);
     a.pos = cv.take<int>(H);
     a.first = cv.take<int>(N + 1);
-    a.sum[0] = cv.take<double>(H); a.sum[1] = cv.take<double>(H);
-    a.rank[0] = cv.take<int>(H);   a.rank[1] = cv.take<int>(H);
-    a.pred[0] = cv.take<int>(H);   a.pred[1] = cv.take<int>(H);
+    a.node[0] = cv.take<TourNode>(H); a.node[1] = cv.take<TourNode>(H);
+    GridBarrier *bar = cv.take<GridBarrier>(1);
     void *sort_ws = cv.base + cv.off;
     const size_t sort_ws_bytes = ws_bytes - cv.off;
 
@@ -236,20 +278,25 @@ static int tree_tour(const int64_t *tree, int64_t n_tree, const int32_t *tail, c
     while (bits < 32 && (1ll << bits) < N) ++bits;
     int rc = sx_argsort_u64(a.origin, H, bits, a.ho, a.sorted_origin, sort_ws, sort_ws_bytes, st);
     if (rc != SX_OK) return rc;
-    SX_CUDA(cudaMemsetAsync(a.first, 0xff, sizeof(int) * (size_t)(N + 1), st));
-    tree_first_kernel<<<tr_grid(H), kTrThreads, 0, st>>>(H, a);
-    SX_LAUNCH_CHECK();
-    tree_succ_kernel<<<tr_grid(H), kTrThreads, 0, st>>>(H, a);
-    SX_LAUNCH_CHECK();
-    tree_cut_kernel<<<1, 1, 0, st>>>(root, a, status_out);
-    SX_LAUNCH_CHECK();
     int rounds = 1;
     while ((1ll << rounds) < H) ++rounds;
-    cur = 0;
-    for (int r = 0; r < rounds; ++r, cur ^= 1) {
-        tree_jump_kernel<<<tr_grid(H), kTrThreads, 0, st>>>(H, a.sum[cur], a.rank[cur], a.pred[cur],
-                                                            a.sum[cur ^ 1], a.rank[cur ^ 1], a.pred[cur ^ 1]);
-        SX_LAUNCH_CHECK();
+    cur = rounds & 1;
+    SX_CUDA(cudaMemsetAsync(bar, 0, sizeof(GridBarrier), st));
+    long long H_ = H, N_ = N, root_ = root;
+    void *args[] = {(void *)&H_, (void *)&N_, (void *)&root_, (void *)&rounds, (void *)&a, (void *)&bar, (void *)&status_out};
+    if (H <= kTourSmallH) {
+        const size_t smem = (size_t)2 * H * sizeof(TourNode);
+        SX_CUDA(cudaFuncSetAttribute(tree_tour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(2 * kTourSmallH * sizeof(TourNode))));
+        SX_CUDA(cudaLaunchKernel((void *)tree_tour_kernel, dim3(1), dim3(kTourThreads), args, smem, st));
+    } else {
+        int occ = 0;
+        SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tree_tour_kernel, kTourThreads, 0));
+        if (occ < 1) return SX_ERR_NO_DEVICE;
+        long long grid = (H + kTourThreads - 1) / kTourThreads;
+        const long long max_grid = (long long)num_sms() * (occ > 2 ? 2 : occ);
+        if (grid > max_grid) grid = max_grid;
+        SX_CUDA(cudaLaunchCooperativeKernel((void *)tree_tour_kernel, dim3((unsigned)grid), dim3(kTourThreads), args, 0, st));
     }
     return SX_OK;
 }
@@ -289,8 +336,7 @@ extern "C" int sx_tree_potentials(const int64_t *tree, int64_t n_tree, const int
     int rc = tree_tour(tree, n_tree, tail, head, S, D, N, cost, ld, plus_convention, root, status_out, ws, ws_bytes, st,
                        a, cur);
     if (rc != SX_OK) return rc;
-    tree_finalize_kernel<<<tr_grid(n_tree), kTrThreads, 0, st>>>(n_tree, root, a.sum[cur], a.rank[cur], a.pred[cur],
-                                                                 a.dest, y_out, status_out);
+    tree_finalize_kernel<<<tr_grid(n_tree), kTrThreads, 0, st>>>(n_tree, root, a.node[cur], a.dest, y_out, status_out);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }
@@ -319,13 +365,13 @@ extern "C" int sx_tree_flows(const int64_t *tree, int64_t n_tree, const int32_t 
     if (rc != SX_OK) return rc;
     const long long T = n_tree, H = 2 * T;
     // scratch: the buffers of the finished ranking that are no longer needed
-    double *w = a.sum[cur ^ 1];
+    double *w = reinterpret_cast<double *>(a.node[cur ^ 1]);
     double *phi = reinterpret_cast<double *>(a.origin), *plo = reinterpret_cast<double *>(a.sorted_origin);
-    flow_scatter_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, a.rank[cur], a.pred[cur], a.dest, b, w, status_out);
+    flow_scatter_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, a.node[cur], a.dest, b, w, status_out);
     SX_LAUNCH_CHECK();
     flow_scan_kernel<<<1, 1024, 0, st>>>(H, w, phi, plo);
     SX_LAUNCH_CHECK();
-    flow_finalize_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, a.rank[cur], a.dest, phi, plo, flow_out);
+    flow_finalize_kernel<<<tr_grid(T), kTrThreads, 0, st>>>(T, a.node[cur], phi, plo, flow_out);
     SX_LAUNCH_CHECK();
     return SX_OK;
 }

@@ -141,8 +141,18 @@ def test_c2_784_scores_queue_tree_potentials(dev):
     assert np.array_equal(res.topk_id, small["topk_ids_pert"])
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 70001, 1 << 20])
-def test_argsort_edge_sizes_and_special_values(dev, n):
+@pytest.fixture(params=["one launch", "launch per pass"])
+def sort_mode(request):
+    """Mid-size sorts (8 K < n <= ~1.2 M keys) run every pass in one cooperative launch; the other parameter
+    forces the upsweep / scan / downsweep launches that larger inputs use."""
+    from smart_crossover._native import lib
+    assert lib.sx_sort_set_tuning(1 if request.param == "one launch" else 0) == 0
+    yield request.param
+    assert lib.sx_sort_set_tuning(1) == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 8192, 8193, 70001, 614656, 1 << 20, 1212416, 1212417])
+def test_argsort_edge_sizes_and_special_values(dev, sort_mode, n):
     rng = np.random.default_rng(n)
     key = rng.integers(-3, 4, size=n).astype(np.float64) * rng.choice([0.5, 1.0, 1e-300], size=n)
     if n > 8:
@@ -160,6 +170,27 @@ def test_argsort_edge_sizes_and_special_values(dev, n):
     assert np.array_equal(got[~np.isnan(got)], key[ref][~np.isnan(got)])
     if not np.isnan(key).any():
         assert np.array_equal(u32(korder), orc.kruskal_order(key))
+
+
+@pytest.mark.parametrize("n,bits", [(3134, 11), (8192, 13), (20000, 20), (300000, 33), (1 << 20, 63), (100, 63)])
+def test_argsort_u64_partial_key_bits(dev, sort_mode, n, bits):
+    """sx_argsort_u64 looks at ceil(bits / 8) low bytes only (ties among them by index), on every size path."""
+    import ctypes
+    from smart_crossover._native import check, lib
+    rng = np.random.default_rng(bits)
+    key = rng.integers(0, 1 << min(bits, 62), size=n, dtype=np.int64).astype(np.uint64)
+    key[::5] |= np.uint64(1) << np.uint64(63)                     # bits above the sorted range must be ignored ...
+    passes = max(2, (bits + 7) // 8)
+    masked = key & np.uint64((1 << (8 * passes)) - 1 if passes < 8 else 0xFFFFFFFFFFFFFFFF)
+    ref = np.argsort(masked, kind="stable")
+    kt = torch.from_numpy(key.view(np.int64)).cuda()
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    skey = torch.empty(n, dtype=torch.int64, device="cuda")
+    ws = torch.empty(lib.sx_argsort_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    check(lib.sx_argsort_u64(dev._ptr(kt), n, bits, dev._ptr(order), dev._ptr(skey), dev._ptr(ws), ws.numel(),
+                             dev._stream()), "sx_argsort_u64")
+    assert np.array_equal(u32(order), ref)
+    assert np.array_equal(skey.cpu().numpy().view(np.uint64), key[ref])           # ... but travel with the key
 
 
 def test_kruskal_order_long_runs(dev):
