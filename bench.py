@@ -261,7 +261,23 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # tree-basis build timing (single GPU): scores -> argsort -> Kruskal order -> tree -> potentials
 # ------------------------------------------------------------------------------------------------
-def time_tree_build(S, D, device, reps=3):
+def cpu_tree_build_ot(x, s, d, M, S, D, note):
+    """Oracle port of the same steps on ONE host core: scores (net_manager.py:377-378), stable argsort
+    (:379), Kruskal on the stable order of -w (tree_BI.py:47-57), potentials of the tree (B^T y = c_B)."""
+    from oracle import network_oracle as orc
+    t = [time.perf_counter()]
+    F = orc.ot_flow_scores(x, s, d); t.append(time.perf_counter())
+    q = orc.stable_queue(F); t.append(time.perf_counter())
+    tree = orc.max_weight_spanning_tree(F, S, D, drop_zero_weight=False); t.append(time.perf_counter())
+    orc.ot_tree_potentials(tree, M); t.append(time.perf_counter())
+    names = ["score", "argsort", "kruskal (incl. its own stable argsort)", "potentials"]
+    return {"ms": round(1e3 * (t[-1] - t[0]), 2), "breakdown_ms": {n: round(1e3 * (t[i + 1] - t[i]), 2) for i, n in enumerate(names)},
+            "cores": 1, "kind": "port", "host_cpus": os.cpu_count(), "sample": note}
+
+
+def time_tree_build(S, D, device, reps=3, cpu=None):
+    """`cpu`: None = no CPU leg; (S_cpu, D_cpu) = time the oracle port on an instance of that shape (the same
+    instance when equal to (S, D), else a smaller stand-in built the same way)."""
     import torch
     from smart_crossover import device as dev
     P, Q, a = make_points(S, D, device, seed=20260002)
@@ -324,7 +340,27 @@ def time_tree_build(S, D, device, reps=3):
     names_full = ["score", "argsort", "kruskal_order", "kruskal", "potentials"]
     from smart_crossover.network_methods.tree_BI import use_prefix_path
     prefix = use_prefix_path(S * D, N)                      # what tree_basis_identify runs on bare weights
+    cpu_leg = None
+    if cpu is not None:
+        if tuple(cpu) == (S, D):
+            cpu_leg = cpu_tree_build_ot(x.cpu().numpy(), s.cpu().numpy(), d.cpu().numpy(), M.cpu().numpy(), S, D,
+                                        "the same instance, copied to the host")
+        else:
+            Sc, Dc = cpu
+            Pc, Qc, _ = make_points(Sc, Dc, device, seed=20260002)
+            Mc = make_slab(Pc, Qc, 0, Sc)
+            gc_ = torch.Generator(device=device).manual_seed(99)
+            sc = torch.rand(Sc, generator=gc_, device=device, dtype=torch.float64) + 0.1
+            dc = torch.rand(Dc, generator=gc_, device=device, dtype=torch.float64) + 0.1
+            sc /= sc.sum(); dc /= dc.sum()
+            tc = 1.0 + 40.0 * (Mc / 0.33)
+            xc = ((sc[:, None] * dc[None, :]) / (tc * tc * tc * tc)).reshape(-1)
+            cpu_leg = cpu_tree_build_ot(xc.cpu().numpy(), sc.cpu().numpy(), dc.cpu().numpy(), Mc.cpu().numpy(), Sc, Dc,
+                                        f"stand-in {Sc}x{Dc} ({Sc * Dc} arcs) built like the {S}x{D} instance: the "
+                                        f"full-size oracle run takes minutes (SURVEY.md section 8d)")
+            cpu_leg["arcs"] = Sc * Dc
     return {"workload": f"OT {S}x{D} ({S * D} arcs)", "ms": round(sum(best) if prefix else sum(full), 4),
+            "cpu_baseline": cpu_leg,
             "path": "kruskal_prefix" if prefix else "full_argsort",
             "kruskal_prefix_ms": round(sum(best), 4),
             "breakdown_ms": {n: round(v, 4) for n, v in zip(names, best)},
@@ -332,7 +368,62 @@ def time_tree_build(S, D, device, reps=3):
             "with_full_argsort_breakdown_ms": {n: round(v, 4) for n, v in zip(names_full, full)}}
 
 
-def time_mcf_path(N, E, device, reps=3):
+def time_price_arcs_planted(N, E, device, frac=1e-4, reps=20):
+    """`price_arcs_kernel` (17 B per arc: c 8 + tail 4 + head 4 + status 1; y gathers from L2) on planted
+    near-optimal duals: c_k = (y_tail - y_head) + slack_k with slack >= 0, and `frac` of the arcs pushed below
+    -tol -- the converged regime a column-generation pass sees, not the 44 % violators of the flow-score tree."""
+    import torch
+    from smart_crossover import device as dev
+    g = torch.Generator(device=device).manual_seed(20260303)
+    tail = torch.randint(0, N, (E,), generator=g, device=device, dtype=torch.int32)
+    head = (tail + 1 + torch.randint(0, N - 1, (E,), generator=g, device=device, dtype=torch.int32)) % N
+    y = torch.rand(N, generator=g, device=device, dtype=torch.float64) * 100.0
+    slack = torch.rand(E, generator=g, device=device, dtype=torch.float64) + 1e-3
+    viol = torch.rand(E, generator=g, device=device, dtype=torch.float64) < frac
+    slack = torch.where(viol, -slack, slack)
+    c = (y[tail.long()] - y[head.long()]) + slack
+    del slack
+    vb = torch.full((E,), -1, dtype=torch.int8, device=device)
+    pr = dev.Pricer(device, 1024, fused=False)
+    for _ in range(3):
+        pr.reset(); pr.price_arcs(c, tail, head, vb, y)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        pr.reset()
+        a.record()
+        pr.price_arcs(c, tail, head, vb, y)
+        b.record()
+    pr.select()
+    torch.cuda.synchronize()
+    res = pr.fetch()
+    ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
+    exact = int(((c - (y[tail.long()] - y[head.long()])) < -TOL).sum().item())
+    assert res.n_violating == exact, (res.n_violating, exact)
+    peak, _ = measured_peak_gbs()
+    gbs = 17.0 * E / (ms * 1e-3) / 1e9
+    return {"arcs": E, "nodes": N, "violating_arcs": res.n_violating, "kernel_ms": round(ms, 4),
+            "arcs_per_s": E / (ms * 1e-3), "algorithmic_bytes_per_arc": 17, "achieved_GBs": round(gbs, 1),
+            "frac_of_measured_peak": round(gbs / peak, 4),
+            "l2": f"inputs {17 * E / 1e6:.0f} MB vs 126 MB L2" + (" (L2-resident between repetitions)" if 17 * E < 1.2e8 else "")}
+
+
+def cpu_mcf_path(tail, head, c, u, x, A, N):
+    """Oracle port on ONE host core: MCF flow indicators (net_manager.py:156-182), stable argsort (:184),
+    Kruskal over the stable order of -w, potentials of the forest's tree."""
+    from oracle import network_oracle as orc
+    t = [time.perf_counter()]
+    ind = orc.mcf_flow_scores(x, u, A); t.append(time.perf_counter())
+    orc.stable_queue(ind); t.append(time.perf_counter())
+    tree = orc.spanning_forest(orc.kruskal_order(ind), N, tail=tail, head=head); t.append(time.perf_counter())
+    if tree.size == N - 1:
+        orc.tree_potentials(tail[tree], head[tree], c[tree], N, N - 1)
+    t.append(time.perf_counter())
+    names = ["score", "argsort", "kruskal (incl. its own stable argsort)", "potentials"]
+    return {"ms": round(1e3 * (t[-1] - t[0]), 1), "breakdown_ms": {n: round(1e3 * (t[i + 1] - t[i]), 1) for i, n in enumerate(names)},
+            "cores": 1, "kind": "port", "host_cpus": os.cpu_count(), "sample": "the same instance (built on the host)"}
+
+
+def time_mcf_path(N, E, device, reps=3, cpu=False):
     """BASELINE.json configs[2] shape (NETGEN-style 1M nodes / 10M arcs): scoring, sort, spanning
     forest, potentials and arc pricing on one GPU, CUDA-event times (best of `reps`)."""
     import scipy.sparse as sp
@@ -375,10 +466,16 @@ def time_mcf_path(N, E, device, reps=3):
             best = parts
     res = pr.fetch()
     names = ["score", "argsort", "kruskal_order", "kruskal", "potentials", "price_arcs", "topk"]
+    cpu_leg = cpu_mcf_path(tail, head, c, u, x, A.astype(np.float64), N) if cpu else None
+    del xs, us, cs, t32, h32, ptr, arc, sgn, vb
+    torch.cuda.empty_cache()
+    planted = [time_price_arcs_planted(N, E, device), time_price_arcs_planted(10 * N, 10 * E, device, reps=10)]
     return {"workload": f"NETGEN-style MCF {N} nodes / {E} arcs", "tree_build_ms": round(sum(best[:5]), 4),
-            "breakdown_ms": {n: round(v, 4) for n, v in zip(names, best)},
+            "breakdown_ms": {n: round(v, 4) for n, v in zip(names, best)}, "cpu_baseline": cpu_leg,
             "price_arcs_per_s": E / ((best[5] + best[6]) * 1e-3), "violating_arcs": res.n_violating,
-            "price_arcs_bytes_per_arc": 17}
+            "price_arcs_note": "duals of the flow-score tree: 44 % of the arcs violate, every tile on the violator "
+                               "path; see price_arcs_planted for the kernel's streaming rate",
+            "price_arcs_bytes_per_arc": 17, "price_arcs_planted": planted}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -428,9 +525,10 @@ def main():
         assert _lib.sx_kruskal_set_tuning(args.kruskal_chunk) == 0
     if args.tree_only:
         if args.tree_only < 0:                           # --tree-only -1: the MCF configuration (1M nodes / 10M arcs)
-            print(json.dumps(time_mcf_path(1_000_000, 10_000_000, device, reps=2)), flush=True)
+            print(json.dumps(time_mcf_path(1_000_000, 10_000_000, device, reps=2, cpu=not args.no_cpu)), flush=True)
             return
-        print(json.dumps(time_tree_build(args.tree_only, args.tree_only, device, reps=2)), flush=True)
+        T = args.tree_only
+        print(json.dumps(time_tree_build(T, T, device, reps=2, cpu=None if args.no_cpu else (min(T, 3000),) * 2)), flush=True)
         return
 
     def host_barrier():
@@ -471,8 +569,10 @@ def main():
     tree = None
     if world == 1 and not args.no_tree:
         torch.cuda.empty_cache()
-        tree = [time_tree_build(784, 784, device), time_tree_build(20000, 20000, device, reps=1),
-                time_mcf_path(1_000_000, 10_000_000, device, reps=1)]
+        cpu = not args.no_cpu
+        tree = [time_tree_build(784, 784, device, cpu=(784, 784) if cpu else None),
+                time_tree_build(20000, 20000, device, reps=1, cpu=(3000, 3000) if cpu else None),
+                time_mcf_path(1_000_000, 10_000_000, device, reps=1, cpu=cpu)]
 
     def roofline_of(leg):
         achieved = 8.0 * leg["S_loc"] * leg["D"] / (leg["kernel_ms"] * 1e-3) / 1e9

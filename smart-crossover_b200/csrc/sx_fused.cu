@@ -33,7 +33,8 @@
 
 namespace sx {
 
-constexpr int kFusedDirectCap = 8192;   // candidate lists up to this length are ranked as they are
+constexpr int kFusedDirectCap = 2048;   // candidate lists up to this length are ranked as they are (the all-pairs
+                                        // rank is quadratic: 6990 candidates took 45 us, the filter path 12)
 constexpr int kFusedSurvCap   = 4096;   // survivors of the filter the in-kernel rank takes (64 KB list)
 constexpr int kFusedTile      = 2048;   // elements staged in shared memory at a time (32 KB)
 constexpr int kMergeCtas      = 64;     // CTAs (from the end of the grid) that merge the G blocks
