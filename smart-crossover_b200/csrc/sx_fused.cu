@@ -42,7 +42,8 @@ constexpr int kMergeCtas      = 64;     // CTAs (from the end of the grid) that 
 struct FusedCtl {
     unsigned long long pass;      // passes completed; parity selects the selection state in use
     GridBarrier        bar;       // grid-wide barrier (sx_gridbar.cuh)
-    unsigned int       pad[4];
+    unsigned int       dyn_ctr;   // tail stealing of the pricing walk: next dynamically assigned tile (0 between passes)
+    unsigned int       pad[3];
     unsigned long long ts[8];     // diagnostics: %globaltimer of CTA 0 at the phase boundaries of the last pass
 };
 struct FusedState {
@@ -66,6 +67,7 @@ struct FusedParams {
     long long       *merged;         // [K rc bits | K ids | n_out | total count, min key, largest count, status]
     int             *xstatus;        // SX_ERR_PEER_TIMEOUT lands here
     unsigned long long timeout_ns;
+    int              steal;          // 1: the last eighth of the tiles is handed out dynamically
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
@@ -118,6 +120,7 @@ price_fused_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p
     DenseParams p = p0;
     p.sink.hdr = &sel->hdr;
     p.sink.sel = sel;
+    p.dyn_ctr = f.steal ? &ctl->dyn_ctr : nullptr;
     price_tiles<ROWS, STAGES, CWARPS, false>(tmap, p, smem_raw);
     stamp(ctl, 1);
 
@@ -127,6 +130,7 @@ price_fused_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p
         // every CTA has read `pass` and the exchange epoch: advance them for the next launch (the merge
         // epoch [2] moves with the push epoch [0]: this kernel is both sides of the exchange)
         *reinterpret_cast<volatile unsigned long long *>(&ctl->pass) = pass + 1ull;
+        *reinterpret_cast<volatile unsigned int *>(&ctl->dyn_ctr) = 0u;      // every CTA is past its pricing walk
         if (ll_ctr) {
             *reinterpret_cast<volatile unsigned long long *>(ll_ctr) = epoch;
             if (f.merged) *reinterpret_cast<volatile unsigned long long *>(ll_ctr + 2) = epoch;
@@ -414,7 +418,7 @@ extern "C" int sx_price_dense_ot_fused(const double *M, int64_t ld, int64_t row0
     p.y_src = y_src; p.y_dst = y_dst; p.S_loc = S_loc; p.D = D; p.row0 = row0; p.thr = -tol;
     p.sink.hdr = nullptr; p.sink.sel = nullptr;                   // set on the device from the pass parity
     p.sink.rc = cand_rc; p.sink.id = (int64_t *)cand_id; p.sink.cap = cand_cap;
-    p.rc_out = nullptr; p.ld_out = 0; p.zero = 0; p.evict_first = 1;
+    p.rc_out = nullptr; p.ld_out = 0; p.zero = 0; p.evict_first = 1; p.dyn_ctr = nullptr;
     p.n_col_blocks = (D + kBoxCols - 1) / kBoxCols;
     p.n_row_tiles = (S_loc + kFRows - 1) / kFRows;
     CUtensorMap map;
@@ -426,6 +430,9 @@ extern "C" int sx_price_dense_ot_fused(const double *M, int64_t ld, int64_t row0
     f.K = (unsigned)K; f.block = (long long *)block; f.surv = (KeyId *)ws;
     f.peer_bufs = (char *const *)peer_bufs_dev; f.rank = rank; f.G = peer_bufs_dev ? G : 1; f.block_len = block_len;
     f.merged = (long long *)merged_out; f.xstatus = (int *)status_dev; f.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    static int steal = -1;
+    if (steal < 0) { const char *e = getenv("SX_FUSED_STEAL"); steal = (e && e[0] == '0') ? 0 : 1; }
+    f.steal = steal;
 
     auto kern = price_fused_kernel<kFRows, kFStages, kFWarps, kFMinB>;
     constexpr size_t smem = tma_smem_bytes(kFRows, kFStages, kFWarps);

@@ -291,6 +291,7 @@ extern "C" int sx_price_dense_ot(const double *M, int64_t ld, int64_t row0, int6
     p.sink.hdr = header; p.sink.sel = (SelState *)sel; p.sink.rc = cand_rc; p.sink.id = (int64_t *)cand_id;
     p.sink.cap = cand_cap;
     p.rc_out = rc_out; p.ld_out = ld_out; p.zero = 0; p.evict_first = (uint32_t)g_tma_evict_first;
+    p.dyn_ctr = nullptr;
     p.n_col_blocks = (D + kBoxCols - 1) / kBoxCols;
 
     int rc = SX_OK;

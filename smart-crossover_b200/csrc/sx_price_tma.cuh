@@ -192,6 +192,7 @@ struct DenseParams {
     long long     n_col_blocks, n_row_tiles;
     uint32_t      zero;    // 0, but only the host knows: see mbar_arrive_after
     uint32_t      evict_first;
+    unsigned int *dyn_ctr; // tail stealing: device counter (0 at kernel start) or nullptr = static walk only
 };
 
 // Lazy epilogue of one warp's share of a tile: RPT rows x 2 columns per thread already in registers
@@ -251,18 +252,29 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
 
     // Grid-stride tile walk, tile t = row_tile * n_col_blocks + col_block: at any time the CTAs of
     // the grid read neighbouring 2 KB segments of the same few matrix rows (DRAM page locality).
+    // With p.dyn_ctr the last eighth of the tiles is not assigned up front but handed out by an atomic
+    // counter ("tail stealing"): SMs stream at visibly different rates (the slowest CTA of a static walk
+    // finishes 3-7 % after the fastest, and everybody waits for it at the grid barrier that follows), so
+    // the fast ones take more of the tail.  The producer publishes each dynamic tile's index in shared
+    // memory before it arms the stage's barrier; consumers read it after the barrier's wait.
     const long long total = p.n_row_tiles * p.n_col_blocks;
     const long long G = gridDim.x;
     long long rt = (long long)blockIdx.x / p.n_col_blocks;
     long long cb = (long long)blockIdx.x - rt * p.n_col_blocks;
     const long long d_rt = G / p.n_col_blocks, d_cb = G - d_rt * p.n_col_blocks;
+    const bool dynamic = p.dyn_ctr != nullptr;
+    // static tiles of this CTA: all of its grid-stride share, or 7/8 of the common share when the tail is dynamic
+    const long long share = total / G;
+    const long long n_static = dynamic ? share - share / 8 : (total - (long long)blockIdx.x + G - 1) / G;
+    const long long dyn_base = n_static * G;                                 // first dynamically assigned tile
+    volatile long long *ticket = reinterpret_cast<volatile long long *>(scratch + CWARPS);
 
     if (warp == CWARPS) {
         // ===== producer warp: one elected lane issues the TMA loads =====
         if (lane_id() == 0) {
             const uint64_t pol = p.evict_first ? l2_evict_first_policy() : l2_evict_normal_policy();
             uint32_t it = 0;
-            for (long long t = blockIdx.x; t < total; t += G, ++it) {
+            for (long long k = 0; k < n_static; ++k, ++it) {
                 const int s = it % STAGES;
                 if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
                 mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
@@ -271,6 +283,21 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
                 rt += d_rt; cb += d_cb;
                 if (cb >= p.n_col_blocks) { cb -= p.n_col_blocks; ++rt; }
             }
+            if (dynamic) {
+                long long t_next = dyn_base + (long long)atomicAdd(p.dyn_ctr, 1u);
+                for (;; ++it) {
+                    const int s = it % STAGES;
+                    const long long t = t_next;
+                    if (t < total) t_next = dyn_base + (long long)atomicAdd(p.dyn_ctr, 1u);   // in flight during the waits
+                    if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+                    ticket[s] = t < total ? t : -1;
+                    if (t >= total) { mbar_arrive_after(&full_bar[s], 0u); break; }          // sentinel: no data follows
+                    const long long trt = t / p.n_col_blocks, tcb = t - trt * p.n_col_blocks;
+                    mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    tma_load_2d(stage_base + (size_t)s * ROWS * kBoxCols, &tmap, &full_bar[s],
+                                (int)(tcb * kBoxCols), (int)(trt * ROWS), pol);
+                }
+            }
         }
     } else {
         // ===== consumer warps =====
@@ -278,9 +305,8 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
         const int rg = threadIdx.x >> 7;             // row group
         double    tmin = INFINITY, lim = INFINITY;
         WarpTally tally;
-        uint32_t  it = 0;
-        for (long long t = blockIdx.x; t < total; t += G, ++it) {
-            const int s = it % STAGES;
+        // one tile: (rt, cb) in stage s of pipeline iteration it; `waited` = the stage's data is known to be there
+        auto process = [&](long long rt, long long cb, int s, uint32_t it, bool waited) {
             const long long j0 = cb * kBoxCols + 2 * c;
             const long long i0 = rt * ROWS + (long long)rg * RPT;
             const bool interior = (cb + 1) * kBoxCols <= p.D && (rt + 1) * ROWS <= p.S_loc;   // CTA-uniform
@@ -298,7 +324,7 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
 #pragma unroll
                 for (int r = 0; r < RPT; ++r) u[r] = (i0 + r < p.S_loc) ? __ldg(p.y_src + i0 + r) : 0.0;
             }
-            mbar_wait(&full_bar[s], (it / STAGES) & 1);
+            if (!waited) mbar_wait(&full_bar[s], (it / STAGES) & 1);
             const double2 *tile = reinterpret_cast<const double2 *>(stage_base + (size_t)s * ROWS * kBoxCols) +
                                   (size_t)rg * RPT * (kBoxCols / 2) + c;
             double2 m[RPT];
@@ -345,8 +371,22 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
                 }
             }
             tile_epilogue<RPT>(p, tally, tmin, lim, rc0, rc1, hit, (p.row0 + i0) * p.D + j0, p.D);
+        };
+        uint32_t it = 0;
+        for (long long k = 0; k < n_static; ++k, ++it) {
+            process(rt, cb, (int)(it % STAGES), it, false);
             rt += d_rt; cb += d_cb;
             if (cb >= p.n_col_blocks) { cb -= p.n_col_blocks; ++rt; }
+        }
+        if (dynamic) {
+            for (;; ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                const long long t = ticket[s];
+                if (t < 0) break;
+                const long long trt = t / p.n_col_blocks;
+                process(trt, t - trt * p.n_col_blocks, s, it, true);
+            }
         }
         warp_flush(p.sink, tally);
         const long long k = warp_min(f64_to_min_key(tmin));
@@ -364,7 +404,7 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
 
 constexpr size_t tma_smem_bytes(int rows, int stages, int cwarps) {
     return (size_t)stages * rows * kBoxCols * sizeof(double) + 2 * (size_t)stages * sizeof(uint64_t) +
-           (size_t)cwarps * sizeof(long long) + 64;
+           (size_t)cwarps * sizeof(long long) + (size_t)stages * sizeof(long long) + 64;   // + tile tickets
 }
 
 
