@@ -767,6 +767,30 @@ def test_fused_pass_sequence_on_one_pricer(dev, K):
         assert np.array_equal(res.topk_id, ids) and res.topk_rc.tobytes() == vals.tobytes(), f"pass {it}"
 
 
+@pytest.mark.parametrize("E,off", [(100003, 0), (4096, 0), (7, 0), (50001, 1), (50002, 2)])
+def test_price_arcs_vector_and_scalar_paths(dev, E, off):
+    """Arc-list pricing takes 128-bit loads over the bulk of 16-byte aligned arrays and scalar loads for the last
+    < 4 arcs or misaligned views (`off` shifts every array by that many elements): same reduced costs (bitwise),
+    count, min and top-K either way."""
+    N, K = 5000, 100
+    rng = np.random.default_rng(E + off)
+    tail = rng.integers(0, N, E + off).astype(np.int32)
+    head = ((tail + 1 + rng.integers(0, N - 1, E + off)) % N).astype(np.int32)
+    c = rng.integers(1, 100, E + off).astype(np.float64)
+    y = rng.random(N) * 60.0
+    vb = rng.choice(np.array([-1, -2, 0], dtype=np.int8), E + off, p=[0.8, 0.1, 0.1])
+    ct, tt, ht, vt = cu(c)[off:], cu(tail)[off:], cu(head)[off:], cu(vb)[off:]
+    rc_ref = orc.reduced_costs_arcs(c[off:], tail[off:], head[off:], y, vb[off:])
+    cnt, mn, ids, vals = orc.price_summary(rc_ref, K)
+    res = dev.price_arcs(ct, tt, ht, cu(y), vbasis=vt, K=K, want_rc=True)
+    assert res.rc.cpu().numpy().tobytes() == rc_ref.tobytes()
+    assert res.n_violating == cnt and res.min_rc == mn
+    assert np.array_equal(res.topk_id, ids) and res.topk_rc.tobytes() == vals.tobytes()
+    res = dev.price_arcs(ct, tt, ht, cu(y), vbasis=None, K=K)              # no basis statuses
+    cnt, mn, ids, vals = orc.price_summary(orc.reduced_costs_arcs(c[off:], tail[off:], head[off:], y), K)
+    assert res.n_violating == cnt and np.array_equal(res.topk_id, ids)
+
+
 @pytest.mark.parametrize("name", MCF_FULL)
 def test_mcf_scores_queue_and_arc_pricing_golden(dev, name):
     import scipy.sparse as sp
