@@ -252,7 +252,7 @@ price_fused_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p
         }
     }
 
-    if (blockIdx.x == gridDim.x - 1 && tid == 0) ctl->ts[6] = global_timer_ns();
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) ctl->ts[6] = global_timer_ns();   // overwritten at the end of the merge
     // ---- merge of the G blocks out of the local exchange buffer (replaces sx_topk_merge_ll) ----
     if (f.peer_bufs == nullptr || f.merged == nullptr) return;
     const int n_merge = gridDim.x < kMergeCtas ? (int)gridDim.x : kMergeCtas;
@@ -275,25 +275,33 @@ price_fused_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p
         w_id = ll_load_slot(ll_slot(ll_local, f, epoch, g, (long long)K + (e_lo + tid - g * K)));
     }
     {
+        // kBatch slots are requested together and the whole batch is requested again until every slot carries
+        // this epoch's flag: the merge CTAs start polling while the peers are still ranking, and re-polling the
+        // late slots one by one would cost one L2 round trip each (28 per thread at G = 8: 20 us; measured).
         constexpr int kBatch = 8;
         int real = 0;
         for (int e0 = tid; e0 < GK; e0 += nthr * kBatch) {
             uint4 w[kBatch];
+            for (;;) {
+                bool all = true;
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int e = e0 + u * nthr;
-                if (e < GK) { const int g = e / K; w[u] = ll_load_slot(ll_slot(ll_local, f, epoch, g, e - g * K)); }
+                for (int u = 0; u < kBatch; ++u) {
+                    const int e = e0 + u * nthr;
+                    if (e < GK) { const int g = e / K; w[u] = ll_load_slot(ll_slot(ll_local, f, epoch, g, e - g * K)); }
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int e = e0 + u * nthr;
+                    if (e < GK && !ll_ready(w[u], flag)) all = false;
+                }
+                if (all) break;
+                if (global_timer_ns() - t_start > f.timeout_ns) { ok = false; break; }
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const int e = e0 + u * nthr;
                 if (e >= GK) continue;
-                unsigned long long bits = ll_value(w[u]);
-                if (!ll_ready(w[u], flag)) {
-                    const int g = e / K;
-                    ok = ll_poll(ll_slot(ll_local, f, epoch, g, e - g * K), flag, bits, t_start, f.timeout_ns) && ok;
-                    if (!ok) bits = 0x7ff0000000000000ull;
-                }
+                const unsigned long long bits = ll_ready(w[u], flag) ? ll_value(w[u]) : 0x7ff0000000000000ull;
                 const unsigned long long key = f64_to_sort_key(__longlong_as_double((long long)bits));
                 mkey[e] = key;
                 real += key != kPadKey;
@@ -359,6 +367,7 @@ price_fused_kernel(const __grid_constant__ CUtensorMap tmap, const DenseParams p
         }
     }
     if (!ok) atomicExch(f.xstatus, SX_ERR_PEER_TIMEOUT);
+    if (mc == n_merge - 1 && tid == 0) ctl->ts[6] = global_timer_ns();      // end of the merge (diagnostics)
 }
 
 __global__ void __launch_bounds__(256) fused_init_kernel(FusedState *st, unsigned K) {

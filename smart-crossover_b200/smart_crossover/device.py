@@ -266,7 +266,7 @@ class Pricer:
         t = self.fstate[off:off + 64].view(torch.int64).cpu().numpy()
         names = ["pricing", "barrier1", "bound+filter", "barrier2", "rank+emit"]
         out = {n: round(float(t[i + 1] - t[i]) * 1e-3, 2) for i, n in enumerate(names)}
-        out["last_cta_end_minus_cta0_rank_end"] = round(float(t[6] - t[5]) * 1e-3, 2)
+        out["last_cta_end_(after_merge_if_any)_minus_cta0_rank_end"] = round(float(t[6] - t[5]) * 1e-3, 2)
         out["gap_since_previous_pass_end"] = round(float(t[0] - t[7]) * 1e-3, 2)
         return out
 
