@@ -85,9 +85,24 @@ int alloc_candidates(sx_ot_pricer *p, DevCtx *c, int64_t cap) {
 int run_pass(sx_ot_pricer *p, DevCtx *c) {
     const int64_t Kp = p->Kp, D = p->D;
     // the duals this device needs: its own rows' source duals + every sink dual (pageable -> pinned)
-    memcpy(c->h_y, p->y_src_h + c->row0, (size_t)c->S_loc * 8);
-    memcpy(c->h_y + c->S_loc, p->y_dst_h, (size_t)D * 8);
-    SX_CUDA(cudaMemcpyAsync(c->y_loc, c->h_y, (size_t)(c->S_loc + D) * 8, cudaMemcpyHostToDevice, c->st));
+    // staged in chunks so that the DMA of one chunk overlaps the host copy of the next (the upload of the
+    // duals is most of what a pass costs beyond the kernel: 0.5-1 MB per GPU)
+    {
+        const size_t total = (size_t)(c->S_loc + D), chunk = 16384;          // 128 KB
+        for (size_t off = 0; off < total; off += chunk) {
+            const size_t len = total - off < chunk ? total - off : chunk;
+            for (size_t done = 0; done < len;) {                                // [off, off + len) spans the two host vectors
+                const size_t pos = off + done;
+                const bool in_src = pos < (size_t)c->S_loc;
+                const size_t left = in_src ? (size_t)c->S_loc - pos : total - pos;
+                const size_t n = left < len - done ? left : len - done;
+                const double *from = in_src ? p->y_src_h + c->row0 + pos : p->y_dst_h + (pos - (size_t)c->S_loc);
+                memcpy(c->h_y + pos, from, n * 8);
+                done += n;
+            }
+            SX_CUDA(cudaMemcpyAsync(c->y_loc + off, c->h_y + off, len * 8, cudaMemcpyHostToDevice, c->st));
+        }
+    }
     const int64_t cap = p->K > 0 ? p->cap : 0;
     int32_t *xstatus = reinterpret_cast<int32_t *>(c->merged + 2 * Kp + 5);
     if (p->mode == kFused) {
