@@ -407,6 +407,48 @@ def time_price_arcs_planted(N, E, device, frac=1e-4, reps=20):
             "l2": f"inputs {17 * E / 1e6:.0f} MB vs 126 MB L2" + (" (L2-resident between repetitions)" if 17 * E < 1.2e8 else "")}
 
 
+def time_sinkhorn(S, D, device, iters=20):
+    """The device Sinkhorn warm start (`sx_sinkhorn_ot`; the reference's driver calls POT for it,
+    scripts/run_network_crossover.py:96): ms per Sinkhorn-Knopp iteration = two streaming passes over the fp64
+    cost matrix (column log-sum-exp, row log-sum-exp), 16 B per arc and iteration.  Parity of this function is
+    UNPINNED (POT is not installed anywhere reachable): its oracle restates POT's published loop."""
+    import ctypes
+    import torch
+    from smart_crossover import device as dev
+    from smart_crossover._native import check, lib
+    P, Q, a = make_points(S, D, device, seed=20260004)
+    M = make_slab(P, Q, 0, S)
+    g_ = torch.Generator(device=device).manual_seed(5)
+    sa = torch.rand(S, generator=g_, device=device, dtype=torch.float64) + 0.1
+    sb = torch.rand(D, generator=g_, device=device, dtype=torch.float64) + 0.1
+    sa /= sa.sum(); sb /= sb.sum()
+    f = torch.empty(S, dtype=torch.float64, device=device)
+    gg = torch.empty(D, dtype=torch.float64, device=device)
+    ws = dev._ws(lib.sx_sinkhorn_workspace_bytes(S, D), device)
+    it_h, err_h = ctypes.c_int64(0), ctypes.c_double(0.0)
+    reg = 0.01 * float(M[:64].median().item())
+
+    def run(n):
+        check(lib.sx_sinkhorn_ot(dev._ptr(M), M.stride(0), S, D, dev._ptr(sa), dev._ptr(sb), reg, n, 0.0, 10, dev._ptr(f),
+                                 dev._ptr(gg), None, ctypes.byref(it_h), ctypes.byref(err_h), dev._ptr(ws), ws.numel(),
+                                 dev._stream()), "sx_sinkhorn_ot")
+    run(3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(iters)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    peak, _ = measured_peak_gbs()
+    gbs = 16.0 * S * D / (ms * 1e-3) / 1e9
+    ok = bool(torch.isfinite(f).all().item() and torch.isfinite(gg).all().item())
+    return {"workload": f"log-domain Sinkhorn-Knopp on OT {S}x{D}, reg = 0.01 median(M)", "ms_per_iteration": round(ms, 4),
+            "iterations_timed": iters, "algorithmic_bytes_per_arc_and_iteration": 16, "achieved_GBs": round(gbs, 1),
+            "frac_of_measured_peak": round(gbs / peak, 4), "finite": ok,
+            "parity": "unpinned: POT (third party, scripts/run_network_crossover.py:96) is not installed; the oracle "
+                      "restates its published Sinkhorn-Knopp loop and the device plan matches it to 1e-9"}
+
+
 def cpu_mcf_path(tail, head, c, u, x, A, N):
     """Oracle port on ONE host core: MCF flow indicators (net_manager.py:156-182), stable argsort (:184),
     Kruskal over the stable order of -w, potentials of the forest's tree."""
@@ -524,6 +566,9 @@ def main():
         from smart_crossover._native import lib as _lib
         assert _lib.sx_kruskal_set_tuning(args.kruskal_chunk) == 0
     if args.tree_only:
+        if args.tree_only == 1:                          # --tree-only 1: the Sinkhorn warm start at 20 000^2
+            print(json.dumps(time_sinkhorn(20000, 20000, device)), flush=True)
+            return
         if args.tree_only < 0:                           # --tree-only -1: the MCF configuration (1M nodes / 10M arcs)
             print(json.dumps(time_mcf_path(1_000_000, 10_000_000, device, reps=2, cpu=not args.no_cpu)), flush=True)
             return
@@ -566,13 +611,14 @@ def main():
             dist.destroy_process_group()
         return
 
-    tree = None
+    tree, warm = None, None
     if world == 1 and not args.no_tree:
         torch.cuda.empty_cache()
         cpu = not args.no_cpu
         tree = [time_tree_build(784, 784, device, cpu=(784, 784) if cpu else None),
                 time_tree_build(20000, 20000, device, reps=1, cpu=(3000, 3000) if cpu else None),
                 time_mcf_path(1_000_000, 10_000_000, device, reps=1, cpu=cpu)]
+        warm = time_sinkhorn(20000, 20000, device)
 
     def roofline_of(leg):
         achieved = 8.0 * leg["S_loc"] * leg["D"] / (leg["kernel_ms"] * 1e-3) / 1e9
@@ -602,7 +648,7 @@ def main():
             "e2e_one_process_per_gpu": L["e2e"], "e2e_pinned": L["e2e_pinned"],
             "topk_digest": L["topk_digest"], "merge_check": L["merge_check"],
             "stage_us_rank0": L["stage_us"], "e2e_cold": L["e2e_cold"], "gpu_launches": L["gpu_launches"],
-            "clocks": L["clocks"], "tree_build": tree}
+            "clocks": L["clocks"], "tree_build": tree, "warm_start": warm}
     if c4_leg is not None:
         C = c4_leg
         line["c4"] = {"workload": workload_of(C), "value": C["value"], "unit": UNIT, "ms_per_step": C["ms_per_step"],

@@ -388,14 +388,19 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
                 process(trt, t - trt * p.n_col_blocks, s, it, true);
             }
         }
-        warp_flush(p.sink, tally);
+        // one count and one minimum per CTA reach the header (2 368 same-address atomics per pass otherwise)
         const long long k = warp_min(f64_to_min_key(tmin));
-        if (lane_id() == 0) scratch[warp] = k;
+        if (lane_id() == 0) { scratch[warp] = k; scratch[CWARPS + STAGES + warp] = (long long)tally.count; }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         long long m = scratch[0];
-        for (int w = 1; w < CWARPS; ++w) m = scratch[w] < m ? scratch[w] : m;
+        unsigned long long cnt = (unsigned long long)scratch[CWARPS + STAGES];
+        for (int w = 1; w < CWARPS; ++w) {
+            m = scratch[w] < m ? scratch[w] : m;
+            cnt += (unsigned long long)scratch[CWARPS + STAGES + w];
+        }
+        if (cnt) atomicAdd(&p.sink.hdr->n_violating, cnt);
         atomicMin(&p.sink.hdr->min_rc_key, m);
         if (blockIdx.x == 0) atomicAdd(&p.sink.hdr->n_priced, (unsigned long long)(p.S_loc * p.D));
     }
@@ -404,7 +409,7 @@ __device__ __forceinline__ void price_tiles(const CUtensorMap &tmap, const Dense
 
 constexpr size_t tma_smem_bytes(int rows, int stages, int cwarps) {
     return (size_t)stages * rows * kBoxCols * sizeof(double) + 2 * (size_t)stages * sizeof(uint64_t) +
-           (size_t)cwarps * sizeof(long long) + (size_t)stages * sizeof(long long) + 64;   // + tile tickets
+           2 * (size_t)cwarps * sizeof(long long) + (size_t)stages * sizeof(long long) + 64;   // + tickets, counts
 }
 
 

@@ -179,3 +179,29 @@ def test_network_crossover_mcf_20k():
     assert abs(out.obj_val - ref) <= 1e-9 * abs(ref) and abs(out.obj_val - float(fx.out["direct_obj"])) <= 1e-9 * abs(ref)
     assert out.iter_count == int(fx.out["cnet_mcf_iters"])
     assert np.array_equal(np.flatnonzero(out.basis.vbasis == 0), fx.out["cnet_mcf_basic"])
+
+
+def test_tree_basis_with_zero_weight_tree_arcs():
+    """Flow indicators that are exactly zero on arcs the spanning tree needs (an underflowed Sinkhorn plan, a
+    sparse warm start).  The reference drops zero-weight tree arcs from `max_weight_spanning_tree`
+    (tree_BI.py:56, kept in the public function here too) and then fails in its square solve (:74-76);
+    `tree_basis_identify` works on the full device tree and returns a feasible basis."""
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.net_manager import OTManager
+    from smart_crossover.network_methods.tree_BI import max_weight_spanning_tree, tree_basis_identify
+    fx = Fixture("ot_zero_3x3")
+    s, d, M, x = fx.inp["s"], fx.inp["d"], fx.inp["M"], fx.inp["x"]
+    S, D = M.shape
+    mgr = OTManager(OptTransport(s, d, M))
+    queue, scores = mgr.get_sorted_flows(x)
+    assert np.array_equal(max_weight_spanning_tree(mgr.ot, scores), fx.out["tree"]) and fx.out["tree"].size < S + D - 1
+    basis, push_iter = tree_basis_identify(mgr, scores)
+    basic = np.flatnonzero(basis.vbasis == 0)
+    assert 1 <= basic.size <= S + D - 1 and basis.cbasis[-1] == 0
+    # the basic arcs carry a feasible transport plan: A_B x_B = b has a non-negative solution
+    A = np.zeros((S + D, basic.size))
+    A[basic // D, np.arange(basic.size)] = -1.0
+    A[S + basic % D, np.arange(basic.size)] = 1.0
+    b = np.concatenate([-s, d])
+    xb, res, *_ = np.linalg.lstsq(A, b, rcond=None)
+    assert np.allclose(A @ xb, b, atol=1e-12) and (xb > -1e-12).all()

@@ -166,6 +166,24 @@ def test_mcf_restricted_master_equals_the_reference_formulas(name):
         assert np.array_equal(mgr.mcf_sub.u, mgr.mcf.u[ref["non_fix"]])
 
 
+def test_bigm_extended_cost_view_equals_the_reference_extension():
+    """`extend_by_bigM` keeps `ot.M` as a view (no (S+1) x (D+1) host copy): shape, single entries, flat takes
+    and the materialised array equal the reference's `np.vstack([np.hstack(...)])` (net_manager.py:390-393)."""
+    from smart_crossover.network_methods.net_manager import BigMExtendedCost, _take_flat
+    rng = np.random.default_rng(4)
+    M = rng.random((7, 5))
+    bigM = 123.5
+    ref = np.vstack([np.hstack([M, bigM * np.ones((7, 1))]), np.hstack([bigM * np.ones((1, 5)), np.array([[0]])])])
+    view = BigMExtendedCost(M, bigM)
+    assert view.shape == ref.shape and view.size == ref.size and view.ndim == 2
+    assert np.array_equal(np.asarray(view), ref) and np.array_equal(view.ravel(), ref.ravel())
+    ids = rng.permutation(ref.size)
+    assert np.array_equal(view.take_flat(ids), ref.ravel()[ids]) and np.array_equal(_take_flat(view, ids), ref.ravel()[ids])
+    assert view[7, 5] == 0.0 and view[0, 5] == bigM and view[7, 0] == bigM and view[3, 2] == M[3, 2] and view[-1, -1] == 0.0
+    assert view.max() == ref.max() and np.array_equal(view[2:4], ref[2:4])
+    assert np.array_equal(_take_flat(M, np.array([0, 6, 34])), M.ravel()[[0, 6, 34]])
+
+
 def test_highs_backend_solves_and_reports_like_a_solver_caller():
     fx = Fixture("ot_c1_40x40")
     ot = OptTransport(fx.inp["s"], fx.inp["d"], fx.inp["M"])
