@@ -275,7 +275,7 @@ def cpu_tree_build_ot(x, s, d, M, S, D, note):
             "cores": 1, "kind": "port", "host_cpus": os.cpu_count(), "sample": note}
 
 
-def time_tree_build(S, D, device, reps=3, cpu=None):
+def time_tree_build(S, D, device, reps=3, cpu=None, call_host=False):
     """`cpu`: None = no CPU leg; (S_cpu, D_cpu) = time the oracle port on an instance of that shape (the same
     instance when equal to (S, D), else a smaller stand-in built the same way)."""
     import torch
@@ -336,6 +336,20 @@ def time_tree_build(S, D, device, reps=3, cpu=None):
         if full is None or sum(parts) < sum(full):
             full = parts
         del F, order, skey, korder, tree, y
+    # the reference-facing call with HOST arrays in and out (net_manager.py:368-379): upload of x, scores, sort,
+    # download of the two n-sized results through pinned staging (wall clock, once)
+    call_s = None
+    if call_host:
+        from smart_crossover.formats import OptTransport
+        from smart_crossover.network_methods.net_manager import OTManager
+        x_h, s_h, d_h = x.cpu().numpy(), s.cpu().numpy(), d.cpu().numpy()
+        mgr = OTManager(OptTransport(s_h, d_h, np.zeros((1, 1))))            # the cost matrix plays no part in this call
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        q_h, sc_h = mgr.get_sorted_flows(x_h)
+        call_s = time.perf_counter() - t0
+        assert q_h.shape == (S * D,) and sc_h.shape == (S * D,)
+        del q_h, sc_h, x_h, mgr
     names = ["score", "kruskal_prefix", "kruskal", "potentials"]
     names_full = ["score", "argsort", "kruskal_order", "kruskal", "potentials"]
     from smart_crossover.network_methods.tree_BI import use_prefix_path
@@ -360,7 +374,7 @@ def time_tree_build(S, D, device, reps=3, cpu=None):
                                         f"full-size oracle run takes minutes (SURVEY.md section 8d)")
             cpu_leg["arcs"] = Sc * Dc
     return {"workload": f"OT {S}x{D} ({S * D} arcs)", "ms": round(sum(best) if prefix else sum(full), 4),
-            "cpu_baseline": cpu_leg,
+            "cpu_baseline": cpu_leg, "get_sorted_flows_host_call_s": None if call_s is None else round(call_s, 4),
             "path": "kruskal_prefix" if prefix else "full_argsort",
             "kruskal_prefix_ms": round(sum(best), 4),
             "breakdown_ms": {n: round(v, 4) for n, v in zip(names, best)},
@@ -573,7 +587,8 @@ def main():
             print(json.dumps(time_mcf_path(1_000_000, 10_000_000, device, reps=2, cpu=not args.no_cpu)), flush=True)
             return
         T = args.tree_only
-        print(json.dumps(time_tree_build(T, T, device, reps=2, cpu=None if args.no_cpu else (min(T, 3000),) * 2)), flush=True)
+        print(json.dumps(time_tree_build(T, T, device, reps=2, cpu=None if args.no_cpu else (min(T, 3000),) * 2,
+                                         call_host=True)), flush=True)
         return
 
     def host_barrier():
@@ -616,7 +631,7 @@ def main():
         torch.cuda.empty_cache()
         cpu = not args.no_cpu
         tree = [time_tree_build(784, 784, device, cpu=(784, 784) if cpu else None),
-                time_tree_build(20000, 20000, device, reps=1, cpu=(3000, 3000) if cpu else None),
+                time_tree_build(20000, 20000, device, reps=1, cpu=(3000, 3000) if cpu else None, call_host=True),
                 time_mcf_path(1_000_000, 10_000_000, device, reps=1, cpu=cpu)]
         warm = time_sinkhorn(20000, 20000, device)
 

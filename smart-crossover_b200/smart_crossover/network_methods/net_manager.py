@@ -59,11 +59,8 @@ def _dev():
 
 
 def _cuda(a, dtype=None):
-    import torch
-    t = torch.from_numpy(np.ascontiguousarray(a))
-    if dtype is not None:
-        t = t.to(dtype)
-    return t.cuda()
+    """Host array -> tensor on the current device (large arrays through pinned staging, `device.to_device`)."""
+    return _dev().to_device(np.asarray(a), dtype=dtype)
 
 
 class BigMExtendedCost:
@@ -153,16 +150,21 @@ def _take_flat(M, ids: np.ndarray) -> np.ndarray:
 
 class _SortedFlows:
     """Device-resident result of one `get_sorted_flows` call, kept so that the tree build
-    (`tree_BI.max_weight_spanning_tree`) can reuse the sort instead of repeating it."""
+    (`tree_BI.max_weight_spanning_tree`) can reuse the sort instead of repeating it.
+    `scores_np = None`: the scores are downloaded here, on a copy stream, WHILE the sort runs."""
 
-    def __init__(self, scores_t, scores_np):
+    def __init__(self, scores_t, scores_np=None):
+        import torch
         dev = _dev()
         self.scores_t = scores_t
-        self.scores_np = scores_np
+        ready = torch.cuda.Event()
+        ready.record()                                   # the scores are complete; the sort is enqueued after this
         self.order, self.sorted_key = dev.argsort_f64(scores_t)
+        self.scores_np = scores_np if scores_np is not None else dev.to_host(scores_t, ready=ready)
 
     def queue(self) -> np.ndarray:
-        return _dev().queue_from_order(self.order).cpu().numpy()
+        dev = _dev()
+        return dev.to_host(dev.queue_from_order(self.order))
 
     def kruskal_order(self):
         return _dev().kruskal_order(self.sorted_key, self.order)
@@ -268,9 +270,8 @@ class OTManager:
         scores_t = dev.score_ot(_cuda(np.asarray(x, dtype=np.float64).ravel()),
                                 _cuda(np.asarray(self.ot.s, dtype=np.float64)),
                                 _cuda(np.asarray(self.ot.d, dtype=np.float64)))
-        scores = scores_t.cpu().numpy()
-        self._sorted = _SortedFlows(scores_t, scores)
-        return self._sorted.queue(), scores
+        self._sorted = _SortedFlows(scores_t)
+        return self._sorted.queue(), self._sorted.scores_np
 
     # ---- big-M extension ----------------------------------------------------------------------------------
     def extend_by_bigM(self, bigM: float) -> None:
@@ -450,9 +451,8 @@ class MCFManagerStd:
         scores_t = dev.score_mcf(_cuda(np.asarray(x, dtype=np.float64)), _cuda(np.asarray(self.mcf.u, dtype=np.float64)),
                                  arcs["tail"], arcs["head"], _cuda(A.indptr, torch.int64),
                                  _cuda(A.indices, torch.int32), _cuda(np.sign(A.data), torch.int8))
-        scores = scores_t.cpu().numpy()
-        self._sorted = _SortedFlows(scores_t, scores)
-        return self._sorted.queue(), scores
+        self._sorted = _SortedFlows(scores_t)
+        return self._sorted.queue(), self._sorted.scores_np
 
     # ---- big-M extension, rescaling, fixing (host) -----------------------------------------------------------------
     def extend_by_bigM(self, bigM: float) -> None:

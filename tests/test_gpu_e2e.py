@@ -205,3 +205,39 @@ def test_tree_basis_with_zero_weight_tree_arcs():
     b = np.concatenate([-s, d])
     xb, res, *_ = np.linalg.lstsq(A, b, rcond=None)
     assert np.allclose(A @ xb, b, atol=1e-12) and (xb > -1e-12).all()
+
+
+def test_get_sorted_flows_downloads_through_pinned_staging():
+    """Above 64 MB the scores and the queue come back through the chunked pinned-staging download
+    (`device.to_host`), the scores while the sort is still running: 3 200 x 3 200 = 82 MB per array, bitwise
+    equal to the oracle (net_manager.py:368-379 with a stable argsort)."""
+    import cases
+    from oracle import network_oracle as orc
+    from smart_crossover import device as dev
+    from smart_crossover.formats import OptTransport
+    from smart_crossover.network_methods.net_manager import OTManager
+    S = D = 3200
+    s, d, M = cases.ot_points(S, D, 31)
+    x = cases.interior_flow(s, d, M, 31, 0.33)
+    queue, scores = OTManager(OptTransport(s, d, M)).get_sorted_flows(x)
+    ref = orc.ot_flow_scores(x, s, d)
+    assert scores.tobytes() == ref.tobytes()
+    assert queue.dtype == np.int64 and np.array_equal(queue, orc.stable_queue(ref))
+    t = torch.arange(3 * (1 << 22) + 5, dtype=torch.int64, device="cuda")          # 100 MB, not a chunk multiple
+    assert np.array_equal(dev.to_host(t), np.arange(3 * (1 << 22) + 5, dtype=np.int64))
+
+
+def test_staged_upload_matches_plain_copy():
+    from smart_crossover import device as dev
+    rng = np.random.default_rng(0)
+    a = rng.random(3 * (1 << 22) + 7)                                  # 100 MB, not a chunk multiple
+    assert np.array_equal(dev.to_device(a).cpu().numpy(), a)
+    b = rng.integers(0, 1 << 40, size=(4099, 2051))                    # 2-D int64, 67 MB
+    t = dev.to_device(b)
+    assert t.shape == b.shape and t.dtype == torch.int64 and np.array_equal(t.cpu().numpy(), b)
+    assert dev.to_device(np.arange(10, dtype=np.int64), dtype=torch.int32).dtype == torch.int32
+    M = rng.random((3001, 2800))                                       # 67 MB: CostSlabs upload through staging
+    slabs = dev.CostSlabs.from_host(M, [torch.cuda.current_device()], border=(9.0, 0.0))
+    got = slabs.view(0).cpu().numpy()
+    assert np.array_equal(got[:3001, :2800], M) and (got[3001, :2800] == 9.0).all() and (got[:3001, 2800] == 9.0).all()
+    assert got[3001, 2800] == 0.0
