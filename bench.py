@@ -62,6 +62,8 @@ def parse():
                     help="price / select / push as separate launches (round-1 path) instead of the fused kernel")
     ap.add_argument("--no-c4", action="store_true", help="skip the second leg (dense OT 20 000 x 20 000)")
     ap.add_argument("--no-manager", action="store_true", help="skip the OTManager end-to-end leg")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: equal row shards instead of shards sized by each GPU's measured rate")
     ap.add_argument("--c4-size", type=int, default=20000)
     ap.add_argument("--sweep", action="store_true", help="time every pricing-kernel variant / tuning and exit")
     ap.add_argument("--sweep-ab", default="", metavar="I,J,..",
@@ -637,8 +639,9 @@ def main():
 
     def roofline_of(leg):
         achieved = 8.0 * leg["S_loc"] * leg["D"] / (leg["kernel_ms"] * 1e-3) / 1e9
+        traffic, traffic_src = committed_traffic(leg["S_loc"], leg["D"])
         return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": committed_traffic(leg["S_loc"], leg["D"]),
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel": leg["kernel"], "kernel_ms": round(leg["kernel_ms"], 4),
                 "kernel_ms_per_rank": leg["kernel_ms_per_rank"], "kernel_ms_source": leg["kernel_ms_source"],
                 "algorithmic_bytes_per_arc": 8,
@@ -656,7 +659,7 @@ def main():
             "config": {"workload": workload_of(L),
                        "S": S, "D": D, "topk": args.topk, "tol": TOL, "violating_arcs": L["violating_arcs"],
                        "rows_per_gpu": L["S_loc"], "variant": args.variant, "exchange": L["exchange"],
-                       "fused": L["fused"],
+                       "fused": L["fused"], "row_partition": L["balance"] or "equal shares",
                        "l2": f"inputs larger than L2 ({8 * L['S_loc'] * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
             "roofline": roofline_of(L), "cpu_baseline": L["cpu_baseline"],
             "e2e": main_mgr if main_mgr is not None else L["e2e"],
@@ -667,7 +670,8 @@ def main():
     if c4_leg is not None:
         C = c4_leg
         line["c4"] = {"workload": workload_of(C), "value": C["value"], "unit": UNIT, "ms_per_step": C["ms_per_step"],
-                      "steps": steps, "rows_per_gpu": C["S_loc"], "violating_arcs": C["violating_arcs"],
+                      "steps": steps, "rows_per_gpu": C["S_loc"], "row_partition": C["balance"] or "equal shares",
+                      "violating_arcs": C["violating_arcs"],
                       "roofline": roofline_of(C), "stage_us_rank0": C["stage_us"],
                       "e2e": c4_mgr if c4_mgr is not None else C["e2e"], "e2e_one_process_per_gpu": C["e2e"],
                       "e2e_pinned": C["e2e_pinned"], "topk_digest": C["topk_digest"],
@@ -693,7 +697,7 @@ def manager_leg(args, S, D, ctx, steps, leg):
         from smart_crossover.network_methods.net_manager import OTManager
         K = args.topk
         devices = [(ctx["local"] + i) % torch.cuda.device_count() for i in range(world)]
-        slabs = dev.CostSlabs(S, D, devices)
+        slabs = dev.CostSlabs(S, D, devices, leg["row_bounds"])
         for g, d in enumerate(devices):
             with torch.cuda.device(d):
                 P, Q, a = make_points(S, D, torch.device("cuda", d))
@@ -737,16 +741,25 @@ def manager_leg(args, S, D, ctx, steps, leg):
 
 
 def committed_traffic(S_loc, D):
-    """dram read + write bytes of one pricing-kernel launch from the committed `ncu --set full` captures
-    (profiles/price_traffic.json: one entry per slab shape), or None when that shape was not captured."""
+    """dram read + write bytes of one pricing-kernel launch from the committed ncu captures
+    (profiles/price_traffic.json: one entry per captured slab shape).  Exact shape: the captured bytes.  Other
+    row counts of the same D (rate-balanced shards, N = 2 / 4): the capture with the nearest row count, its
+    traffic / algorithmic ratio applied to this slab's algorithmic bytes -- returned with a note saying so."""
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "price_traffic.json")))
-        for e in tj if isinstance(tj, list) else [tj]:
-            if (e["S_loc"], e["D"]) == (S_loc, D):
-                return e["traffic_bytes"]
+        tj = tj if isinstance(tj, list) else [tj]
+        same = [e for e in tj if e["D"] == D]
+        for e in same:
+            if e["S_loc"] == S_loc:
+                return e["traffic_bytes"], "ncu capture of this slab shape (profiles/price_traffic.json)"
+        if same:
+            e = min(same, key=lambda e: abs(e["S_loc"] - S_loc))
+            ratio = e["traffic_bytes"] / e["algorithmic_bytes"]
+            return ratio * 8.0 * S_loc * D, (f"scaled: traffic / algorithmic = {ratio:.4f} of the ncu capture at "
+                                             f"{e['S_loc']} x {D} applied to {S_loc} x {D}")
     except Exception:
         pass
-    return None
+    return None, None
 
 
 def topk_digest(ids, rc, count, min_rc):
@@ -777,6 +790,38 @@ def pricing_leg(args, S, D, ctx, steps, warmup, sampler, want_cpu, want_cold):
     y_host = y_dev.cpu().numpy()
     sp = ShardedDensePricer(M_loc, S, row0, K, TOL, variant=args.variant, exchange=args.exchange,
                             fused=not args.no_fused)
+    row_bounds = [S * g // world for g in range(world + 1)]
+    balance = None
+    if world > 1 and sp.fused and not args.no_balance:
+        # Shards sized by measured rate.  An exchanged pass ends when the SLOWEST GPU has delivered its block, and
+        # the GPUs of one box stream at rates a few percent apart (power / thermal headroom): time every GPU's own
+        # pricing phase (in-kernel stamps: CTA 0's pricing + its wait at the barrier all CTAs reach after pricing)
+        # over a few passes of the equal partition, then give each GPU rows in proportion to its rate.
+        from smart_crossover.device import balanced_row_bounds
+        for _ in range(5):
+            sp.enqueue(y_dev)
+        ts = []
+        for _ in range(8):
+            sp.enqueue(y_dev)
+            torch.cuda.synchronize()
+            ph = sp.pricer.fused_phase_us()
+            ts.append(ph["pricing"] + ph["barrier1"])
+        spr = torch.zeros(world, dtype=torch.float64, device=device)
+        spr[rank] = float(np.median(ts)) / S_loc
+        dist.all_reduce(spr, op=dist.ReduceOp.SUM)
+        spr = spr.cpu().numpy()
+        new_bounds = balanced_row_bounds(S, spr)
+        balance = {"us_per_1000_rows_equal_partition": [round(float(v) * 1e3, 3) for v in spr],
+                   "rows_per_gpu": [new_bounds[g + 1] - new_bounds[g] for g in range(world)]}
+        if new_bounds != row_bounds:
+            del sp, M_loc
+            torch.cuda.empty_cache()
+            row_bounds = new_bounds
+            row0, S_loc = row_bounds[rank], row_bounds[rank + 1] - row_bounds[rank]
+            M_loc = make_slab(P, Q, row0, S_loc)
+            sp = ShardedDensePricer(M_loc, S, row0, K, TOL, variant=args.variant, exchange=args.exchange,
+                                    fused=not args.no_fused)
+        barrier()
 
     # ---- device-resident arm ---------------------------------------------------------------------
     for _ in range(warmup):
@@ -927,7 +972,7 @@ def pricing_leg(args, S, D, ctx, steps, warmup, sampler, want_cpu, want_cold):
            "stage_us": stages,
            "gpu_launches": launches, "violating_arcs": count_dev, "topk_digest": digest, "merge_check": merge_check,
            "e2e": e2e, "e2e_pinned": e2e_pinned, "e2e_cold": cold, "cpu_baseline": cpu_baseline, "clocks": clocks,
-           "exchange": sp.exchange, "fused": sp.fused, "y_host": y_host}
+           "exchange": sp.exchange, "fused": sp.fused, "y_host": y_host, "row_bounds": row_bounds, "balance": balance}
     del sp, M_loc, y_dev
     torch.cuda.empty_cache()
     barrier()

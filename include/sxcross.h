@@ -49,7 +49,7 @@ extern "C" {
 #define SX_ERR_PEER_TIMEOUT    -8   /* sx_exchange_blocks: a peer never raised its flag */
 #define SX_ERR_PUSH_ASSERT     -9   /* sx_push_tree_h: the reference's assertions would fire (tree_BI.py:93-94) */
 
-#define SX_ABI_VERSION 3
+#define SX_ABI_VERSION 4
 
 /* Endpoint convention of sx_tree_potentials (which end of an arc carries +1 in A). */
 #define SX_PLUS_IS_HEAD 0   /* OT:  A[S+j,k] = +1, A[i,k] = -1      (formats.py:156-158)     */
@@ -391,6 +391,9 @@ SX_API int    sx_sinkhorn_ot(const double *M, int64_t ld, int64_t S, int64_t D, 
  *   slabs[g]: DEVICE pointer (on device devs[g], caller-owned, resident for the life of the pricer) to that
  *     row range of M, row-major with leading dimension ld (even ld and 16-byte aligned slabs select the
  *     TMA / fused path; anything else is priced by the scalar-load kernels).
+ *   row_bounds (HOST, ndev + 1 entries, may be NULL): shard g holds rows [row_bounds[g], row_bounds[g + 1]);
+ *     NULL = the equal partition above.  GPUs of one box stream at rates a few percent apart and a pass ends
+ *     when the slowest has delivered its block, so callers may size the shards by measured rate.
  *   K: top-K size (0: count / min only).  ndev > 1 needs K <= SX_TOPK_MAX_K and peer access between the
  *     devices (SX_ERR_NO_DEVICE otherwise).
  * sx_ot_pricer_price_h: y_src_h (S source duals) and y_dst_h (D sink duals) are HOST vectors (pageable is
@@ -401,8 +404,8 @@ SX_API int    sx_sinkhorn_ot(const double *M, int64_t ld, int64_t S, int64_t D, 
  *   fused kernel and the in-kernel merge are in use.
  */
 typedef struct sx_ot_pricer sx_ot_pricer;
-SX_API int    sx_ot_pricer_create(int ndev, const int *devs, const double *const *slabs, int64_t ld, int64_t S,
-                           int64_t D, int64_t K, double tol, sx_ot_pricer **out);
+SX_API int    sx_ot_pricer_create(int ndev, const int *devs, const double *const *slabs, const int64_t *row_bounds,
+                           int64_t ld, int64_t S, int64_t D, int64_t K, double tol, sx_ot_pricer **out);
 SX_API int    sx_ot_pricer_destroy(sx_ot_pricer *p);
 SX_API int    sx_ot_pricer_info(const sx_ot_pricer *p, int g, int *dev, int64_t *row0, int64_t *S_loc);
 SX_API int    sx_ot_pricer_price_h(sx_ot_pricer *p, const double *y_src_h, const double *y_dst_h,

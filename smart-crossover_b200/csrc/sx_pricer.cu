@@ -5,11 +5,14 @@
 // vector, as the LP solver returns it), violator count / min reduced cost / top-K out.  sx_ot_pricer keeps
 // everything that call needs alive between rounds -- candidate buffers, the two selection states of the
 // fused pass, exchange buffers, pinned staging, one stream and one host worker thread per GPU -- so a pass
-// allocates nothing, and it row-shards the cost matrix over every GPU it was given: worker g uploads the
-// duals of its rows, launches ONE kernel (sx_price_dense_ot_fused: price + select + NVLink push + merge)
-// and reads the merged result back; the workers run concurrently, so the GPUs start within microseconds
-// of each other and the caller sees a plain function call (SURVEY.md section 8e "process model").
+// allocates nothing, and it row-shards the cost matrix over every GPU it was given: per GPU one host thread
+// (the caller's own for device 0, a worker for each other device) uploads the duals of its rows, launches
+// ONE kernel (sx_price_dense_ot_fused: price + select + NVLink push + merge) and reads the merged result
+// back; the threads run concurrently, so the GPUs start within microseconds of each other and the caller
+// sees a plain function call (SURVEY.md section 8e "process model").
 // The cost-matrix slabs are caller-owned device memory (the managers upload M once per problem).
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -41,12 +44,13 @@ struct DevCtx {
     void **peer_bufs_dev = nullptr;
     double *h_y = nullptr;
     int64_t *h_out = nullptr;
-    // worker thread
+    // worker thread (devices 1..G-1; device 0 is driven by the calling thread itself)
     std::thread th;
     std::mutex mu;
     std::condition_variable cv;
+    std::atomic<unsigned> posted{0}, finished{0};     // sequence numbers of the last command handed over / completed
+    bool sleeping = false;                            // under mu: the worker gave up spinning and waits on cv
     int cmd = kIdle, rc = SX_OK;
-    bool done = false;
 };
 
 }  // namespace
@@ -131,39 +135,67 @@ int run_pass(sx_ot_pricer *p, DevCtx *c) {
     return SX_OK;
 }
 
+int do_cmd(sx_ot_pricer *p, DevCtx *c, int cmd) {
+    if (cmd == kPrice) return run_pass(p, c);
+    if (cmd == kGrow) return alloc_candidates(p, c, p->new_cap);
+    return SX_OK;
+}
+
+// A worker spins for its next command for a short while after finishing one -- passes of a benchmark loop or
+// of a fast column-generation round follow each other within microseconds, and a futex wake-up costs 20-50 us,
+// a third of a pass over a 0.4 GB slab -- and then sleeps on the condition variable.
+constexpr long long kSpinNs = 200 * 1000;
+
 void worker(sx_ot_pricer *p, DevCtx *c) {
     cudaSetDevice(c->dev);
+    unsigned last = 0;
     for (;;) {
-        int cmd;
-        {
-            std::unique_lock<std::mutex> lk(c->mu);
-            c->cv.wait(lk, [&] { return c->cmd != kIdle; });
-            cmd = c->cmd;
+        const unsigned want = last + 1;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (c->posted.load(std::memory_order_acquire) != want) {
+            if (std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count() > kSpinNs) {
+                std::unique_lock<std::mutex> lk(c->mu);
+                c->sleeping = true;
+                c->cv.wait(lk, [&] { return c->posted.load(std::memory_order_acquire) == want; });
+                c->sleeping = false;
+                break;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
         }
-        int rc = SX_OK;
-        if (cmd == kPrice) rc = run_pass(p, c);
-        else if (cmd == kGrow) rc = alloc_candidates(p, c, p->new_cap);
-        {
-            std::lock_guard<std::mutex> lk(c->mu);
-            c->rc = rc;
-            c->cmd = kIdle;
-            c->done = true;
-        }
-        c->cv.notify_all();
+        last = want;
+        const int cmd = c->cmd;
+        c->rc = do_cmd(p, c, cmd);
+        c->finished.store(want, std::memory_order_release);
         if (cmd == kQuit) return;
     }
 }
 
-// Hand `cmd` to every worker, wait for all of them; the first error code wins.
+void post(DevCtx *c, int cmd) {
+    c->cmd = cmd;
+    c->posted.store(c->posted.load(std::memory_order_relaxed) + 1, std::memory_order_release);
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->sleeping) c->cv.notify_all();
+}
+
+// Hand `cmd` to every worker, run device 0's share on the calling thread, wait for the workers (they finish
+// within microseconds of device 0: every GPU runs the same pass); the first error code wins.
 int run_all(sx_ot_pricer *p, int cmd) {
-    for (DevCtx *c : p->ctx) {
-        { std::lock_guard<std::mutex> lk(c->mu); c->done = false; c->cmd = cmd; }
-        c->cv.notify_all();
-    }
-    int rc = SX_OK;
-    for (DevCtx *c : p->ctx) {
-        std::unique_lock<std::mutex> lk(c->mu);
-        c->cv.wait(lk, [&] { return c->done; });
+    for (size_t g = 1; g < p->ctx.size(); ++g) post(p->ctx[g], cmd);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(p->ctx[0]->dev);
+    int rc = do_cmd(p, p->ctx[0], cmd);
+    cudaSetDevice(prev);
+    for (size_t g = 1; g < p->ctx.size(); ++g) {
+        DevCtx *c = p->ctx[g];
+        const unsigned want = c->posted.load(std::memory_order_relaxed);
+        while (c->finished.load(std::memory_order_acquire) != want) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         if (rc == SX_OK && c->rc != SX_OK) rc = c->rc;
     }
     return rc;
@@ -189,8 +221,7 @@ extern "C" int sx_ot_pricer_destroy(sx_ot_pricer *p) {
     cudaGetDevice(&prev);
     for (DevCtx *c : p->ctx) {
         if (c->th.joinable()) {
-            { std::lock_guard<std::mutex> lk(c->mu); c->done = false; c->cmd = kQuit; }
-            c->cv.notify_all();
+            post(c, kQuit);
             c->th.join();
         }
     }
@@ -200,12 +231,16 @@ extern "C" int sx_ot_pricer_destroy(sx_ot_pricer *p) {
     return SX_OK;
 }
 
-extern "C" int sx_ot_pricer_create(int ndev, const int *devs, const double *const *slabs, int64_t ld, int64_t S,
-                                   int64_t D, int64_t K, double tol, sx_ot_pricer **out) {
+extern "C" int sx_ot_pricer_create(int ndev, const int *devs, const double *const *slabs, const int64_t *row_bounds,
+                                   int64_t ld, int64_t S, int64_t D, int64_t K, double tol, sx_ot_pricer **out) {
     if (!out) return SX_ERR_INVALID;
     *out = nullptr;
     if (ndev < 1 || ndev > 64 || !devs || !slabs || S < 1 || D < 1 || ld < D || K < 0) return SX_ERR_INVALID;
     if (ndev > S) return SX_ERR_INVALID;                      // every device needs at least one row
+    if (row_bounds) {
+        if (row_bounds[0] != 0 || row_bounds[ndev] != S) return SX_ERR_INVALID;
+        for (int g = 0; g < ndev; ++g) if (row_bounds[g + 1] <= row_bounds[g]) return SX_ERR_INVALID;
+    }
     const int64_t Kp = K > 0 ? K : 1;
     if (ndev > 1 && (K > SX_TOPK_MAX_K || (size_t)16 * ndev * Kp > 200 * 1024)) return SX_ERR_TOO_LARGE;
     int prev = 0;
@@ -224,8 +259,8 @@ extern "C" int sx_ot_pricer_create(int ndev, const int *devs, const double *cons
         if (!c) return fail(SX_ERR_INVALID);
         p->ctx.push_back(c);
         c->dev = devs[g]; c->g = g;
-        c->row0 = S * g / ndev;
-        c->S_loc = S * (g + 1) / ndev - c->row0;
+        c->row0 = row_bounds ? row_bounds[g] : S * g / ndev;
+        c->S_loc = (row_bounds ? row_bounds[g + 1] : S * (g + 1) / ndev) - c->row0;
         c->M = slabs[g];
         if (!c->M) return fail(SX_ERR_INVALID);
         if (((uintptr_t)c->M & 15) != 0) p->fusable = false;
@@ -274,7 +309,7 @@ extern "C" int sx_ot_pricer_create(int ndev, const int *devs, const double *cons
         }
     }
 #undef SXA
-    for (DevCtx *c : p->ctx) c->th = std::thread(worker, p, c);
+    for (size_t g = 1; g < p->ctx.size(); ++g) p->ctx[g]->th = std::thread(worker, p, p->ctx[g]);
     cudaSetDevice(prev);
     *out = p;
     return SX_OK;
@@ -376,7 +411,7 @@ extern "C" int sx_price_dense_ot_h(const double *M_h, const double *M_dev, int64
     }
     sx_ot_pricer *p = nullptr;
     const double *slabs[1] = {M_dev};
-    int rc = sx_ot_pricer_create(1, &dev, slabs, ld, S, D, K, tol, &p);
+    int rc = sx_ot_pricer_create(1, &dev, slabs, nullptr, ld, S, D, K, tol, &p);
     if (rc == SX_OK) {
         rc = sx_ot_pricer_price_h(p, y_h, y_h + S, n_violating_h, min_rc_h, topk_rc_h, topk_id_h, topk_n_h, nullptr);
         sx_ot_pricer_destroy(p);

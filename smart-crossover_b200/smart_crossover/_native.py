@@ -23,7 +23,7 @@ SX_STATUS_K_MISMATCH = 4
 SX_STATUS_NAN_RC = 8
 SX_STATUS_NEED_UNFUSED = 16
 SX_STATUS_REPEAT_MASK = 19
-SX_ABI_VERSION = 3
+SX_ABI_VERSION = 4
 
 
 class SxError(RuntimeError):
@@ -107,7 +107,7 @@ SIGNATURES = {
     "sx_sinkhorn_workspace_bytes": (_sz, [_i64, _i64]),
     "sx_sinkhorn_ot": (_int, [_p, _i64, _i64, _i64, _p, _p, _dbl, _i64, _dbl, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "sx_price_dense_ot_h": (_int, [_p, _p, _i64, _i64, _p, _dbl, _i64, _p, _p, _p, _p, _p]),
-    "sx_ot_pricer_create": (_int, [_int, _p, _p, _i64, _i64, _i64, _i64, _dbl, _p]),
+    "sx_ot_pricer_create": (_int, [_int, _p, _p, _p, _i64, _i64, _i64, _i64, _dbl, _p]),
     "sx_ot_pricer_destroy": (_int, [_p]),
     "sx_ot_pricer_info": (_int, [_p, _int, _p, _p, _p]),
     "sx_ot_pricer_price_h": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p]),

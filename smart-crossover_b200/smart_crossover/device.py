@@ -434,17 +434,41 @@ def pricing_devices(n_arcs: int, S: int) -> list:
     return devs
 
 
+def balanced_row_bounds(S: int, seconds_per_row, multiple: int = 16):
+    """Row partition with shares proportional to each shard's measured rate (1 / seconds per row), boundaries
+    rounded to a multiple of the pricing kernel's 16-row tiles.  A pass ends when the slowest GPU has delivered
+    its block, and the GPUs of one box stream at rates a few percent apart."""
+    rate = 1.0 / np.asarray(seconds_per_row, dtype=np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(rate)]) / rate.sum() * S
+    b = [int(round(v / multiple) * multiple) for v in cum]
+    b[0], b[-1] = 0, int(S)
+    for g in range(1, len(b)):                      # keep every shard non-empty
+        b[g] = max(b[g], b[g - 1] + 1) if g < len(b) - 1 else b[g]
+    for g in range(len(b) - 2, 0, -1):
+        b[g] = min(b[g], b[g + 1] - 1)
+    return b
+
+
 class CostSlabs:
     """Row shards of a dense S x D cost matrix, one per device, resident for the life of the problem (as the
     reference keeps `ot.M` in its manager).  Leading dimension rounded up to even (TMA path)."""
 
-    def __init__(self, S: int, D: int, devices):
+    def __init__(self, S: int, D: int, devices, row_bounds=None):
+        """`row_bounds` (G + 1 increasing row indices from 0 to S): shard g = rows [row_bounds[g], row_bounds[g+1]);
+        default = equal shares.  See `balanced_row_bounds`."""
         _require_cuda()
         self.S, self.D, self.devices = int(S), int(D), list(devices)
         self.ld = self.D + (self.D & 1)
         G = len(self.devices)
-        self.row0 = [self.S * g // G for g in range(G)]
-        self.rows = [self.S * (g + 1) // G - self.row0[g] for g in range(G)]
+        if row_bounds is None:
+            row_bounds = [self.S * g // G for g in range(G + 1)]
+        row_bounds = [int(v) for v in row_bounds]
+        if len(row_bounds) != G + 1 or row_bounds[0] != 0 or row_bounds[-1] != self.S \
+                or any(b <= a for a, b in zip(row_bounds, row_bounds[1:])):
+            raise ValueError("row_bounds must be G + 1 strictly increasing row indices from 0 to S")
+        self.row_bounds = row_bounds
+        self.row0 = row_bounds[:-1]
+        self.rows = [row_bounds[g + 1] - row_bounds[g] for g in range(G)]
         self.t = [torch.empty(self.rows[g], self.ld, dtype=torch.float64, device=torch.device("cuda", d))
                   for g, d in enumerate(self.devices)]
 
@@ -453,14 +477,14 @@ class CostSlabs:
         return self.t[g][:, :self.D]
 
     @classmethod
-    def from_host(cls, M, devices, border=None):
+    def from_host(cls, M, devices, border=None, row_bounds=None):
         """Upload a host matrix.  `border` = (bigM, corner): the device matrix is the (S+1) x (D+1) big-M
         extension of M (net_manager.py:390-393) -- last row / column = bigM, corner = `corner` -- built on the
         device, so the extended matrix never exists on the host."""
         M = np.asarray(M, dtype=np.float64)
         S0, D0 = M.shape
         S, D = (S0 + 1, D0 + 1) if border is not None else (S0, D0)
-        self = cls(S, D, devices)
+        self = cls(S, D, devices, row_bounds)
         for g in range(len(self.devices)):
             r0, r1 = self.row0[g], self.row0[g] + self.rows[g]
             h1 = min(r1, S0)
@@ -492,7 +516,8 @@ class OTPricer:
         ptrs = (ctypes.c_void_p * G)(*[t.data_ptr() for t in slabs.t])
         self._h = ctypes.c_void_p()
         slabs.sync()
-        check(lib.sx_ot_pricer_create(G, devs, ptrs, slabs.ld, slabs.S, slabs.D, self.K, float(tol),
+        bounds = (ctypes.c_int64 * (G + 1))(*slabs.row_bounds)
+        check(lib.sx_ot_pricer_create(G, devs, ptrs, bounds, slabs.ld, slabs.S, slabs.D, self.K, float(tol),
                                       ctypes.byref(self._h)), "sx_ot_pricer_create")
         Kp = max(self.K, 1)
         self._rc = np.empty(Kp, dtype=np.float64)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), f"{name} declared in sxcross.h but not exported"
     lib.sx_abi_version.restype = ctypes.c_int
-    assert lib.sx_abi_version() == 3
+    assert lib.sx_abi_version() == 4
     lib.sx_error_string.restype = ctypes.c_char_p
     assert b"spanning" in lib.sx_error_string(-5)
 

@@ -153,6 +153,21 @@ def test_ot_pricer_all_devices_one_process(dev, S, D, K):
 
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
+def test_ot_pricer_uneven_shards(dev):
+    """Shards sized by the caller (`row_bounds`, as `balanced_row_bounds` produces them): same answers."""
+    G = min(n_gpus(), 8)
+    S, D, K = 16 * G + 37, 1030, 128
+    s, d, M = cases.ot_points(S, D, 55)
+    bounds = [0] + sorted(np.random.default_rng(3).choice(np.arange(1, S), G - 1, replace=False).tolist()) + [S]
+    pr = dev.OTPricer(dev.CostSlabs.from_host(M, list(range(G)), row_bounds=bounds), K)
+    for y in pass_list(M, 2):
+        check_pass(pr.price(y[:S], y[S:]), M, y, K)
+    pr.close()
+    with pytest.raises(ValueError):
+        dev.CostSlabs(S, D, list(range(G)), row_bounds=[0] * G + [S])
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs at least 2 GPUs")
 def test_ot_pricer_multi_device_repeat_protocol(dev):
     """Ties that the fused pass cannot resolve, on every device at once: all ranks repeat together."""
     G = min(n_gpus(), 8)

@@ -25,6 +25,22 @@ def test_row_partition_is_a_balanced_cover():
         assert max(p[1] for p in parts) - min(p[1] for p in parts) <= 1
 
 
+def test_balanced_row_bounds_cover_the_rows_in_proportion_to_the_rates():
+    from smart_crossover.device import balanced_row_bounds
+    rng = np.random.default_rng(0)
+    for S, G in [(60000, 8), (20000, 8), (20000, 3), (301, 2), (10, 8), (8, 8), (100003, 5)]:
+        spr = 1.0 + 0.05 * rng.random(G)                          # seconds per row of each GPU
+        b = balanced_row_bounds(S, spr)
+        assert b[0] == 0 and b[-1] == S and len(b) == G + 1
+        assert all(y > x for x, y in zip(b, b[1:]))                 # every shard non-empty
+        if S >= 1000 * G:
+            rows = np.diff(b)
+            t = rows * spr                                          # predicted time per GPU: equal within a tile row
+            assert (t.max() - t.min()) / t.mean() < 2 * 16 * G / S + 1e-9
+            assert all(v % 16 == 0 for v in b[1:-1])
+    assert balanced_row_bounds(64, [1, 1]) == [0, 32, 64]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
