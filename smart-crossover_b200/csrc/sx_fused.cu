@@ -461,13 +461,7 @@ extern "C" int sx_price_dense_ot_fused(const double *M, int64_t ld, int64_t row0
     long long grid = (long long)num_sms() * occ_cached[dev];
     if (grid > total) grid = total;
     void *args[] = {(void *)&map, (void *)&p, (void *)&f};
-    static int coop = -1;
-    if (coop < 0) { const char *e = getenv("SX_FUSED_COOP"); coop = (e && e[0] == '0') ? 0 : 1; }
-    if (coop) {
-        SX_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)grid), dim3(threads), args, smem, st));
-    } else {
-        // experiment only: plain launch; the grid barriers then rely on nothing else occupying the device
-        SX_CUDA(cudaLaunchKernel((void *)kern, dim3((unsigned)grid), dim3(threads), args, smem, st));
-    }
+    // cooperative: the grid-wide barriers need every CTA resident (a plain launch measured the same speed)
+    SX_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3((unsigned)grid), dim3(threads), args, smem, st));
     return SX_OK;
 }

@@ -70,10 +70,18 @@ __device__ __forceinline__ unsigned long long kr_ld(const unsigned long long *q)
     return SINGLE ? *reinterpret_cast<const volatile unsigned long long *>(q) : __ldcg(q);
 }
 
+// The two survivor lists (position in the order + the roots found for its ends) of a run.
+struct KrLists {
+    uint32_t *q[2];
+    int2     *roots[2];
+    long long cap;
+};
+
 // `ctr`: [0] tree count, [1], [2] survivor counts of the two lists (shared memory when SINGLE).
-template <bool SINGLE>
+// LSMEM: the survivor lists live in shared memory too (plain loads).
+template <bool SINGLE, bool LSMEM>
 __device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, unsigned long long *best,
-                                             unsigned long long *ctr) {
+                                             unsigned long long *ctr, const KrLists &L) {
     GridBarrier *bar = reinterpret_cast<GridBarrier *>(p.ctr + 4);
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gsz  = (long long)gridDim.x * blockDim.x;
@@ -82,7 +90,7 @@ __device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, uns
 
     long long pos = 0;
     long long csize = p.first_chunk;
-    if (csize > p.list_cap) csize = p.list_cap;
+    if (csize > L.cap) csize = L.cap;
     unsigned long long epoch = 0;
     const unsigned long long want = (unsigned long long)(p.N - 1);
     bool done = false;
@@ -96,6 +104,9 @@ __device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, uns
             ++epoch;
             const unsigned long long tag = (kEpochMax - epoch) << 40;
             const int nxt = cur ^ 1;
+            // (selected without indexing the pointer tables, which would put them in local memory)
+            uint32_t *q_cur = cur ? L.q[1] : L.q[0], *q_nxt = cur ? L.q[0] : L.q[1];
+            int2 *r_cur = cur ? L.roots[1] : L.roots[0], *r_nxt = cur ? L.roots[0] : L.roots[1];
             const long long cnt_in = first ? (cend - pos) : (long long)kr_ld<SINGLE>(&ctr[1 + cur]);
             // ---- phase A: filter + propose ----
             for (long long base = (long long)blockIdx.x * blockDim.x; base < cnt_in; base += gsz) {
@@ -104,9 +115,17 @@ __device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, uns
                 uint32_t q = 0;
                 int ru = 0, rv = 0;
                 if (idx < cnt_in) {
-                    q = first ? (uint32_t)(pos + idx) : __ldcg(&p.list[cur][idx]);
                     int u, v;
-                    kr_endpoints(p, p.korder[q], u, v);
+                    if (first) {
+                        q = (uint32_t)(pos + idx);
+                        kr_endpoints(p, p.korder[q], u, v);
+                    } else {
+                        // a survivor: continue from the roots found last round (same components, no second
+                        // trip to the order and the arc's end points)
+                        q = LSMEM ? q_cur[idx] : __ldcg(&q_cur[idx]);
+                        const int2 r = LSMEM ? r_cur[idx] : __ldcg(&r_cur[idx]);
+                        u = r.x; v = r.y;
+                    }
                     ru = kr_find<SINGLE>(parent, u);
                     rv = kr_find<SINGLE>(parent, v);
                     alive = ru != rv;
@@ -119,8 +138,8 @@ __device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, uns
                     slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(m) - 1);
                     if (alive) {
                         const long long slot = (long long)slot0 + __popc(m & ((1u << lane_id()) - 1u));
-                        p.list[nxt][slot]  = q;
-                        p.roots[nxt][slot] = make_int2(ru, rv);
+                        q_nxt[slot] = q;
+                        r_nxt[slot] = make_int2(ru, rv);
                         atomicMin(&best[ru], tag | q);
                         atomicMin(&best[rv], tag | q);
                     }
@@ -132,8 +151,8 @@ __device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, uns
             // ---- phase B: hook the winners ----
             if (gtid == 0) ctr[1 + cur] = 0;   // becomes the append counter of the next round
             for (long long idx = gtid; idx < alive_n; idx += gsz) {
-                const uint32_t q = __ldcg(&p.list[nxt][idx]);
-                const int2 r = __ldcg(&p.roots[nxt][idx]);
+                const uint32_t q = LSMEM ? q_nxt[idx] : __ldcg(&q_nxt[idx]);
+                const int2 r = LSMEM ? r_nxt[idx] : __ldcg(&r_nxt[idx]);
                 const unsigned long long key = tag | q;
                 const bool su = (SINGLE ? best[r.x] : __ldcg(&best[r.x])) == key;
                 const bool sv = (SINGLE ? best[r.y] : __ldcg(&best[r.y])) == key;
@@ -161,22 +180,36 @@ __device__ __forceinline__ void kruskal_body(const KrParams &p, int *parent, uns
         kr_sync<SINGLE>(bar);
         pos = cend;
         csize *= 2;
-        if (csize > p.list_cap) csize = p.list_cap;
+        if (csize > L.cap) csize = L.cap;
     }
 }
 
-__global__ void __launch_bounds__(kKrThreads) kruskal_kernel(KrParams p) { kruskal_body<false>(p, p.parent, p.best, p.ctr); }
+__global__ void __launch_bounds__(kKrThreads) kruskal_kernel(KrParams p) {
+    const KrLists L{{p.list[0], p.list[1]}, {p.roots[0], p.roots[1]}, p.list_cap};
+    kruskal_body<false, false>(p, p.parent, p.best, p.ctr, L);
+}
 
 constexpr int kKrSmallThreads = 1024;
 constexpr long long kKrSmallN = 16000;      // 12 bytes of shared memory per node
-__global__ void __launch_bounds__(kKrSmallThreads) kruskal_small_kernel(KrParams p) {
+__global__ void __launch_bounds__(kKrSmallThreads) kruskal_small_kernel(KrParams p, long long lists_in_smem) {
     extern __shared__ __align__(16) unsigned char kr_raw[];
     unsigned long long *best = reinterpret_cast<unsigned long long *>(kr_raw);
     int *parent = reinterpret_cast<int *>(kr_raw + (size_t)p.N * sizeof(unsigned long long));
     __shared__ unsigned long long s_ctr[4];
     if (threadIdx.x < 4) s_ctr[threadIdx.x] = 0;
     __syncthreads();
-    kruskal_body<true>(p, parent, best, s_ctr);
+    if (lists_in_smem > 0) {
+        // small forests leave room for the survivor lists as well: a round then touches global memory only for the
+        // first visit of an arc and for the tree arcs it records
+        unsigned char *base = kr_raw + (((size_t)p.N * 12 + 15) & ~(size_t)15);
+        int2 *r0 = reinterpret_cast<int2 *>(base), *r1 = r0 + lists_in_smem;
+        uint32_t *q0 = reinterpret_cast<uint32_t *>(r1 + lists_in_smem), *q1 = q0 + lists_in_smem;
+        const KrLists L{{q0, q1}, {r0, r1}, lists_in_smem};
+        kruskal_body<true, true>(p, parent, best, s_ctr, L);
+    } else {
+        const KrLists L{{p.list[0], p.list[1]}, {p.roots[0], p.roots[1]}, p.list_cap};
+        kruskal_body<true, false>(p, parent, best, s_ctr, L);
+    }
     __syncthreads();
     if (threadIdx.x == 0) p.ctr[0] = s_ctr[0];          // read by kr_count_kernel
 }
@@ -259,9 +292,15 @@ extern "C" int sx_kruskal(const uint32_t *korder, int64_t n, const int32_t *tail
     kr_fill_kernel<<<(int)((tcap + 8 + 255) / 256), 256, 0, st>>>(raw_tree, tcap, p.ctr);
     SX_LAUNCH_CHECK();
     if (n > 0 && tcap > 0 && N <= kKrSmallN) {
-        const size_t smem = (size_t)N * 12 + 16;
-        SX_CUDA(cudaFuncSetAttribute(kruskal_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kKrSmallN * 12 + 16)));
-        kruskal_small_kernel<<<1, kKrSmallThreads, smem, st>>>(p);
+        // shared memory: 12 bytes per node, and -- when at least 4 096 survivors fit beside them -- both lists
+        constexpr size_t kBudget = 200 * 1024;
+        const size_t forest = (((size_t)N * 12 + 15) & ~(size_t)15) + 16;
+        long long lists = forest < kBudget ? (long long)((kBudget - forest) / 24) : 0;
+        if (lists < 4096) lists = 0;
+        if (lists > p.list_cap) lists = p.list_cap;
+        const size_t smem = forest + (size_t)lists * 24;
+        SX_CUDA(cudaFuncSetAttribute(kruskal_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBudget + 1024));
+        kruskal_small_kernel<<<1, kKrSmallThreads, smem, st>>>(p, lists);
         SX_LAUNCH_CHECK();
     } else if (n > 0 && tcap > 0) {
         int dev = 0, sms = 0, per_sm = 0;
