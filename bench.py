@@ -324,7 +324,8 @@ def time_tree_build(S, D, device, reps=3, cpu=None, call_host=False):
         ev[1].record()
         order, skey = dev.argsort_f64(F)
         ev[2].record()
-        korder = dev.kruskal_order_head(skey, order, 16 * N)     # as tree_BI does when the sort exists
+        from smart_crossover.network_methods.tree_BI import PREFIX_MIN_ARCS
+        korder = dev.kruskal_order_head(skey, order, 16 * N) if S * D >= PREFIX_MIN_ARCS else None   # as tree_BI does
         if korder is None:
             korder = dev.kruskal_order(skey, order)
         ev[3].record()
@@ -810,9 +811,13 @@ def pricing_leg(args, S, D, ctx, steps, warmup, sampler, want_cpu, want_cold):
         spr[rank] = float(np.median(ts)) / S_loc
         dist.all_reduce(spr, op=dist.ReduceOp.SUM)
         spr = spr.cpu().numpy()
-        new_bounds = balanced_row_bounds(S, spr)
+        # time ~ rows only holds when the phase is long against its fixed ramp-up / drain (~6 us) and its
+        # run-to-run noise: below 200 us per pass the calibration would mostly redistribute noise
+        long_enough = float(np.min(spr * S / world)) >= 200.0
+        new_bounds = balanced_row_bounds(S, spr) if long_enough else row_bounds
         balance = {"us_per_1000_rows_equal_partition": [round(float(v) * 1e3, 3) for v in spr],
-                   "rows_per_gpu": [new_bounds[g + 1] - new_bounds[g] for g in range(world)]}
+                   "rows_per_gpu": [new_bounds[g + 1] - new_bounds[g] for g in range(world)],
+                   "applied": long_enough}
         if new_bounds != row_bounds:
             del sp, M_loc
             torch.cuda.empty_cache()

@@ -79,8 +79,9 @@ def _device_tree(ot: OptTransport, flow_weights: np.ndarray, _sorted: _SortedFlo
         _sorted = _SortedFlows(_cuda(flow_weights), flow_weights)
         if bool(_sorted.sorted_key[-1:].isnan().item()):
             raise ValueError(nan_msg)
-    if n > 4 * PREFIX_FACTOR * N:
-        # the sort exists: only its heaviest 16 N arcs are put into Kruskal order first
+    if n >= PREFIX_MIN_ARCS and n > 4 * PREFIX_FACTOR * N:
+        # the sort exists: only its heaviest 16 N arcs are put into Kruskal order first (one host round trip for
+        # the start of the tie run; below ~2 M arcs flipping everything costs less than that round trip)
         head = _sorted.kruskal_order_head(PREFIX_FACTOR * N)
         if head is not None:
             tree_t, n_t = dev.kruskal(head, N, S=S, D=D)
