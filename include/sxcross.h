@@ -117,8 +117,8 @@ SX_API int    sx_score_mcf(const double *x, const double *u, const int32_t *tail
  * sx_kruskal_order:      descending key, ties by ASCENDING id = stable argsort of -key, the
  *   order SciPy's Kruskal visits arcs in (tree_BI.py:47,53).
  */
-SX_API int    sx_sort_set_tuning(int downsweep_threads);   /* 256, 384 (default), 512 or 1024 threads per tile of the large-input
-                                                              downsweep; 0 / 1: mid-size inputs as launches per pass / as ONE
+SX_API int    sx_sort_set_tuning(int downsweep_threads);   /* 256, 384, 512 or 1024 threads per tile of the large-input
+                                                              downsweep, 2 = chosen by size (default: 1024 from 2^26 keys); 0 / 1: mid-size inputs as launches per pass / as ONE
                                                               cooperative launch (default).  Process-wide, for bench sweeps */
 SX_API size_t sx_argsort_workspace_bytes(int64_t n);
 SX_API int    sx_argsort_f64(const double *key, int64_t n, uint32_t *order_asc_out,

@@ -263,12 +263,11 @@ __device__ __forceinline__ void rs_rank_tile(RsSmem<THREADS> &sm, const unsigned
     __syncthreads();
 }
 
-// Exchange through shared memory (keys grouped by digit, stable) and run-coalesced scatter to the tile's
-// global positions sm.digit_base[d] + (index within the tile's digit run).
-template <int THREADS, bool LAST_F64>
-__device__ __forceinline__ void rs_scatter_tile(RsSmem<THREADS> &sm, const unsigned long long (&key)[kRsItems],
-                                                const uint32_t (&val)[kRsItems], const uint32_t (&rank)[kRsItems],
-                                                int shift, long long valid, const RsDst &dst) {
+// Exchange through shared memory: the tile's keys grouped by digit, stable.
+template <int THREADS>
+__device__ __forceinline__ void rs_exchange_tile(RsSmem<THREADS> &sm, const unsigned long long (&key)[kRsItems],
+                                                 const uint32_t (&val)[kRsItems], const uint32_t (&rank)[kRsItems],
+                                                 int shift) {
     const int warp = threadIdx.x >> 5;
 #pragma unroll
     for (int r = 0; r < kRsItems; ++r) {
@@ -277,7 +276,12 @@ __device__ __forceinline__ void rs_scatter_tile(RsSmem<THREADS> &sm, const unsig
         sm.keys[pos] = key[r];
         sm.vals[pos] = val[r];
     }
-    __syncthreads();
+}
+
+// Run-coalesced scatter of the exchanged tile to its global positions sm.digit_base[d] + (index within the tile's
+// digit run).
+template <int THREADS, bool LAST_F64>
+__device__ __forceinline__ void rs_writeout_tile(RsSmem<THREADS> &sm, int shift, long long valid, const RsDst &dst) {
 #pragma unroll
     for (int k = 0; k < kRsItems; ++k) {
         const int i = threadIdx.x + k * THREADS;
@@ -295,11 +299,20 @@ __device__ __forceinline__ void rs_scatter_tile(RsSmem<THREADS> &sm, const unsig
     }
 }
 
-// 384 threads x 3 CTAs/SM (56 registers, 51 KB of shared memory) is the shipped shape: 5.5 % faster than
-// 512 x 2 at 2.7e8 keys (25.7 vs 27.2 ms) -- a third CTA hides more of the key-load latency at the top of a
-// tile, which ncu's source view shows as 25 % of all stall samples.
+template <int THREADS, bool LAST_F64>
+__device__ __forceinline__ void rs_scatter_tile(RsSmem<THREADS> &sm, const unsigned long long (&key)[kRsItems],
+                                                const uint32_t (&val)[kRsItems], const uint32_t (&rank)[kRsItems],
+                                                int shift, long long valid, const RsDst &dst) {
+    rs_exchange_tile<THREADS>(sm, key, val, rank, shift);
+    __syncthreads();
+    rs_writeout_tile<THREADS, LAST_F64>(sm, shift, valid, dst);
+}
+
+// The tile loop is software pipelined (below).  Shapes measured with the pipelined loop at 4e8 keys: 1024 threads
+// x 1 CTA/SM 28.9 ms, 512 x 2 32.7, 384 x 3 38.5 (56 registers leave no room to hold the prefetched tile), 256 x 4
+// 43.5; before pipelining 512 x 2 took 39.8 ms on the same box class.
 template <int THREADS, int SRC, bool LAST_F64>
-__global__ void __launch_bounds__(THREADS, THREADS == 384 ? 3 : 1)
+__global__ void __launch_bounds__(THREADS, THREADS == 384 ? 3 : (THREADS == 512 ? 2 : (THREADS == 256 ? 4 : 1)))
 rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tiles_per_block,
                     const uint32_t *hist, int grid) {
     extern __shared__ __align__(16) unsigned char rs_raw[];
@@ -308,16 +321,19 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
     const int warp = threadIdx.x >> 5, lane = lane_id();
     if (threadIdx.x < 256) sm.digit_base[threadIdx.x] = hist[(size_t)threadIdx.x * grid + blockIdx.x];
 
+    // Software pipeline over the CTA's tiles: once a tile's keys sit in the shared-memory exchange, its registers
+    // are free, so the NEXT tile's keys are requested before the write-out of this one -- the load latency at the
+    // top of a tile was 25 % of all stall samples (ncu source view).
     const long long tile0 = (long long)blockIdx.x * tiles_per_block;
-    for (long long tl = tile0; tl < tile0 + tiles_per_block; ++tl) {
+    long long tile_end = tile0 + tiles_per_block;
+    if (tile_end * kTile > n) tile_end = (n + kTile - 1) / kTile;
+    if (tile0 >= tile_end) return;
+    const int li0 = warp * (32 * kRsItems) + lane;
+    unsigned long long key[kRsItems];
+    uint32_t           val[kRsItems];
+    auto load_tile = [&](long long tl) {
         const long long tbase = tl * kTile;
-        if (tbase >= n) break;
         const long long valid = (n - tbase < kTile) ? (n - tbase) : kTile;
-        // zero the per-warp counters
-        for (int i = threadIdx.x; i < kWarps * 256; i += THREADS) (&sm.cnt[0][0])[i] = 0;
-        unsigned long long key[kRsItems];
-        uint32_t           val[kRsItems];
-        const int li0 = warp * (32 * kRsItems) + lane;
         if (valid == kTile) {                                    // every tile but the last: no bounds checks
 #pragma unroll
             for (int r = 0; r < kRsItems; ++r) {
@@ -339,10 +355,21 @@ rs_downsweep_kernel(RsSrc src, RsDst dst, long long n, int shift, long long tile
                 }
             }
         }
-        __syncthreads();
+    };
+    for (int i = threadIdx.x; i < kWarps * 256; i += THREADS) (&sm.cnt[0][0])[i] = 0;
+    load_tile(tile0);
+    __syncthreads();
+    for (long long tl = tile0; tl < tile_end; ++tl) {
+        const long long tbase = tl * kTile;
+        const long long valid = (n - tbase < kTile) ? (n - tbase) : kTile;
         uint32_t rank[kRsItems];
         rs_rank_tile<THREADS>(sm, key, shift, rank);
-        rs_scatter_tile<THREADS, LAST_F64>(sm, key, val, rank, shift, valid, dst);
+        rs_exchange_tile<THREADS>(sm, key, val, rank, shift);
+        __syncthreads();
+        // key / val / rank are dead, the counters have been read: fetch the next tile and clear the counters for it
+        if (tl + 1 < tile_end) load_tile(tl + 1);
+        for (int i = threadIdx.x; i < kWarps * 256; i += THREADS) (&sm.cnt[0][0])[i] = 0;
+        rs_writeout_tile<THREADS, LAST_F64>(sm, shift, valid, dst);
         __syncthreads();
         if (threadIdx.x < 256) sm.digit_base[threadIdx.x] += sm.tile_cnt[threadIdx.x];
     }
@@ -526,17 +553,20 @@ struct RsPlan {
     long long tiles, tiles_per_block;
     int       grid, threads;
 };
-static int g_rs_threads = 384;
+static int g_rs_threads = 0;    // 0 = by size: 1024-thread tiles from 2^26 keys up, 512 below (sx_sort_set_tuning overrides)
 static int g_rs_coop = 1;      // mid-size inputs take the single cooperative launch (sx_sort_set_tuning(0 / 1) switches it)
 static RsPlan rs_plan(long long n) {
     RsPlan p;
-    p.threads = g_rs_threads;
+    // 8192-key tiles (1024 threads, one CTA per SM) win on large inputs: half the barriers per key and twice as
+    // long runs in the scatter (28.9 vs 32.7 ms at 4e8 keys, 7.8 vs 8.6 at 1e8); 512 x 2 CTAs/SM wins below
+    // (1.08 vs 1.31 ms at 1e7, where a pass is latency bound)
+    p.threads = g_rs_threads ? g_rs_threads : (n >= (1ll << 26) ? 1024 : 512);
     const long long tile = (long long)p.threads * kRsItems;
     p.tiles = (n + tile - 1) / tile;
     if (p.tiles < 1) p.tiles = 1;
     // One wave of downsweep CTAs (2 per SM) is enough up to ~64 M keys and keeps the (256 x grid) counter table --
     // which a single CTA scans between the sweeps -- small: 31 -> ~10 us per pass at 10 M keys.
-    long long max_grid = n < (1ll << 26) ? 2ll * num_sms() : kRsMaxGrid;
+    long long max_grid = n < (1ll << 26) ? (p.threads == 1024 ? 1ll : 2ll) * num_sms() : kRsMaxGrid;
     if (max_grid > kRsMaxGrid) max_grid = kRsMaxGrid;
     p.tiles_per_block = (p.tiles + max_grid - 1) / max_grid;
     p.grid = (int)((p.tiles + p.tiles_per_block - 1) / p.tiles_per_block);
@@ -853,6 +883,7 @@ using namespace sx;
 
 extern "C" int sx_sort_set_tuning(int downsweep_threads) {
     if (downsweep_threads == 0 || downsweep_threads == 1) { g_rs_coop = downsweep_threads; return SX_OK; }
+    if (downsweep_threads == 2) { g_rs_threads = 0; return SX_OK; }        // back to the size-based choice
     if (downsweep_threads != 256 && downsweep_threads != 384 && downsweep_threads != 512 && downsweep_threads != 1024) return SX_ERR_INVALID;
     g_rs_threads = downsweep_threads;
     return SX_OK;

@@ -148,7 +148,7 @@ def sort_mode(request):
     from smart_crossover._native import lib
     assert lib.sx_sort_set_tuning(1 if request.param == "one launch" else 0) == 0
     yield request.param
-    assert lib.sx_sort_set_tuning(1) == 0
+    assert lib.sx_sort_set_tuning(1) == 0 and lib.sx_sort_set_tuning(2) == 0
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 8192, 8193, 70001, 614656, 1 << 20, 1212416, 1212417])
@@ -929,9 +929,20 @@ def test_kruskal_prefix_large_properties(dev):
     assert float(w[rest].max()) < float(hw[-1])
 
 
-def test_large_sort_properties(dev):
-    """2^25 keys: output is a permutation, keys non-decreasing, ties in ascending id."""
-    n = 1 << 25
+@pytest.mark.parametrize("threads,n", [(2, 1 << 25), (1024, (1 << 25) + 12345), (512, 3_000_001), (1024, 3_000_001),
+                                       (256, 1_300_000), (384, 1_300_000)])
+def test_large_sort_properties(dev, threads, n):
+    """Output is a permutation, keys non-decreasing, ties in ascending id -- for every downsweep tile shape
+    (`threads`; 2 = chosen by size; 1024 is what inputs of 2^26 keys and more take), partial last tiles included."""
+    from smart_crossover._native import lib
+    assert lib.sx_sort_set_tuning(threads) == 0 and lib.sx_sort_set_tuning(0) == 0     # launches per pass
+    try:
+        _large_sort_properties(dev, n)
+    finally:
+        assert lib.sx_sort_set_tuning(2) == 0 and lib.sx_sort_set_tuning(1) == 0
+
+
+def _large_sort_properties(dev, n):
     g = torch.Generator(device="cuda").manual_seed(7)
     key = torch.randint(0, 1 << 20, (n,), generator=g, device="cuda").to(torch.float64) / 1024.0
     order, skey = dev.argsort_f64(key)

@@ -31,4 +31,4 @@ for codes in [a.split(",") for a in sys.argv[2:]] or [["512"]]:
         ref = order.clone()
     same = bool((order == ref).all())
     print(f"n={n} tuning={'+'.join(codes)}: {best:.3f} ms ({n / best / 1e6:.2f} Gkeys/s) same_order_as_first={same}", flush=True)
-lib.sx_sort_set_tuning(384)
+lib.sx_sort_set_tuning(2)
