@@ -13,7 +13,12 @@
  *  - Every function returns 0 (SX_OK) or a negative SX_ERR_* code; nothing throws.
  *  - Pointers are DEVICE pointers owned by the caller unless the parameter name ends
  *    in `_h` (host pointer).  No hidden allocation: `sx_*_workspace_bytes` reports the
- *    scratch a call needs and the caller passes `ws` / `ws_bytes`.
+ *    scratch a call needs and the caller passes `ws` / `ws_bytes`.  The one exception is
+ *    the opaque handle sx_ot_pricer, which owns its buffers from create to destroy.
+ *  - No per-call state lives in the library.  The `sx_*_set_tuning` functions set
+ *    PROCESS-WIDE defaults (kernel shapes) for bench sweeps and tests; the product path
+ *    never calls them and they are not meant to be changed while another thread is
+ *    inside the library.
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous with respect
  *    to the host and ordered by that stream, except the `_h` entry points, which
  *    synchronise the stream before returning.
