@@ -663,7 +663,7 @@ def main():
                        "fused": L["fused"], "row_partition": L["balance"] or "equal shares",
                        "l2": f"inputs larger than L2 ({8 * L['S_loc'] * D / 1e9:.1f} GB per GPU vs 126 MB), no flush needed"},
             "roofline": roofline_of(L), "cpu_baseline": L["cpu_baseline"],
-            "e2e": main_mgr if main_mgr is not None else L["e2e"],
+            "e2e": main_mgr if main_mgr is not None else L["e2e"], "e2e_manager_error": L.get("manager_error"),
             "e2e_one_process_per_gpu": L["e2e"], "e2e_pinned": L["e2e_pinned"],
             "topk_digest": L["topk_digest"], "merge_check": L["merge_check"],
             "stage_us_rank0": L["stage_us"], "e2e_cold": L["e2e_cold"], "gpu_launches": L["gpu_launches"],
@@ -694,49 +694,59 @@ def manager_leg(args, S, D, ctx, steps, leg):
     out = None
     ctx["host_barrier"]()
     if rank == 0 and not args.no_manager:
-        from smart_crossover import device as dev
-        from smart_crossover.network_methods.net_manager import OTManager
-        K = args.topk
-        devices = [(ctx["local"] + i) % torch.cuda.device_count() for i in range(world)]
-        slabs = dev.CostSlabs(S, D, devices, leg["row_bounds"])
-        for g, d in enumerate(devices):
-            with torch.cuda.device(d):
-                P, Q, a = make_points(S, D, torch.device("cuda", d))
-                make_slab(P, Q, slabs.row0[g], slabs.rows[g], out=slabs.view(g))
-                del P, Q, a
-        slabs.sync()
-        mgr = OTManager.from_device_cost(np.full(S, 1.0 / S), np.full(D, 1.0 / D), slabs)
-        y = np.array(leg["y_host"], copy=True)               # pageable, as a solver hands it over
-        for _ in range(3):
-            res = mgr.price(y, K=K)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            res = mgr.price(y, K=K)
-        dt = time.perf_counter() - t0
-        assert topk_digest(res.topk_id, res.topk_rc, res.n_violating, res.min_rc) == leg["topk_digest"], \
-            "OTManager.price disagrees with the device-timed arm"
-        for _ in range(3):
-            opt = mgr.check_optimality_condition(None, y)
-        t1 = time.perf_counter()
-        for _ in range(steps):
-            opt = mgr.check_optimality_condition(None, y)
-        dt0 = time.perf_counter() - t1
-        assert opt == (leg["violating_arcs"] == 0)
-        st = mgr._pricer(K).stats()
-        G = len(devices)
-        blk = 2 * max(K, 1) + 6
-        out = {"value": S * D * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps,
-               "h2d_bytes_per_step": 8 * (S + G * D), "d2h_bytes_per_step": 8 * blk * G,
-               "call": "OTManager.price(y, K) -- one process drives all GPUs (sx_ot_pricer)",
-               "check_optimality_condition_ms": 1e3 * dt0 / steps,
-               "devices": devices, "fused": st["fused"], "merge_in_kernel": st["merge_in_kernel"],
-               "repeated_passes": st["repeated_passes"], "timer": "host wall clock around the blocking calls",
-               "inputs": "duals y in a pageable NumPy vector every step; each GPU's worker thread stages its "
-                         "S_loc + D entries in pinned memory and uploads them; merged result read back; cost "
-                         "matrix resident (uploaded / generated once per problem)"}
-        mgr._drop_device_state()
-        del mgr, slabs
-        torch.cuda.empty_cache()
+        try:
+            from smart_crossover import device as dev
+            from smart_crossover.network_methods.net_manager import OTManager
+            K = args.topk
+            devices = [(ctx["local"] + i) % torch.cuda.device_count() for i in range(world)]
+            slabs = dev.CostSlabs(S, D, devices, leg["row_bounds"])
+            for g, d in enumerate(devices):
+                with torch.cuda.device(d):
+                    P, Q, a = make_points(S, D, torch.device("cuda", d))
+                    make_slab(P, Q, slabs.row0[g], slabs.rows[g], out=slabs.view(g))
+                    del P, Q, a
+            slabs.sync()
+            mgr = OTManager.from_device_cost(np.full(S, 1.0 / S), np.full(D, 1.0 / D), slabs)
+            y = np.array(leg["y_host"], copy=True)               # pageable, as a solver hands it over
+            for _ in range(3):
+                res = mgr.price(y, K=K)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                res = mgr.price(y, K=K)
+            dt = time.perf_counter() - t0
+            assert topk_digest(res.topk_id, res.topk_rc, res.n_violating, res.min_rc) == leg["topk_digest"], \
+                "OTManager.price disagrees with the device-timed arm"
+            for _ in range(3):
+                opt = mgr.check_optimality_condition(None, y)
+            t1 = time.perf_counter()
+            for _ in range(steps):
+                opt = mgr.check_optimality_condition(None, y)
+            dt0 = time.perf_counter() - t1
+            assert opt == (leg["violating_arcs"] == 0)
+            st = mgr._pricer(K).stats()
+            G = len(devices)
+            blk = 2 * max(K, 1) + 6
+            out = {"value": S * D * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps,
+                   "h2d_bytes_per_step": 8 * (S + G * D), "d2h_bytes_per_step": 8 * blk * G,
+                   "call": "OTManager.price(y, K) -- one process drives all GPUs (sx_ot_pricer)",
+                   "check_optimality_condition_ms": 1e3 * dt0 / steps,
+                   "devices": devices, "fused": st["fused"], "merge_in_kernel": st["merge_in_kernel"],
+                   "repeated_passes": st["repeated_passes"], "timer": "host wall clock around the blocking calls",
+                   "inputs": "duals y in a pageable NumPy vector every step; each GPU's worker thread stages its "
+                             "S_loc + D entries in pinned memory and uploads them; merged result read back; cost "
+                             "matrix resident (uploaded / generated once per problem)"}
+            mgr._drop_device_state()
+            del mgr, slabs
+            torch.cuda.empty_cache()
+        except AssertionError:                       # a wrong result is never swallowed
+            raise
+        except Exception as exc:                     # e.g. no peer access between the GPUs of this box: say so and
+            out = None                               # let the line fall back to the one-process-per-GPU number
+            leg["manager_error"] = f"{type(exc).__name__}: {exc}"
+            try:
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
     ctx["host_barrier"]()
     return out
 
