@@ -438,8 +438,6 @@ rs_small_sort_kernel(RsSrc src, int n, int passes, uint32_t *order_out, double *
 // derives its own digit bases (digits before mine over all tiles + my digit over earlier tiles), scatter, grid
 // barrier.  16 barriers instead of 24 launches: the 614 656 keys of a 784 x 784 instance are launch-latency
 // bound (0.25 ms for ~2 us of memory traffic per pass).
-constexpr int kCoopThreads = 512;
-constexpr int kCoopTile = kCoopThreads * kRsItems;
 
 struct RsCoop {
     const double *key_f64;                 // first pass source (one of the two)
@@ -455,11 +453,15 @@ struct RsCoop {
     unsigned long long *sorted_u64;
 };
 
-template <bool F64>
-__global__ void __launch_bounds__(kCoopThreads, 2) rs_coop_sort_kernel(RsCoop c) {
+// kCoopThreads = 512 (4 096-key tiles, two CTAs per SM) or 1 024 (8 192-key tiles, one per SM: half as many
+// arrivals at the barriers and rows in the table -- taken from 64 tiles up).
+template <bool F64, int kCoopThreads>
+__global__ void __launch_bounds__(kCoopThreads, kCoopThreads == 512 ? 2 : 1) rs_coop_sort_kernel(RsCoop c) {
+    constexpr int kCoopTile = kCoopThreads * kRsItems;
     extern __shared__ __align__(16) unsigned char rs_raw[];
     RsSmem<kCoopThreads> &sm = *reinterpret_cast<RsSmem<kCoopThreads> *>(rs_raw);
     constexpr int kWarps = kCoopThreads / 32;
+    constexpr int kPartHalf = (kCoopThreads / 64) * 256;            // uint32 words of one half of the partial-sum scratch
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int grid = gridDim.x;
     const long long tbase = (long long)blockIdx.x * kCoopTile;
@@ -518,14 +520,14 @@ __global__ void __launch_bounds__(kCoopThreads, 2) rs_coop_sort_kernel(RsCoop c)
             // partial sums of the 8 groups: sm.keys (free until the scatter) as 2 x 8 x 256 uint32
             uint32_t *part = reinterpret_cast<uint32_t *>(sm.keys);
             reinterpret_cast<uint4 *>(part + g * 256)[q] = tot;
-            reinterpret_cast<uint4 *>(part + 2048 + g * 256)[q] = pre;
+            reinterpret_cast<uint4 *>(part + kPartHalf + g * 256)[q] = pre;
         }
         __syncthreads();
         if (threadIdx.x < 256) {
             const uint32_t *part = reinterpret_cast<const uint32_t *>(sm.keys);
             uint32_t tot = 0, pre = 0;
 #pragma unroll
-            for (int g = 0; g < kCoopThreads / 64; ++g) { tot += part[g * 256 + threadIdx.x]; pre += part[2048 + g * 256 + threadIdx.x]; }
+            for (int g = 0; g < kCoopThreads / 64; ++g) { tot += part[g * 256 + threadIdx.x]; pre += part[kPartHalf + g * 256 + threadIdx.x]; }
             uint32_t incl = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -632,25 +634,37 @@ static int rs_sort(const double *key_f64, const unsigned long long *key_u64, lon
     const bool f64 = key_f64 != nullptr;
     {
         // mid-size: one tile per CTA, all passes in one cooperative launch, if every tile can be resident
-        const long long tiles = (n + kCoopTile - 1) / kCoopTile;
-        static int coop_max[64] = {0};
+        static int coop_max[64][2] = {};                       // [device][0: 512-thread CTAs, 1: 1024-thread CTAs]
         int dev = 0;
         SX_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && coop_max[dev] == 0) {
-            int occ_a = 0, occ_b = 0;
-            SX_CUDA(cudaFuncSetAttribute(rs_coop_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<kCoopThreads>)));
-            SX_CUDA(cudaFuncSetAttribute(rs_coop_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem<kCoopThreads>)));
-            SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, rs_coop_sort_kernel<true>, kCoopThreads, sizeof(RsSmem<kCoopThreads>)));
-            SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, rs_coop_sort_kernel<false>, kCoopThreads, sizeof(RsSmem<kCoopThreads>)));
-            const int occ = occ_a < occ_b ? occ_a : occ_b;
-            coop_max[dev] = occ > 0 ? occ * num_sms() : -1;
+        if (dev >= 0 && dev < 64 && coop_max[dev][0] == 0) {
+            auto probe = [&](auto ka, auto kb, int threads, size_t smem, int &out) -> int {
+                int occ_a = 0, occ_b = 0;
+                SX_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SX_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, ka, threads, smem));
+                SX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, kb, threads, smem));
+                const int occ = occ_a < occ_b ? occ_a : occ_b;
+                out = occ > 0 ? occ * num_sms() : -1;
+                return SX_OK;
+            };
+            int rc = probe(rs_coop_sort_kernel<true, 512>, rs_coop_sort_kernel<false, 512>, 512, sizeof(RsSmem<512>), coop_max[dev][0]);
+            if (rc != SX_OK) return rc;
+            rc = probe(rs_coop_sort_kernel<true, 1024>, rs_coop_sort_kernel<false, 1024>, 1024, sizeof(RsSmem<1024>), coop_max[dev][1]);
+            if (rc != SX_OK) return rc;
         }
-        if (dev >= 0 && dev < 64 && g_rs_coop && tiles <= coop_max[dev] && tiles <= kRsMaxGrid) {
+        const long long tiles512 = (n + 512 * kRsItems - 1) / (512 * kRsItems);
+        const int big = tiles512 > 64 ? 1 : 0;
+        const int threads = big ? 1024 : 512;
+        const long long tiles = (n + (long long)threads * kRsItems - 1) / ((long long)threads * kRsItems);
+        if (dev >= 0 && dev < 64 && g_rs_coop && tiles <= coop_max[dev][big] && tiles <= kRsMaxGrid) {
             RsCoop c{key_f64, key_u64, {kbuf[0], kbuf[1]}, {vbuf[0], vbuf[1]}, hist, bar, n, passes, order_out, sorted_f64, sorted_u64};
             SX_CUDA(cudaMemsetAsync(bar, 0, sizeof(GridBarrier), st));
             void *args[] = {(void *)&c};
-            void *kern = f64 ? (void *)rs_coop_sort_kernel<true> : (void *)rs_coop_sort_kernel<false>;
-            SX_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)tiles), dim3(kCoopThreads), args, sizeof(RsSmem<kCoopThreads>), st));
+            void *kern = big ? (f64 ? (void *)rs_coop_sort_kernel<true, 1024> : (void *)rs_coop_sort_kernel<false, 1024>)
+                             : (f64 ? (void *)rs_coop_sort_kernel<true, 512> : (void *)rs_coop_sort_kernel<false, 512>);
+            const size_t smem = big ? sizeof(RsSmem<1024>) : sizeof(RsSmem<512>);
+            SX_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)tiles), dim3(threads), args, smem, st));
             return SX_OK;
         }
     }
