@@ -11,41 +11,100 @@
 //     g_j = reg log b_j - reg LSE_i((f_i - M_ij) / reg)
 //     f_i = reg log a_i - reg LSE_j((g_j - M_ij) / reg)
 //     X_ij = exp((f_i + g_j - M_ij) / reg)
-// HBM-bound streaming passes over M: one per half-iteration (8 B per arc) with an online
-// (running max, scaled sum) log-sum-exp, plus one read + one write for X at the end.
+// Streaming passes over M: one per half-iteration (8 B per arc) with an online (running max, scaled
+// sum) log-sum-exp taken in groups of 8 arcs per thread, plus one read + one write for X at the end.
 // The column-marginal error of POT's test is free: with the new f and the old g the column sums of X
 // are b_j exp((g_old_j - g_new_j) / reg), so the error of iteration k is known during the column pass
 // of iteration k + 1 (the loop then stops with that pass's g, one half-step further than POT).
 #include <math.h>
 
 #include "sx_common.cuh"
+#include "sx_expm.cuh"
 
 namespace sx {
+
+// The two streaming passes were instruction-issue and fp64-pipe bound, not HBM bound (round-2 capture of
+// the first version, profiles/r02_sinkhorn_raw.csv: 84 % issue slots, 91 warp instructions per arc, fp64
+// pipe 52 %, DRAM 33 %): one libm exp per arc plus a second one whenever ANY lane of the warp met a new
+// running maximum.  They now take the arcs in groups of kSkGroup per thread -- loads first (kSkGroup
+// independent 8-byte loads in flight), one shared maximum per group, one rescale of the running sum per
+// group, and the sign-aware 11-operation exp of sx_expm.cuh -- ~17 fp64 operations per arc and no
+// divergent branch.
+constexpr int kSkGroup = 8;
+
+__constant__ double c_exp_tab[kExpTabSize] = {SX_EXP_TAB_VALUES};
+
+__device__ __forceinline__ void load_exp_tab(double *s_tab) {      // all threads of the CTA call this
+    if (threadIdx.x < kExpTabSize) s_tab[threadIdx.x] = c_exp_tab[threadIdx.x];
+    __syncthreads();
+}
 
 struct Lse {          // log-sum-exp accumulator: sum of exp(t_k) = s * exp(m)
     double m, s;
 };
-__device__ __forceinline__ void lse_add(Lse &a, double t) {
-    if (t <= a.m) a.s += exp(t - a.m);
-    else { a.s = a.s * exp(a.m - t) + 1.0; a.m = t; }
+// Accumulation works on the unscaled w_k = potential - cost (t_k = w_k / reg): `wm` is the running
+// maximum of w, acc.m = wm / reg rounded once, and every exponent is fma(w_k, 1 / reg, -acc.m).
+__device__ __forceinline__ void lse_add_group(Lse &a, double &wm, const double (&w)[kSkGroup], double inv,
+                                              const double *tab) {
+    double gm = w[0];
+#pragma unroll
+    for (int k = 1; k < kSkGroup; ++k) gm = w[k] > gm ? w[k] : gm;
+    gm = gm > wm ? gm : wm;
+    if (gm == -INFINITY) return;                      // only masked slots so far
+    const double q = gm * inv;
+    double s = a.s * exp_nonpos(a.m - q, tab);        // a.m = -inf: exp gives 0 (and a.s is 0)
+    const double nq = -q;
+#pragma unroll
+    for (int k = 0; k < kSkGroup; ++k) s += exp_nonpos(fma(w[k], inv, nq), tab);   // masked slots (-inf) add 0
+    wm = gm;
+    a.m = q;
+    a.s = s;
 }
 __device__ __forceinline__ void lse_merge(Lse &a, const Lse &b) {
     if (b.m <= a.m) a.s += b.s * exp(b.m - a.m);
     else { a.s = a.s * exp(a.m - b.m) + b.s; a.m = b.m; }
 }
 
-// f update: one warp per row, lanes stride the columns (coalesced).
+// f update: one warp per row, lanes stride the columns (coalesced), kSkGroup * 32 columns per step.
 __global__ void __launch_bounds__(256)
 sk_row_kernel(const double *__restrict__ M, long long ld, long long S, long long D, const double *__restrict__ g,
               const double *__restrict__ log_a, double reg, double *__restrict__ f) {
+    __shared__ double s_tab[kExpTabSize];
+    load_exp_tab(s_tab);
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = lane_id();
     const double inv = 1.0 / reg;
+    constexpr long long kStep = (long long)kSkGroup * 32;
     for (long long i = warp; i < S; i += n_warps) {
         const double *row = M + i * ld;
         Lse acc{-INFINITY, 0.0};
-        for (long long j = lane; j < D; j += 32) lse_add(acc, (g[j] - __ldcs(row + j)) * inv);
+        double wm = -INFINITY;
+        long long j0 = 0;
+        double nx[kSkGroup];                          // the next group's costs, in flight during this group's math
+        if (kStep <= D) {
+#pragma unroll
+            for (int k = 0; k < kSkGroup; ++k) nx[k] = __ldcs(row + lane + 32 * k);
+        }
+        for (; j0 + kStep <= D; j0 += kStep) {
+            double w[kSkGroup];
+#pragma unroll
+            for (int k = 0; k < kSkGroup; ++k) w[k] = g[j0 + lane + 32 * k] - nx[k];
+            if (j0 + 2 * kStep <= D) {
+#pragma unroll
+                for (int k = 0; k < kSkGroup; ++k) nx[k] = __ldcs(row + j0 + kStep + lane + 32 * k);
+            }
+            lse_add_group(acc, wm, w, inv, s_tab);
+        }
+        if (j0 < D) {
+            double w[kSkGroup];
+#pragma unroll
+            for (int k = 0; k < kSkGroup; ++k) {
+                const long long j = j0 + lane + 32 * k;
+                w[k] = j < D ? g[j] - __ldcs(row + j) : -INFINITY;
+            }
+            lse_add_group(acc, wm, w, inv, s_tab);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             Lse other{__shfl_xor_sync(0xffffffffu, acc.m, o), __shfl_xor_sync(0xffffffffu, acc.s, o)};
@@ -60,13 +119,38 @@ __global__ void __launch_bounds__(256)
 sk_col_partial_kernel(const double *__restrict__ M, long long ld, long long S, long long D,
                       const double *__restrict__ f, double reg, long long rows_per_chunk,
                       double *__restrict__ pm, double *__restrict__ ps) {
+    __shared__ double s_tab[kExpTabSize];
+    load_exp_tab(s_tab);
     const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
     const long long chunk = blockIdx.y;
     const long long i0 = chunk * rows_per_chunk, i1 = i0 + rows_per_chunk < S ? i0 + rows_per_chunk : S;
     if (j >= D) return;
     const double inv = 1.0 / reg;
+    const double *col = M + j;
     Lse acc{-INFINITY, 0.0};
-    for (long long i = i0; i < i1; ++i) lse_add(acc, (f[i] - __ldcs(M + i * ld + j)) * inv);
+    double wm = -INFINITY;
+    long long i = i0;
+    double nx[kSkGroup];                              // the next group's costs, in flight during this group's math
+    if (i + kSkGroup <= i1) {
+#pragma unroll
+        for (int k = 0; k < kSkGroup; ++k) nx[k] = __ldcs(col + (i + k) * ld);
+    }
+    for (; i + kSkGroup <= i1; i += kSkGroup) {
+        double w[kSkGroup];
+#pragma unroll
+        for (int k = 0; k < kSkGroup; ++k) w[k] = f[i + k] - nx[k];
+        if (i + 2 * kSkGroup <= i1) {
+#pragma unroll
+            for (int k = 0; k < kSkGroup; ++k) nx[k] = __ldcs(col + (i + kSkGroup + k) * ld);
+        }
+        lse_add_group(acc, wm, w, inv, s_tab);
+    }
+    if (i < i1) {
+        double w[kSkGroup];
+#pragma unroll
+        for (int k = 0; k < kSkGroup; ++k) w[k] = i + k < i1 ? f[i + k] - __ldcs(col + (i + k) * ld) : -INFINITY;
+        lse_add_group(acc, wm, w, inv, s_tab);
+    }
     pm[chunk * D + j] = acc.m;
     ps[chunk * D + j] = acc.s;
 }
@@ -110,15 +194,16 @@ __global__ void sk_fill_kernel(double *out, long long n, double v) {
         out[i] = v;
 }
 
-// X_ij = exp((f_i + g_j - M_ij) / reg)
+// X_ij = exp((f_i + g_j - M_ij) / reg): a CTA per row (grid-stride), threads stride the columns.
 __global__ void __launch_bounds__(256)
 sk_plan_kernel(const double *__restrict__ M, long long ld, long long S, long long D, const double *__restrict__ f,
                const double *__restrict__ g, double reg, double *__restrict__ X) {
     const double inv = 1.0 / reg;
-    const long long n = S * D;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const long long i = k / D, j = k - i * D;
-        X[k] = exp((f[i] + g[j] - __ldcs(M + i * ld + j)) * inv);
+    for (long long i = blockIdx.x; i < S; i += gridDim.x) {
+        const double fi = f[i];
+        const double *row = M + i * ld;
+        double *out = X + i * D;
+        for (long long j = threadIdx.x; j < D; j += blockDim.x) out[j] = exp((fi + g[j] - __ldcs(row + j)) * inv);
     }
 }
 

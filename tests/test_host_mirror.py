@@ -227,3 +227,36 @@ def test_mcf_manager_bookkeeping():
     mgr.add_free_variables(fx.out["queue"][:10])
     assert np.array_equal(mgr.var_info["non_fix"][-10:], fx.out["queue"][:10])
     assert not np.isin(fx.out["queue"][:10], mgr.var_info["fix"]).any()
+
+
+def test_exp_nonpos_of_the_warm_start_is_within_two_ulp_of_libm(tmp_path):
+    """csrc/sx_expm.cuh is host-compilable: the exponential the Sinkhorn passes use (x <= 0, table + degree-6
+    Taylor) stays within 2 ulp of libm on (-700, 0], is exactly 1 at 0, 0 from -700 down, and passes NaN."""
+    import ctypes
+    import pathlib
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    hdr = pathlib.Path(__file__).resolve().parents[1] / "smart-crossover_b200" / "csrc" / "sx_expm.cuh"
+    src = tmp_path / "expm_shim.cpp"
+    src.write_text(f'#include "{hdr}"\n'
+                   "static const double tab[sx::kExpTabSize] = {SX_EXP_TAB_VALUES};\n"
+                   'extern "C" void expm_eval(const double *x, long n, double *out) {\n'
+                   "    for (long i = 0; i < n; ++i) out[i] = sx::exp_nonpos(x[i], tab);\n}\n")
+    so = tmp_path / "expm_shim.so"
+    subprocess.run(["g++", "-O2", "-mfma", "-x", "c++", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+    fn = ctypes.CDLL(str(so)).expm_eval
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+    rng = np.random.default_rng(5)
+    x = np.concatenate([-700 * rng.random(400000), -5 * rng.random(400000), -60 * rng.random(200000) ** 3,
+                        -np.ldexp(1.0, -np.arange(1, 60)), -np.log(2) / 32 * np.arange(0, 20000)])
+    x = np.ascontiguousarray(x[x > -700.0])
+    out = np.empty_like(x)
+    fn(x.ctypes.data, x.size, out.ctypes.data)
+    ref = np.exp(x)
+    assert np.max(np.abs(out - ref) / ref) < 2 * np.finfo(np.float64).eps
+    edge = np.array([0.0, -0.0, -700.0, -745.2, -1e9, -np.inf, np.nan])
+    got = np.empty_like(edge)
+    fn(edge.ctypes.data, edge.size, got.ctypes.data)
+    assert got[0] == 1.0 and got[1] == 1.0 and np.all(got[2:6] == 0.0) and np.isnan(got[6])
